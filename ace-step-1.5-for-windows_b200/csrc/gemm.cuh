@@ -1,0 +1,299 @@
+// gemm.cuh — the one tensor-core kernel of libacestep_b200.
+//
+// A persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//
+//     D[m, n] = sum_{tap} sum_{k < Kc}  A[m + shift[tap], k] * B[n, tap*Kc + k]      (fp32 in TMEM)
+//
+//   * A  : bf16, row-major [rows_A, Kc] with an arbitrary row pitch (K-major operand).
+//          Rows outside [0, rows_A) read as zero (TMA out-of-bounds fill), which is what makes
+//          the "taps" useful: a 1-D convolution over a channels-last signal is this GEMM with
+//          shift[tap] = (tap - centre) * dilation, a stride-s transposed convolution is the
+//          2-tap case {0, -1}, a plain nn.Linear is the 1-tap case.
+//   * B  : bf16, row-major [N, ntaps*Kc]  (nn.Linear weight layout, K-major operand).
+//   * D  : never stored raw — an epilogue functor consumes the fp32 accumulator rows straight
+//          out of TMEM (tcgen05.ld, one accumulator row per thread) and writes the fused result.
+//
+// Pipeline: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B), warp 1 = single-thread
+// tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.  STAGES-deep smem ring
+// (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Grid = min(#tiles, #SMs).
+//
+// Replaces the cuBLAS calls behind every nn.Linear of the reference DiT layer
+// (acestep/models/turbo/modeling_acestep_v15_turbo.py:276-279, Qwen3MLP) and the cuDNN
+// convolutions of AutoencoderOobleck (structure: acestep/models/mlx/vae_model.py:62-230).
+#pragma once
+
+#include "common.cuh"
+
+namespace ace {
+
+constexpr int GEMM_BM = 128;      // UMMA M (one TMEM lane per accumulator row)
+constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_MAX_TAPS = 8;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmShape {
+  int M, N;             // output extent
+  int kblocks_per_tap;  // Kc / 64
+  int ntaps;
+  int b_tap_stride;     // elements between taps along B's K axis (= Kc)
+  int shift[GEMM_MAX_TAPS];
+};
+
+// Host-side description of one GEMM problem; tensor maps are encoded once (at bind time) so a
+// launch does no host work besides cudaLaunchKernel and the whole step can live in a CUDA graph.
+struct GemmPlan {
+  CUtensorMap tma_a, tma_b;
+  GemmShape shp;
+  const bf16* a_ptr;
+  long a_ld;
+  int a_rows;
+  const bf16* b_ptr;
+  long b_ld;
+  int bn;
+};
+
+// Encodes a 2-D bf16 tensor map (dim0 = contiguous columns) with a [64 x box_rows] box and
+// 128-byte swizzle.  Implemented in runtime.cu (driver entry point looked up at run time).
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
+                   uint64_t row_pitch_bytes, uint32_t box_rows);
+
+int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
+                   int n, long b_ld, int m, int ntaps, const int* shifts, int bn);
+
+// Debug switch (tests only): route launches through the scalar reference kernels below so the
+// epilogues and the surrounding pipeline can be validated independently of the tcgen05 main loop.
+void set_gemm_debug_reference(bool on);
+bool gemm_debug_reference();
+float* gemm_debug_scratch(size_t elems);  // grows a device scratch buffer; nullptr on failure
+int num_sms();
+
+#ifdef __CUDACC__
+
+// Accumulator sources: the epilogues are written once against this tiny interface.
+struct AccTmem {
+  uint32_t taddr;  // lane-quarter base | first column of this tile's accumulator
+  __device__ __forceinline__ void load32(int col, float (&v)[32]) const {
+    tmem_ld_32x32(taddr + (uint32_t)col, v);
+  }
+};
+struct AccGlobal {
+  const float* p;  // &scratch[row * ld + n0]
+  __device__ __forceinline__ void load32(int col, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = p[col + i];
+  }
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual align
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmShape shp, const Epi epi) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (shp.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int total_kb = shp.ntaps * shp.kblocks_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * GEMM_BM;
+        const int n0 = (tile / m_tiles) * BN;
+        int tap = 0, kk = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK,
+                      m0 + shp.shift[tap]);
+          tma_load_2d(sB + stage * L::B_BYTES, &tma_b, &full_bar[stage],
+                      tap * shp.b_tap_stride + kk * GEMM_BK, n0);
+          if (++kk == shp.kblocks_per_tap) {
+            kk = 0;
+            ++tap;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer (one thread) ----------------
+      constexpr uint32_t idesc = make_umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_umma_desc_k128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t db = make_umma_desc_k128(smem_u32(sB + stage * L::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == total_kb - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: TMEM -> registers -> fused op -> HBM ----------------
+    const int quarter = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile % m_tiles) * GEMM_BM;
+      const int n0 = (tile / m_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tcgen05_fence_after();
+      AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN)};
+      epi.template run<BN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scalar reference path (tests / bring-up only; selected with ace_debug_set_gemm_reference).
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_ref_kernel(const bf16* __restrict__ A, long lda, int a_rows,
+                                const bf16* __restrict__ B, long ldb, GemmShape shp, int kc,
+                                float* __restrict__ out, int ld_out, int m_pad, int n_pad);
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(128)
+gemm_ref_epilogue_kernel(const float* __restrict__ scratch, int ld, GemmShape shp, const Epi epi) {
+  const int m0 = blockIdx.x * GEMM_BM;
+  const int n0 = blockIdx.y * BN;
+  const int row = m0 + threadIdx.x;
+  AccGlobal acc{scratch + (size_t)row * ld + n0};
+  epi.template run<BN>(acc, row, n0, shp.M, shp.N);
+}
+
+template <int BN, int STAGES, class Epi>
+int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  if (gemm_debug_reference()) {
+    const int m_pad = ceil_div(p.shp.M, GEMM_BM) * GEMM_BM;
+    const int n_pad = ceil_div(p.shp.N, BN) * BN;
+    float* scratch = gemm_debug_scratch((size_t)m_pad * n_pad);
+    if (!scratch) {
+      set_error("gemm debug scratch allocation failed");
+      return ACE_ERR_NOMEM;
+    }
+    dim3 g(ceil_div(n_pad, 32), ceil_div(m_pad, 8));
+    gemm_ref_kernel<<<g, dim3(32, 8), 0, stream>>>(p.a_ptr, p.a_ld, p.a_rows, p.b_ptr, p.b_ld,
+                                                   p.shp, p.shp.kblocks_per_tap * GEMM_BK, scratch,
+                                                   n_pad, m_pad, n_pad);
+    gemm_ref_epilogue_kernel<BN, Epi>
+        <<<dim3(m_pad / GEMM_BM, n_pad / BN), 128, 0, stream>>>(scratch, n_pad, p.shp, epi);
+    ACE_CUDA_CHECK(cudaGetLastError());
+    return ACE_OK;
+  }
+  using L = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, Epi>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(p.shp.M, GEMM_BM) * ceil_div(p.shp.N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN, STAGES, Epi><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p.tma_a, p.tma_b, p.shp,
+                                                                           epi);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+template <class Epi>
+int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  if (p.shp.M <= 0 || p.shp.N <= 0) return ACE_OK;
+  switch (p.bn) {
+    case 128:
+      return launch_gemm_bn<128, 6, Epi>(p, epi, stream);
+    default:
+      set_error("launch_gemm: unsupported BLOCK_N %d", p.bn);
+      return ACE_ERR_UNSUPPORTED;
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ace

@@ -1,0 +1,147 @@
+// runtime.cu — host-side plumbing shared by every entry point of libacestep_b200:
+// error strings, TMA tensor-map encoding (driver entry point resolved at run time so the
+// library has no link-time dependency on libcuda), GEMM plans, and the scalar reference GEMM
+// used only by the bring-up/debug switch.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ace {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
+                   uint64_t row_pitch_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return ACE_ERR_CUDA;
+  }
+  ACE_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map base %p not 16-byte aligned", base);
+  ACE_REQUIRE((row_pitch_bytes & 15) == 0, "tensor map pitch %llu not a multiple of 16",
+              (unsigned long long)row_pitch_bytes);
+  ACE_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map box rows %u", box_rows);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p cols=%llu rows=%llu pitch=%llu box=%u",
+              (int)r, base, (unsigned long long)cols, (unsigned long long)rows,
+              (unsigned long long)row_pitch_bytes, box_rows);
+    return ACE_ERR_CUDA;
+  }
+  return ACE_OK;
+}
+
+int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
+                   int n, long b_ld, int m, int ntaps, const int* shifts, int bn) {
+  ACE_REQUIRE(kc > 0 && kc % GEMM_BK == 0, "gemm: per-tap K %d must be a multiple of %d", kc,
+              GEMM_BK);
+  ACE_REQUIRE(ntaps >= 1 && ntaps <= GEMM_MAX_TAPS, "gemm: ntaps %d", ntaps);
+  ACE_REQUIRE(bn == 128, "gemm: BLOCK_N %d unsupported", bn);
+  memset(plan, 0, sizeof(*plan));
+  plan->shp.M = m;
+  plan->shp.N = n;
+  plan->shp.kblocks_per_tap = kc / GEMM_BK;
+  plan->shp.ntaps = ntaps;
+  plan->shp.b_tap_stride = kc;
+  for (int i = 0; i < ntaps; ++i) plan->shp.shift[i] = shifts ? shifts[i] : 0;
+  plan->a_ptr = a;
+  plan->a_ld = a_ld;
+  plan->a_rows = a_rows;
+  plan->b_ptr = b;
+  plan->b_ld = b_ld;
+  plan->bn = bn;
+  if (m <= 0 || n <= 0) return ACE_OK;
+  ACE_PROPAGATE(encode_tmap_2d(&plan->tma_a, a, (uint64_t)kc, (uint64_t)a_rows,
+                               (uint64_t)a_ld * sizeof(bf16), GEMM_BM));
+  ACE_PROPAGATE(encode_tmap_2d(&plan->tma_b, b, (uint64_t)ntaps * kc, (uint64_t)n,
+                               (uint64_t)b_ld * sizeof(bf16), (uint32_t)bn));
+  return ACE_OK;
+}
+
+static bool g_debug_ref = false;
+void set_gemm_debug_reference(bool on) { g_debug_ref = on; }
+bool gemm_debug_reference() { return g_debug_ref; }
+
+float* gemm_debug_scratch(size_t elems) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (elems > cap) {
+    if (buf) {
+      cudaDeviceSynchronize();
+      cudaFree(buf);
+      buf = nullptr;
+      cap = 0;
+    }
+    if (cudaMalloc(&buf, elems * sizeof(float)) != cudaSuccess) {
+      buf = nullptr;
+      return nullptr;
+    }
+    cap = elems;
+  }
+  return buf;
+}
+
+__global__ void gemm_ref_kernel(const bf16* __restrict__ A, long lda, int a_rows,
+                                const bf16* __restrict__ B, long ldb, GemmShape shp, int kc,
+                                float* __restrict__ out, int ld_out, int m_pad, int n_pad) {
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m = blockIdx.y * 8 + threadIdx.y;
+  if (m >= m_pad || n >= n_pad) return;
+  float acc = 0.f;
+  if (m < shp.M && n < shp.N) {
+    for (int tap = 0; tap < shp.ntaps; ++tap) {
+      const long r = (long)m + shp.shift[tap];
+      if (r < 0 || r >= a_rows) continue;
+      const bf16* ap = A + r * lda;
+      const bf16* bp = B + (long)n * ldb + (long)tap * shp.b_tap_stride;
+      for (int k = 0; k < kc; ++k) acc += __bfloat162float(ap[k]) * __bfloat162float(bp[k]);
+    }
+  }
+  out[(size_t)m * ld_out + n] = acc;
+}
+
+}  // namespace ace
