@@ -1,0 +1,108 @@
+"""ctypes binding of libacestep_b200.so (the C ABI declared in include/acestep_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, an exception
+is raised (`B200Error`); nothing silently routes to PyTorch or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200.so")
+
+
+class B200Error(RuntimeError):
+    """Raised when libacestep_b200 is unavailable or an entry point reports a failure."""
+
+
+class AceDitConfig(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int), ("intermediate_size", C.c_int), ("num_layers", C.c_int),
+        ("num_heads", C.c_int), ("num_kv_heads", C.c_int), ("head_dim", C.c_int),
+        ("sliding_window", C.c_int), ("layer_is_sliding", C.c_int * 64),
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+    ]
+
+
+class AceVaeConfig(C.Structure):
+    _fields_ = [
+        ("num_stages", C.c_int), ("ratios", C.c_int * 8), ("channel_multiples", C.c_int * 8),
+        ("encoder_hidden", C.c_int), ("decoder_channels", C.c_int), ("latent_channels", C.c_int),
+        ("audio_channels", C.c_int),
+    ]
+
+
+_P = C.c_void_p
+# name -> (restype, argtypes); must list every symbol of include/acestep_b200.h
+SIGNATURES = {
+    "ace_last_error": (C.c_char_p, []),
+    "ace_abi_version": (C.c_int, []),
+    "ace_init": (C.c_int, [C.c_int]),
+    "ace_dit_packed_elems": (C.c_size_t, [C.POINTER(AceDitConfig)]),
+    "ace_dit_create": (C.c_int, [C.POINTER(_P), C.POINTER(AceDitConfig), _P, C.c_size_t]),
+    "ace_dit_destroy": (None, [_P]),
+    "ace_dit_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int, C.c_int]),
+    "ace_dit_bind": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
+    "ace_dit_set_condition": (C.c_int, [_P, _P, _P]),
+    "ace_dit_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), _P, _P]),
+    "ace_euler_step": (C.c_int, [_P, _P, C.c_float, C.c_size_t, _P]),
+    "ace_sde_step": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_size_t, _P]),
+    "ace_apg": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, C.c_int, C.c_int, _P]),
+    "ace_adg": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_float, _P, C.c_int, C.c_int, _P]),
+    "ace_vae_packed_bytes": (C.c_size_t, [C.POINTER(AceVaeConfig)]),
+    "ace_vae_create": (C.c_int, [C.POINTER(_P), C.POINTER(AceVaeConfig), _P, C.c_size_t]),
+    "ace_vae_destroy": (None, [_P]),
+    "ace_vae_decode_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
+    "ace_vae_encode_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
+    "ace_vae_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ace_vae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "ace_debug_set_gemm_reference": (None, [C.c_int]),
+    "ace_debug_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ace_debug_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and declare every prototype.  Raises B200Error if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} not found — build it with `python -m acestep_b200.build` "
+            "(the B200 backend has no CPU/PyTorch fallback)")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise B200Error(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise B200Error(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().ace_last_error()
+        raise B200Error(f"{what or 'libacestep_b200 call'} failed (status {status}): "
+                        f"{msg.decode(errors='replace') if msg else '?'}")
+
+
+def ptr(t) -> int:
+    """Device/host pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_handle(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,469 @@
+// dit.cu — the DiT denoising step as a stream of fused kernels (one CUDA graph per bound shape).
+//
+// Follows AceStepDiTModel.forward (modeling_acestep_v15_turbo.py:1300-1504) and
+// AceStepDiTLayer.forward (:472-536); what the reference runs as ~60 ATen/cuBLAS/SDPA launches
+// per layer is 10 launches here:
+//     adaLN-RMSNorm -> [QKV GEMM + q/k RMSNorm + RoPE] -> attention -> [o_proj GEMM + gated residual]
+//     RMSNorm       -> [q GEMM + q RMSNorm]           -> cross-attention -> [o_proj GEMM + residual]
+//     adaLN-RMSNorm -> [gate|up GEMM + SwiGLU]        -> [down GEMM + gated residual]
+// The dense S x S masks of create_4d_mask (:53-132) never exist: the band is implicit.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/acestep_b200.h"
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "gemm.cuh"
+#include "kernels.h"
+
+namespace ace {
+
+struct LayerWeights {
+  const bf16 *self_norm, *cross_norm, *mlp_norm, *table;
+  const bf16 *self_qkv, *self_qn, *self_kn, *self_o;
+  const bf16 *cross_q, *cross_kv, *cross_qn, *cross_kn, *cross_o;
+  const bf16 *gate_up, *down;
+};
+
+struct LayerPlans {
+  GemmPlan qkv, self_o, cross_q, cross_o, gate_up, down, cross_kv;
+};
+
+}  // namespace ace
+
+using namespace ace;
+
+struct AceDit {
+  AceDitConfig cfg;
+  int D, I, L, NQ, NKV;
+  bf16* weights = nullptr;
+  size_t n_elems = 0;
+  // global weights
+  const bf16 *proj_in_w, *proj_in_b, *cond_w, *cond_b, *norm_out_w, *out_table, *proj_out_w, *proj_out_b;
+  TimeEmbedWeights te, te_r;
+  std::vector<LayerWeights> lw;
+  bf16* r_const = nullptr;  // [D + 6D]: time_embed_r(0) -> (temb_r, tproj_r), constant per model
+
+  // bound shape
+  int Bc = 0, T = 0, Tpad = 0, S = 0, E = 0, M = 0;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  bf16 *xin, *ctxin, *vout;  // static I/O slots so the graph never sees caller pointers
+  bf16 *xcat, *h, *hn, *qkv, *attn, *qc, *act, *enc_e, *ckv, *temb, *tproj, *gates, *te_scratch;
+  bf16 *rope_cos, *rope_sin;
+  float* t_dev;
+  GemmPlan plan_in, plan_out;
+  std::vector<LayerPlans> lp;
+  cudaGraphExec_t graph = nullptr;
+  bool use_graph = true;
+  bool rope_ready = false;
+};
+
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <class Tp>
+  Tp* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+    off += n * sizeof(Tp);
+    return p;
+  }
+};
+
+// One place defines the workspace layout; called with base == nullptr to size it.
+size_t carve_workspace(AceDit* d, uint8_t* base, int Bc, int T, int E) {
+  const int Tpad = (T + 1) & ~1, S = Tpad / 2;
+  const size_t M = (size_t)Bc * S;
+  const int D = d->D, I = d->I, L = d->L, NQ = d->NQ, NKV = d->NKV;
+  Carver c{base};
+  d->xin = c.take<bf16>((size_t)Bc * T * 64);
+  d->ctxin = c.take<bf16>((size_t)Bc * T * 128);
+  d->vout = c.take<bf16>((size_t)Bc * T * 64);
+  d->xcat = c.take<bf16>((size_t)Bc * Tpad * 192);
+  d->h = c.take<bf16>(M * D);
+  d->hn = c.take<bf16>(M * D);
+  d->qkv = c.take<bf16>(M * (NQ + 2 * NKV));
+  d->attn = c.take<bf16>(M * NQ);
+  d->qc = c.take<bf16>(M * NQ);
+  d->act = c.take<bf16>(M * I);
+  d->enc_e = c.take<bf16>((size_t)Bc * E * D);
+  d->ckv = c.take<bf16>((size_t)L * Bc * E * 2 * NKV);
+  d->temb = c.take<bf16>((size_t)Bc * D);
+  d->tproj = c.take<bf16>((size_t)Bc * 6 * D);
+  d->gates = c.take<bf16>((size_t)L * Bc * 2 * D);
+  d->te_scratch = c.take<bf16>((size_t)Bc * (256 + 2 * D));
+  d->rope_cos = c.take<bf16>((size_t)S * 64);
+  d->rope_sin = c.take<bf16>((size_t)S * 64);
+  d->t_dev = c.take<float>(16);
+  return c.off + 256;
+}
+
+struct TVals {
+  float v[16];
+};
+__global__ void set_t_kernel(float* dst, TVals t, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = t.v[threadIdx.x];
+}
+
+int check_device() {
+  int dev = 0;
+  ACE_CUDA_CHECK(cudaGetDevice(&dev));
+  int major = 0;
+  ACE_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("libacestep_b200 requires an sm_100 (B200) device, found compute capability %d.x", major);
+    return ACE_ERR_CUDA;
+  }
+  return ACE_OK;
+}
+
+// Enqueue one full forward (everything after the inputs sit in xin/ctxin/t_dev).
+int enqueue_forward(AceDit* d, cudaStream_t st) {
+  const int D = d->D, NQ = d->NQ, NKV = d->NKV, S = d->S, Bc = d->Bc, M = d->M, E = d->E;
+  const float eps = d->cfg.rms_eps;
+  const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
+  const int group = d->cfg.num_heads / d->cfg.num_kv_heads;
+  const long QKVW = NQ + 2 * NKV;
+
+  ACE_PROPAGATE(launch_time_embed(d->te, d->t_dev, Bc, D, d->te_scratch, d->temb, d->tproj, d->r_const,
+                                  d->r_const + D, st));
+  ACE_PROPAGATE(launch_gate_table(d->lw[0].table, d->tproj, d->gates, d->L, Bc, D, st));
+  ACE_PROPAGATE(launch_concat_patches(d->ctxin, d->xin, d->xcat, Bc, d->T, d->Tpad, st));
+  ACE_PROPAGATE(launch_gemm(d->plan_in, EpiBias{d->h, (long)D, d->proj_in_b}, st));
+
+  for (int l = 0; l < d->L; ++l) {
+    const LayerWeights& w = d->lw[l];
+    const LayerPlans& p = d->lp[l];
+    const bf16* gate_msa = d->gates + ((size_t)l * Bc * 2 + 0) * D;
+    const bf16* gate_mlp = d->gates + ((size_t)l * Bc * 2 + 1) * D;
+    // --- self attention ---
+    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.self_norm, w.table + 0 * D, w.table + 1 * D,
+                                       d->tproj + 0 * D, d->tproj + 1 * D, 6L * D, d->hn, M, D, S, eps, st));
+    ACE_PROPAGATE(launch_gemm(p.qkv, EpiQKV{d->qkv, QKVW, NQ, NKV, w.self_qn, w.self_kn, d->rope_cos,
+                                            d->rope_sin, S, eps}, st));
+    AttnParams ap{d->qkv, d->qkv + NQ, d->qkv + NQ + NKV, d->attn, QKVW, QKVW, QKVW, (long)NQ, S, S,
+                  d->cfg.layer_is_sliding[l] ? d->cfg.sliding_window : -1, group, scale_log2};
+    ACE_PROPAGATE(launch_attention(ap, d->cfg.num_heads, Bc, st));
+    ACE_PROPAGATE(launch_gemm(p.self_o, EpiGatedResid{d->h, (long)D, gate_msa, 2L * D, S}, st));
+    // --- cross attention ---
+    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.cross_norm, nullptr, nullptr, nullptr, nullptr, 0, d->hn, M,
+                                       D, S, eps, st));
+    ACE_PROPAGATE(launch_gemm(p.cross_q, EpiQKV{d->qc, (long)NQ, NQ, 0, w.cross_qn, w.cross_kn, nullptr,
+                                                nullptr, S, eps}, st));
+    const bf16* kv = d->ckv + (size_t)l * Bc * E * 2 * NKV;
+    AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, E, -1, group,
+                  scale_log2};
+    ACE_PROPAGATE(launch_attention(cp, d->cfg.num_heads, Bc, st));
+    ACE_PROPAGATE(launch_gemm(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S}, st));
+    // --- MLP ---
+    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.mlp_norm, w.table + 3 * D, w.table + 4 * D,
+                                       d->tproj + 3 * D, d->tproj + 4 * D, 6L * D, d->hn, M, D, S, eps, st));
+    ACE_PROPAGATE(launch_gemm(p.gate_up, EpiSwiGLU{d->act, (long)d->I}, st));
+    ACE_PROPAGATE(launch_gemm(p.down, EpiGatedResid{d->h, (long)D, gate_mlp, 2L * D, S}, st));
+  }
+  // output AdaLN: shift = table[0] + temb, scale = table[1] + temb  (:1488-1493)
+  ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, d->norm_out_w, d->out_table, d->out_table + D, d->temb, d->temb,
+                                     (long)D, d->hn, M, D, S, eps, st));
+  ACE_PROPAGATE(launch_gemm(d->plan_out, EpiProjOut{d->vout, d->proj_out_b, S, d->T}, st));
+  return ACE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ace_last_error(void) { return get_error(); }
+int ace_abi_version(void) { return 1; }
+
+int ace_init(int device) {
+  ACE_CUDA_CHECK(cudaSetDevice(device));
+  return check_device();
+}
+
+void ace_debug_set_gemm_reference(int on) { set_gemm_debug_reference(on != 0); }
+
+size_t ace_dit_packed_elems(const AceDitConfig* c) {
+  const size_t D = c->hidden_size, I = c->intermediate_size, L = c->num_layers;
+  const size_t NQ = (size_t)c->num_heads * c->head_dim, NKV = (size_t)c->num_kv_heads * c->head_dim;
+  size_t te = D * 256 + D + D * D + D + 6 * D * D + 6 * D;
+  size_t g = D * 384 + D + 2 * te + D * D + D + D + 2 * D + 128 * D + 64;
+  size_t per = 3 * D + 6 * D + (NQ + 2 * NKV) * D + 256 + D * NQ + NQ * D + 2 * NKV * D + 256 + D * NQ +
+               2 * I * D + D * I;
+  return g + L * per;
+}
+
+int ace_dit_create(AceDit** out, const AceDitConfig* cfg, const uint16_t* weights, size_t n_elems) {
+  ACE_REQUIRE(out && cfg && weights, "ace_dit_create: null argument");
+  ACE_PROPAGATE(check_device());
+  ACE_REQUIRE(cfg->head_dim == 128, "head_dim %d unsupported (kernels are specialised for 128)", cfg->head_dim);
+  ACE_REQUIRE(cfg->hidden_size % 256 == 0 && cfg->intermediate_size % 64 == 0,
+              "hidden_size must be a multiple of 256 and intermediate_size of 64");
+  ACE_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 64, "num_layers %d out of range", cfg->num_layers);
+  ACE_REQUIRE(cfg->num_kv_heads >= 1 && cfg->num_heads % cfg->num_kv_heads == 0, "bad head counts");
+  ACE_REQUIRE(n_elems == ace_dit_packed_elems(cfg), "packed weight blob has %zu elements, expected %zu",
+              n_elems, ace_dit_packed_elems(cfg));
+  AceDit* d = new AceDit();
+  d->cfg = *cfg;
+  d->D = cfg->hidden_size;
+  d->I = cfg->intermediate_size;
+  d->L = cfg->num_layers;
+  d->NQ = cfg->num_heads * 128;
+  d->NKV = cfg->num_kv_heads * 128;
+  d->n_elems = n_elems;
+  const char* ng = getenv("ACE_NO_GRAPH");
+  d->use_graph = !(ng && ng[0] == '1');
+  if (cudaMalloc(&d->weights, n_elems * sizeof(bf16)) != cudaSuccess) {
+    delete d;
+    set_error("cudaMalloc of %zu weight bytes failed", n_elems * sizeof(bf16));
+    return ACE_ERR_NOMEM;
+  }
+  cudaError_t e = cudaMemcpy(d->weights, weights, n_elems * sizeof(bf16), cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaFree(d->weights);
+    delete d;
+    set_error("weight upload failed: %s", cudaGetErrorString(e));
+    return ACE_ERR_CUDA;
+  }
+  const size_t D = d->D, I = d->I, NQ = d->NQ, NKV = d->NKV;
+  const bf16* p = d->weights;
+  auto take = [&](size_t n) {
+    const bf16* r = p;
+    p += n;
+    return r;
+  };
+  d->proj_in_w = take(D * 384);
+  d->proj_in_b = take(D);
+  for (TimeEmbedWeights* te : {&d->te, &d->te_r}) {
+    te->w1 = take(D * 256);
+    te->b1 = take(D);
+    te->w2 = take(D * D);
+    te->b2 = take(D);
+    te->wp = take(6 * D * D);
+    te->bp = take(6 * D);
+  }
+  d->cond_w = take(D * D);
+  d->cond_b = take(D);
+  d->norm_out_w = take(D);
+  d->out_table = take(2 * D);
+  d->proj_out_w = take(128 * D);
+  d->proj_out_b = take(64);
+  d->lw.resize(d->L);
+  // the per-layer AdaLN tables are stored contiguously first ([L, 6, D]) so one kernel can build
+  // every layer's gate vectors; then the remaining per-layer tensors.
+  const bf16* tables = take((size_t)d->L * 6 * D);
+  for (int l = 0; l < d->L; ++l) {
+    LayerWeights& w = d->lw[l];
+    w.table = tables + (size_t)l * 6 * D;
+    w.self_norm = take(D);
+    w.cross_norm = take(D);
+    w.mlp_norm = take(D);
+    w.self_qkv = take((NQ + 2 * NKV) * D);
+    w.self_qn = take(128);
+    w.self_kn = take(128);
+    w.self_o = take(D * NQ);
+    w.cross_q = take(NQ * D);
+    w.cross_kv = take(2 * NKV * D);
+    w.cross_qn = take(128);
+    w.cross_kn = take(128);
+    w.cross_o = take(D * NQ);
+    w.gate_up = take(2 * I * D);
+    w.down = take(D * I);
+  }
+  if ((size_t)(p - d->weights) != n_elems) {
+    cudaFree(d->weights);
+    delete d;
+    set_error("internal: weight layout walk consumed %zu of %zu elements", (size_t)(p - d->weights), n_elems);
+    return ACE_ERR_INVALID;
+  }
+  // time_embed_r always sees t - t = 0 at inference (:1338): evaluate it once.
+  if (cudaMalloc(&d->r_const, (7 * D + 16 * (256 + 2 * D) + 64) * sizeof(bf16) + 64) != cudaSuccess) {
+    cudaFree(d->weights);
+    delete d;
+    set_error("cudaMalloc failed");
+    return ACE_ERR_NOMEM;
+  }
+  {
+    bf16* scratch = d->r_const + 7 * D;
+    float* t0 = reinterpret_cast<float*>(scratch + 16 * (256 + 2 * D));
+    cudaMemset(t0, 0, 64);
+    int s = launch_time_embed(d->te_r, t0, 1, (int)D, scratch, d->r_const, d->r_const + D, nullptr, nullptr, 0);
+    if (s == ACE_OK && cudaDeviceSynchronize() != cudaSuccess) {
+      set_error("time_embed_r precompute failed: %s", cudaGetErrorString(cudaGetLastError()));
+      s = ACE_ERR_CUDA;
+    }
+    if (s != ACE_OK) {
+      cudaFree(d->weights);
+      cudaFree(d->r_const);
+      delete d;
+      return s;
+    }
+  }
+  *out = d;
+  return ACE_OK;
+}
+
+void ace_dit_destroy(AceDit* d) {
+  if (!d) return;
+  if (d->graph) cudaGraphExecDestroy(d->graph);
+  cudaFree(d->weights);
+  cudaFree(d->r_const);
+  delete d;
+}
+
+size_t ace_dit_workspace_bytes(const AceDit* d, int bc, int t, int e) {
+  if (!d || bc <= 0 || t <= 0 || e <= 0) return 0;
+  AceDit tmp = *d;  // carve on a copy: sizing must not disturb a live binding
+  tmp.graph = nullptr;
+  return carve_workspace(&tmp, nullptr, bc, t, e);
+}
+
+int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
+  ACE_REQUIRE(d && ws, "ace_dit_bind: null argument");
+  ACE_REQUIRE(bc >= 1 && bc <= 16, "effective batch %d out of range [1,16]", bc);
+  ACE_REQUIRE(t >= 1 && e >= 1, "bad shape t=%d e=%d", t, e);
+  ACE_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  const size_t need = ace_dit_workspace_bytes(d, bc, t, e);
+  ACE_REQUIRE(ws_bytes >= need, "workspace too small: %zu < %zu", ws_bytes, need);
+  if (d->graph) {
+    cudaGraphExecDestroy(d->graph);
+    d->graph = nullptr;
+  }
+  d->Bc = bc;
+  d->T = t;
+  d->Tpad = (t + 1) & ~1;
+  d->S = d->Tpad / 2;
+  d->E = e;
+  d->M = bc * d->S;
+  d->ws = (uint8_t*)ws;
+  d->ws_bytes = ws_bytes;
+  carve_workspace(d, d->ws, bc, t, e);
+  const int D = d->D, I = d->I, NQ = d->NQ, NKV = d->NKV, M = d->M;
+  const int ME = bc * e;
+  ACE_PROPAGATE(make_gemm_plan(&d->plan_in, d->xcat, M, 384, 384, d->proj_in_w, D, 384, M, 1, nullptr, 128));
+  ACE_PROPAGATE(make_gemm_plan(&d->plan_out, d->hn, M, D, D, d->proj_out_w, 128, D, M, 1, nullptr, 128));
+  d->lp.resize(d->L);
+  for (int l = 0; l < d->L; ++l) {
+    const LayerWeights& w = d->lw[l];
+    LayerPlans& p = d->lp[l];
+    ACE_PROPAGATE(make_gemm_plan(&p.qkv, d->hn, M, D, D, w.self_qkv, NQ + 2 * NKV, D, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->hn, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_kv, d->enc_e, ME, D, D, w.cross_kv, 2 * NKV, D, ME, 1, nullptr, 128));
+  }
+  d->rope_ready = false;
+  return ACE_OK;
+}
+
+int ace_dit_set_condition(AceDit* d, const uint16_t* d_enc, void* stream) {
+  ACE_REQUIRE(d && d->ws, "ace_dit_set_condition: handle not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = d->D, NKV = d->NKV, ME = d->Bc * d->E;
+  // condition_embedder (:1356) straight from the caller's buffer
+  GemmPlan pc;
+  ACE_PROPAGATE(make_gemm_plan(&pc, (const bf16*)d_enc, ME, D, D, d->cond_w, D, D, ME, 1, nullptr, 128));
+  ACE_PROPAGATE(launch_gemm(pc, EpiBias{d->enc_e, (long)D, d->cond_b}, st));
+  for (int l = 0; l < d->L; ++l) {
+    bf16* kv = d->ckv + (size_t)l * ME * 2 * NKV;
+    ACE_PROPAGATE(launch_gemm(d->lp[l].cross_kv,
+                              EpiQKV{kv, 2L * NKV, 0, NKV, d->lw[l].cross_qn, d->lw[l].cross_kn, nullptr,
+                                     nullptr, d->E, d->cfg.rms_eps}, st));
+  }
+  return ACE_OK;
+}
+
+int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t, uint16_t* d_vt,
+                 void* stream) {
+  ACE_REQUIRE(d && d->ws, "ace_dit_step: handle not bound");
+  ACE_REQUIRE(d_xt && d_ctx && h_t && d_vt, "ace_dit_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nx = (size_t)d->Bc * d->T * 64;
+  if (!d->rope_ready) {
+    ACE_PROPAGATE(launch_rope_tables(d->rope_cos, d->rope_sin, d->S, d->cfg.rope_theta, st));
+    d->rope_ready = true;
+  }
+  if ((const bf16*)d_xt != d->xin)
+    ACE_CUDA_CHECK(cudaMemcpyAsync(d->xin, d_xt, nx * 2, cudaMemcpyDeviceToDevice, st));
+  if ((const bf16*)d_ctx != d->ctxin)
+    ACE_CUDA_CHECK(cudaMemcpyAsync(d->ctxin, d_ctx, nx * 4, cudaMemcpyDeviceToDevice, st));
+  TVals tv;
+  for (int i = 0; i < 16; ++i) tv.v[i] = i < d->Bc ? h_t[i] : 0.f;
+  set_t_kernel<<<1, 32, 0, st>>>(d->t_dev, tv, d->Bc);
+
+  const bool graph_ok = d->use_graph && !gemm_debug_reference();
+  if (!graph_ok) {
+    ACE_PROPAGATE(enqueue_forward(d, st));
+  } else {
+    if (!d->graph) {
+      // first use: run once eagerly (sets per-kernel attributes, surfaces launch errors with a
+      // precise message), then capture the identical launch sequence.
+      ACE_PROPAGATE(enqueue_forward(d, st));
+      ACE_CUDA_CHECK(cudaStreamSynchronize(st));
+      cudaStream_t cs;
+      ACE_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      int s = ACE_OK;
+      if (e == cudaSuccess) {
+        s = enqueue_forward(d, cs);
+        e = cudaStreamEndCapture(cs, &g);
+      }
+      if (e == cudaSuccess && s == ACE_OK) e = cudaGraphInstantiate(&d->graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+      cudaStreamDestroy(cs);
+      if (s != ACE_OK) return s;
+      if (e != cudaSuccess) {
+        set_error("CUDA graph capture of the DiT step failed: %s", cudaGetErrorString(e));
+        return ACE_ERR_CUDA;
+      }
+    } else {
+      ACE_CUDA_CHECK(cudaGraphLaunch(d->graph, st));
+    }
+  }
+  if ((bf16*)d_vt != d->vout)
+    ACE_CUDA_CHECK(cudaMemcpyAsync(d_vt, d->vout, nx * 2, cudaMemcpyDeviceToDevice, st));
+  return ACE_OK;
+}
+
+int ace_euler_step(uint16_t* xt, const uint16_t* vt, float dt, size_t n, void* stream) {
+  return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream);
+}
+int ace_sde_step(uint16_t* xt, const uint16_t* vt, const uint16_t* eps, float t_cur, float t_next, size_t n,
+                 void* stream) {
+  return launch_sde((bf16*)xt, (const bf16*)vt, (const bf16*)eps, t_cur, t_next, (long)n, (cudaStream_t)stream);
+}
+int ace_apg(const uint16_t* cond, const uint16_t* uncond, uint16_t* mom, int first_update, float momentum,
+            float norm_threshold, float guidance_scale, uint16_t* out, int b, int t, void* stream) {
+  return launch_apg((const bf16*)cond, (const bf16*)uncond, (bf16*)mom, first_update, momentum, norm_threshold,
+                    guidance_scale, (bf16*)out, b, t, (cudaStream_t)stream);
+}
+int ace_adg(const uint16_t* xt, const uint16_t* cond, const uint16_t* uncond, float sigma, float guidance_scale,
+            float angle_clip, uint16_t* out, int b, int t, void* stream) {
+  return launch_adg((const bf16*)xt, (const bf16*)cond, (const bf16*)uncond, sigma, guidance_scale, angle_clip,
+                    (bf16*)out, b, t, (cudaStream_t)stream);
+}
+
+int ace_debug_linear(const uint16_t* a, const uint16_t* b, const uint16_t* bias, uint16_t* out, int m, int n,
+                     int k, void* stream) {
+  GemmPlan p;
+  ACE_PROPAGATE(make_gemm_plan(&p, (const bf16*)a, m, k, k, (const bf16*)b, n, k, m, 1, nullptr, 128));
+  return launch_gemm(p, EpiBias{(bf16*)out, (long)n, (const bf16*)bias}, (cudaStream_t)stream);
+}
+
+int ace_debug_attention(const uint16_t* q, const uint16_t* k, const uint16_t* v, uint16_t* o, int batch,
+                        int heads, int kv_heads, int sq, int skv, int window, void* stream) {
+  ACE_REQUIRE(kv_heads >= 1 && heads % kv_heads == 0, "bad head counts");
+  AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, heads * 128L, kv_heads * 128L,
+               kv_heads * 128L, heads * 128L, sq, skv, window, heads / kv_heads,
+               (1.0f / sqrtf(128.0f)) * 1.4426950408889634f};
+  return launch_attention(p, heads, batch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

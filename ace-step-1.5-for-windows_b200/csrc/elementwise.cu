@@ -1,0 +1,445 @@
+// elementwise.cu — the memory-bound glue of the DiT step and the sampler update kernels.
+//
+// Everything here is HBM/latency-bound vector work: 16-byte loads/stores, one pass per tensor,
+// fp32 math with the reference's bf16 rounding points reproduced where they are free.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ace {
+
+namespace {
+
+struct alignas(16) Bf8 {
+  uint4 w;
+};
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  uint4 w = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(w.x, v[0], v[1]);
+  unpack_bf16x2(w.y, v[2], v[3]);
+  unpack_bf16x2(w.z, v[4], v[5]);
+  unpack_bf16x2(w.w, v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(v[0], v[1]);
+  w.y = pack_bf16x2(v[2], v[3]);
+  w.z = pack_bf16x2(v[4], v[5]);
+  w.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = w;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void concat_patches_kernel(const bf16* __restrict__ ctx, const bf16* __restrict__ xt,
+                                      bf16* __restrict__ out, int B, int T, int Tpad) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Tpad * 24;
+  if (idx >= total) return;
+  const int c = idx % 24;
+  const long row = idx / 24;
+  const int t = row % Tpad;
+  const int b = row / Tpad;
+  uint4 w = make_uint4(0, 0, 0, 0);
+  if (t < T) {
+    const long src = (long)b * T + t;
+    w = (c < 16) ? *reinterpret_cast<const uint4*>(ctx + src * 128 + c * 8)
+                 : *reinterpret_cast<const uint4*>(xt + src * 64 + (c - 16) * 8);
+  }
+  *reinterpret_cast<uint4*>(out + row * 192 + c * 8) = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm (+ AdaLN modulation).  One 256-thread block per row.
+__global__ void __launch_bounds__(256)
+adaln_rmsnorm_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
+                     const bf16* __restrict__ shift_tab, const bf16* __restrict__ scale_tab,
+                     const bf16* __restrict__ shift_t, const bf16* __restrict__ scale_t, long t_ld,
+                     bf16* __restrict__ out, int D, int rows_per_batch, float eps) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const int b = row / rows_per_batch;
+  const bf16* hp = h + (long)row * D;
+  const int nchunk = D >> 3;
+  float first[8];
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < nchunk; c += 256) {
+    float v[8];
+    ld8(hp + c * 8, v);
+    if (c == (int)threadIdx.x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) first[i] = v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)D + eps);
+  for (int c = threadIdx.x; c < nchunk; c += 256) {
+    float v[8], wv[8];
+    if (c == (int)threadIdx.x) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = first[i];
+    } else {
+      ld8(hp + c * 8, v);
+    }
+    ld8(w + c * 8, wv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = bf16_round(wv[i] * bf16_round(v[i] * rstd));
+    if (scale_tab != nullptr) {
+      float st[8], sv[8], ht[8], hv[8];
+      ld8(scale_tab + c * 8, st);
+      ld8(scale_t + (long)b * t_ld + c * 8, sv);
+      ld8(shift_tab + c * 8, ht);
+      ld8(shift_t + (long)b * t_ld + c * 8, hv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float sc = bf16_round(1.0f + bf16_round(st[i] + sv[i]));
+        const float sh = bf16_round(ht[i] + hv[i]);
+        v[i] = bf16_round(bf16_round(v[i] * sc) + sh);
+      }
+    }
+    st8(out + (long)row * D + c * 8, v);
+  }
+}
+
+__global__ void gate_table_kernel(const bf16* __restrict__ tables, const bf16* __restrict__ tproj,
+                                  bf16* __restrict__ out, int L, int B, int D) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over L*B*2*(D/8)
+  const int nchunk = D >> 3;
+  const long total = (long)L * B * 2 * nchunk;
+  if (idx >= total) return;
+  const int c = idx % nchunk;
+  const int which = (idx / nchunk) % 2;
+  const int b = (idx / (2 * nchunk)) % B;
+  const int l = idx / ((long)2 * nchunk * B);
+  const int mod = which == 0 ? 2 : 5;  // gate_msa, c_gate_msa
+  float a[8], t[8];
+  ld8(tables + ((long)l * 6 + mod) * D + c * 8, a);
+  ld8(tproj + ((long)b * 6 + mod) * D + c * 8, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] += t[i];
+  st8(out + (((long)l * B + b) * 2 + which) * D + c * 8, a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Timestep embedding: tiny GEMVs, bound by reading the weights once (one warp per output row).
+constexpr int TE_MAXB = 16;
+
+__global__ void sinusoid_kernel(const float* __restrict__ t, bf16* __restrict__ out, int B) {
+  // out[b, 0:128] = cos(bf16(1000 t) * f_i), out[b, 128:256] = sin(...), f_i = exp(-ln(1e4) i/128)
+  const int b = blockIdx.x, i = threadIdx.x;  // 128 threads
+  const float ts = bf16_round(t[b] * 1000.0f);
+  const float f = expf(-logf(10000.0f) * (float)i / 128.0f);
+  const float a = ts * f;
+  out[(long)b * 256 + i] = __float2bfloat16_rn(cosf(a));
+  out[(long)b * 256 + 128 + i] = __float2bfloat16_rn(sinf(a));
+}
+
+// y[b, n] = act(bf16(W[n,:] . x[b,:] + bias[n]))  (+ add[b * add_ld + n]; add_ld 0 = broadcast);  act: 0 none, 1 SiLU,
+// 2: write both plain to y and SiLU'd copy to y2.
+__global__ void __launch_bounds__(256)
+gemv_kernel(const bf16* __restrict__ W, const bf16* __restrict__ bias, const bf16* __restrict__ x,
+            int B, int K, int N, int act, const bf16* __restrict__ add, long add_ld,
+            bf16* __restrict__ y, bf16* __restrict__ y2) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[TE_MAXB];
+#pragma unroll
+  for (int b = 0; b < TE_MAXB; ++b) acc[b] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float wv[8];
+    ld8(W + (long)n * K + k, wv);
+#pragma unroll
+    for (int b = 0; b < TE_MAXB; ++b) {
+      if (b < B) {
+        float xv[8];
+        ld8(x + (long)b * K + k, xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[b] += wv[i] * xv[i];
+      }
+    }
+  }
+  const float bn = bias ? __bfloat162float(bias[n]) : 0.f;
+#pragma unroll
+  for (int b = 0; b < TE_MAXB; ++b) {
+    if (b < B) {
+      float v = warp_sum(acc[b]);
+      if (lane == 0) {
+        v = bf16_round(v + bn);
+        const float s = bf16_round(v / (1.0f + expf(-v)));
+        float o = (act == 1) ? s : v;
+        if (add) o = bf16_round(o + __bfloat162float(add[(long)b * add_ld + n]));
+        y[(long)b * N + n] = __float2bfloat16_rn(o);
+        if (act == 2) y2[(long)b * N + n] = __float2bfloat16_rn(s);
+      }
+    }
+  }
+}
+
+__global__ void rope_tables_kernel(bf16* __restrict__ cos_tab, bf16* __restrict__ sin_tab, int S,
+                                   float theta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * 64) return;
+  const int s = idx >> 6, i = idx & 63;
+  const float inv_freq = 1.0f / powf(theta, (float)(2 * i) / 128.0f);
+  const float a = (float)s * inv_freq;
+  cos_tab[idx] = __float2bfloat16_rn(cosf(a));
+  sin_tab[idx] = __float2bfloat16_rn(sinf(a));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void euler_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt, float dt, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float x[8], v[8];
+  ld8(xt + i * 8, x);
+  ld8(vt + i * 8, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = x[k] - bf16_round(v[k] * dt);
+  st8(xt + i * 8, x);
+}
+
+__global__ void sde_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt,
+                           const bf16* __restrict__ eps, float t_cur, float t_next, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float x[8], v[8], e[8];
+  ld8(xt + i * 8, x);
+  ld8(vt + i * 8, v);
+  ld8(eps + i * 8, e);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float x0 = bf16_round(x[k] - bf16_round(v[k] * t_cur));
+    x[k] = bf16_round(t_next * e[k]) + bf16_round((1.0f - t_next) * x0);
+  }
+  st8(xt + i * 8, x);
+}
+
+// APG: one 1024-thread block per batch item; thread (c = tid % 64, lane-in-time = tid / 64).
+__global__ void __launch_bounds__(1024)
+apg_kernel(const bf16* __restrict__ cond, const bf16* __restrict__ uncond, bf16* __restrict__ mom,
+           int first_update, float momentum_coef, float norm_threshold, float guidance_scale,
+           bf16* __restrict__ vt_out, int T) {
+  __shared__ double red[16][64][2];
+  __shared__ float sf_s[64];
+  __shared__ double dot_s[64], cn_s[64];
+  const int c = threadIdx.x & 63, tl = threadIdx.x >> 6;
+  const long base = (long)blockIdx.x * T * 64;
+
+  // phase A: momentum update, sum of squares of the running average along time
+  double ss = 0.0;
+  for (int t = tl; t < T; t += 16) {
+    const long i = base + (long)t * 64 + c;
+    float d = bf16_round(__bfloat162float(cond[i]) - __bfloat162float(uncond[i]));
+    if (!first_update) d = bf16_round(d + bf16_round(momentum_coef * __bfloat162float(mom[i])));
+    mom[i] = __float2bfloat16_rn(d);
+    ss += (double)d * d;
+  }
+  red[tl][c][0] = ss;
+  __syncthreads();
+  if (tl == 0) {
+    double s = 0.0;
+    for (int k = 0; k < 16; ++k) s += red[k][c][0];
+    float sf = 1.0f;
+    if (norm_threshold > 0.f) {
+      const float nrm = bf16_round((float)sqrt(s));
+      sf = fminf(1.0f, bf16_round(norm_threshold / nrm));
+    }
+    sf_s[c] = sf;
+  }
+  __syncthreads();
+  const float sf = sf_s[c];
+
+  // phase B: <diff, cond> and <cond, cond> along time (fp64 like project())
+  double dot = 0.0, cn = 0.0;
+  for (int t = tl; t < T; t += 16) {
+    const long i = base + (long)t * 64 + c;
+    const double d = (double)bf16_round(__bfloat162float(mom[i]) * sf);
+    const double pc = (double)__bfloat162float(cond[i]);
+    dot += d * pc;
+    cn += pc * pc;
+  }
+  red[tl][c][0] = dot;
+  red[tl][c][1] = cn;
+  __syncthreads();
+  if (tl == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < 16; ++k) {
+      s0 += red[k][c][0];
+      s1 += red[k][c][1];
+    }
+    dot_s[c] = s0;
+    cn_s[c] = s1;
+  }
+  __syncthreads();
+  const double nrm = fmax(sqrt(cn_s[c]), 1e-12);  // F.normalize eps
+  const double coef = dot_s[c] / nrm;             // <v0, v1/|v1|>
+
+  // phase C: orthogonal component, guided prediction
+  for (int t = tl; t < T; t += 16) {
+    const long i = base + (long)t * 64 + c;
+    const double d = (double)bf16_round(__bfloat162float(mom[i]) * sf);
+    const float pc = __bfloat162float(cond[i]);
+    const double par = coef * ((double)pc / nrm);
+    const float orth = bf16_round((float)(d - par));
+    vt_out[i] = __float2bfloat16_rn(pc + bf16_round((guidance_scale - 1.0f) * orth));
+  }
+}
+
+// ADG: one warp per (b, t) frame, 2 channels per lane.
+__global__ void adg_kernel(const bf16* __restrict__ xt, const bf16* __restrict__ cond,
+                           const bf16* __restrict__ uncond, float sigma, float guidance_scale,
+                           float angle_clip, bf16* __restrict__ vt_out, long frames) {
+  const long f = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= frames) return;
+  const int lane = threadIdx.x & 31;
+  float w = guidance_scale - 1.0f;
+  w = w * (w > 0.f ? 1.f : 0.f) + 1e-3f;
+  float xt_[2], xtext[2], xunc[2], diff[2];
+  double aa = 0, bb = 0, ab = 0;
+  float du = 0.f, uu = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long i = f * 64 + lane * 2 + k;
+    xt_[k] = __bfloat162float(xt[i]);
+    xtext[k] = bf16_round(xt_[k] - bf16_round(sigma * __bfloat162float(cond[i])));
+    xunc[k] = bf16_round(xt_[k] - bf16_round(sigma * __bfloat162float(uncond[i])));
+    diff[k] = bf16_round(xtext[k] - xunc[k]);
+    aa += (double)xtext[k] * xtext[k];
+    bb += (double)xunc[k] * xunc[k];
+    ab += (double)xtext[k] * xunc[k];
+    du += diff[k] * xunc[k];
+    uu += xunc[k] * xunc[k];
+  }
+  aa = warp_sum_d(aa);
+  bb = warp_sum_d(bb);
+  ab = warp_sum_d(ab);
+  du = warp_sum(du);
+  uu = warp_sum(uu);
+  double cosv = ab / (sqrt(aa) * sqrt(bb));
+  const double theta = acos(cosv);
+  double theta_new = (double)w * theta;
+  theta_new = fmin(fmax(theta_new, -(double)angle_clip), (double)angle_clip);
+  const double st = sin(theta), stn = sin(theta_new), ctn = cos(theta_new);
+  const float pc = du / (uu + 1e-8f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long i = f * 64 + lane * 2 + k;
+    const float perp = diff[k] - pc * xunc[k];
+    const double vnew = ctn * (double)xtext[k];
+    const double pnew = (st > 1e-3) ? (double)perp * stn / st : (double)perp * (double)w;
+    const double xnew = vnew + pnew;
+    vt_out[i] = __float2bfloat16_rn((float)(((double)xt_[k] - xnew) / (double)sigma));
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,
+                          cudaStream_t stream) {
+  const long total = (long)B * Tpad * 24;
+  if (total == 0) return ACE_OK;
+  concat_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ctx, xt, out, B, T, Tpad);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, const bf16* scale_tab,
+                         const bf16* shift_t, const bf16* scale_t, long t_ld, bf16* out, int rows,
+                         int D, int rows_per_batch, float eps, cudaStream_t stream) {
+  ACE_REQUIRE(D % 8 == 0, "adaln_rmsnorm: D %d must be a multiple of 8", D);
+  if (rows == 0) return ACE_OK;
+  adaln_rmsnorm_kernel<<<rows, 256, 0, stream>>>(h, w, shift_tab, scale_tab, shift_t, scale_t, t_ld,
+                                                 out, D, rows_per_batch, eps);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_gate_table(const bf16* tables, const bf16* tproj, bf16* out, int L, int B, int D,
+                      cudaStream_t stream) {
+  const long total = (long)L * B * 2 * (D / 8);
+  gate_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tables, tproj, out, L, B, D);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_time_embed(const TimeEmbedWeights& w, const float* t, int B, int D, bf16* scratch,
+                      bf16* temb, bf16* tproj, const bf16* add_temb, const bf16* add_proj,
+                      cudaStream_t stream) {
+  ACE_REQUIRE(B >= 1 && B <= TE_MAXB, "time_embed: batch %d exceeds %d", B, TE_MAXB);
+  ACE_REQUIRE(D % 256 == 0, "time_embed: D %d must be a multiple of 256", D);
+  bf16* e = scratch;                  // [B, 256]
+  bf16* x1 = scratch + (long)B * 256;  // [B, D]
+  bf16* s2 = x1 + (long)B * D;        // [B, D] silu(temb)
+  sinusoid_kernel<<<B, 128, 0, stream>>>(t, e, B);
+  gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w1, w.b1, e, B, 256, D, 1, nullptr, 0, x1, nullptr);
+  // y = temb_t + temb_r (what the model uses), y2 = SiLU(temb_t) (what time_proj consumes)
+  gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w2, w.b2, x1, B, D, D, 2, add_temb, 0, temb, s2);
+  gemv_kernel<<<ceil_div(6 * D, 8), 256, 0, stream>>>(w.wp, w.bp, s2, B, D, 6 * D, 0, add_proj, 0, tproj,
+                                                     nullptr);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStream_t stream) {
+  if (S == 0) return ACE_OK;
+  rope_tables_kernel<<<ceil_div(S * 64, 256), 256, 0, stream>>>(cos_tab, sin_tab, S, theta);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream) {
+  ACE_REQUIRE(n % 8 == 0, "euler: n must be a multiple of 8");
+  if (n == 0) return ACE_OK;
+  euler_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, dt, n / 8);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_sde(bf16* xt, const bf16* vt, const bf16* eps, float t_cur, float t_next, long n,
+               cudaStream_t stream) {
+  ACE_REQUIRE(n % 8 == 0, "sde: n must be a multiple of 8");
+  if (n == 0) return ACE_OK;
+  sde_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, eps, t_cur, t_next, n / 8);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum, int first_update,
+               float momentum_coef, float norm_threshold, float guidance_scale, bf16* vt_out, int B,
+               int T, cudaStream_t stream) {
+  if (B == 0 || T == 0) return ACE_OK;
+  apg_kernel<<<B, 1024, 0, stream>>>(cond, uncond, momentum, first_update, momentum_coef,
+                                     norm_threshold, guidance_scale, vt_out, T);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma,
+               float guidance_scale, float angle_clip, bf16* vt_out, int B, int T,
+               cudaStream_t stream) {
+  const long frames = (long)B * T;
+  if (frames == 0) return ACE_OK;
+  adg_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, stream>>>(xt, cond, uncond, sigma, guidance_scale,
+                                                              angle_clip, vt_out, frames);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+}  // namespace ace

@@ -1,0 +1,64 @@
+// kernels.h — host-callable launchers of the non-GEMM kernels (attention, elementwise, codec).
+#pragma once
+
+#include "common.cuh"
+
+namespace ace {
+
+struct AttnParams {
+  const bf16* q;
+  const bf16* k;
+  const bf16* v;
+  bf16* o;
+  long ldq, ldk, ldv, ldo;  // row pitches in elements (token-major buffers)
+  int Sq, Skv;              // per batch item
+  int window;               // < 0: full attention, else |i - j| <= window
+  int group;                // query heads per KV head
+  float scale_log2;         // head_dim^-0.5 * log2(e)
+};
+int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t stream);
+
+// x[b, t, :] = [ctx[b, t, 0:128] | xt[b, t, 0:64]] for t < T, zeros for T <= t < Tpad
+int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,
+                          cudaStream_t stream);
+
+// out[r, :] = bf16( rmsnorm(h[r, :]) * w ) [* (1 + scale[b]) + shift[b]]
+//   with scale[b] = bf16(scale_tab + scale_t[b * t_ld ..]) and shift likewise when scale_tab != null
+//   (AdaLN: scale_shift_table + timestep_proj, modeling_acestep_v15_turbo.py:490-496, 1488-1493).
+int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, const bf16* scale_tab,
+                         const bf16* shift_t, const bf16* scale_t, long t_ld, bf16* out, int rows,
+                         int D, int rows_per_batch, float eps, cudaStream_t stream);
+
+// gate[b, :] = bf16(table[idx, :] + tproj[b, idx, :]) for every layer: out [L, B, 2, D] holding
+// (gate_msa, c_gate_msa) so GEMM epilogues read one contiguous vector per (layer, batch).
+int launch_gate_table(const bf16* tables /*[L,6,D]*/, const bf16* tproj /*[B,6,D]*/, bf16* out,
+                      int L, int B, int D, cudaStream_t stream);
+
+// Timestep embedding (TimestepEmbedding.forward): sinusoid -> linear_1 -> SiLU -> linear_2 -> temb;
+// SiLU -> time_proj -> proj.  Weights bf16 row-major [out, in].
+struct TimeEmbedWeights {
+  const bf16 *w1, *b1, *w2, *b2, *wp, *bp;
+};
+int launch_time_embed(const TimeEmbedWeights& w, const float* t /*[B] device*/, int B, int D,
+                      bf16* scratch /*[B, 256 + 2D]*/, bf16* temb /*[B, D]*/, bf16* tproj /*[B, 6D]*/,
+                      const bf16* add_temb, const bf16* add_proj, cudaStream_t stream);
+
+// RoPE tables: cos/sin [S, 64] bf16 (fp32 math, then rounded — Qwen3RotaryEmbedding)
+int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStream_t stream);
+
+// ---- sampler-side elementwise ------------------------------------------------------------------
+// xt <- bf16(xt - bf16(vt * dt))       (Euler, base :1977-1979 / turbo :1985-1991, :1975-1977)
+int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream);
+// xt <- bf16(t_next * eps + (1 - t_next) * bf16(xt - bf16(vt * t_cur)))   (SDE re-noise)
+int launch_sde(bf16* xt, const bf16* vt, const bf16* eps, float t_cur, float t_next, long n,
+               cudaStream_t stream);
+// APG (apg_guidance.py:33-56, dims=[1]): vt_out = cond + (scale-1) * orth(clip(momentum(diff)))
+int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum /*[B,T,64] running average*/,
+               int first_update, float momentum_coef, float norm_threshold, float guidance_scale,
+               bf16* vt_out, int B, int T, cudaStream_t stream);
+// ADG (apg_guidance.py:107-180) per (b, t) frame over the 64 channels
+int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma,
+               float guidance_scale, float angle_clip, bf16* vt_out, int B, int T,
+               cudaStream_t stream);
+
+}  // namespace ace

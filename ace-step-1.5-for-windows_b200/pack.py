@@ -1,0 +1,180 @@
+"""Weight packers: reference `state_dict()` tensors -> the blobs libacestep_b200 consumes.
+
+Same role as the reference's MLX converters (acestep/models/mlx/dit_convert.py:11-66,
+vae_convert.py:18-132): walk the PyTorch module's state dict, fold weight-norm, pre-concatenate
+fused projections and re-lay convolution kernels for the target backend.  The element order here
+must match the walkers in csrc/dit.cu (ace_dit_create) and csrc/vae.cu (walk_blob).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+
+
+def _get(sd: Dict[str, torch.Tensor], key: str) -> torch.Tensor:
+    if key not in sd:
+        raise KeyError(f"state_dict is missing '{key}'")
+    return sd[key].detach().to("cpu")
+
+
+# --------------------------------------------------------------------------------------------
+# DiT
+# --------------------------------------------------------------------------------------------
+def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> torch.Tensor:
+    """Returns a 1-D bf16 CPU tensor in the order ace_dit_create walks.
+
+    `sd` is `model.decoder.state_dict()` of the reference AceStepDiTModel
+    (modeling_acestep_v15_turbo.py:1237-1298); `prefix` e.g. "decoder." for the full model dict.
+    """
+    g = lambda k: _get(sd, prefix + k).float()
+    parts: List[torch.Tensor] = []
+    w_in = g("proj_in.1.weight")  # [D, 192, 2] -> [D, (k, c)]
+    parts += [w_in.permute(0, 2, 1).reshape(w_in.shape[0], -1), g("proj_in.1.bias")]
+    for te in ("time_embed.", "time_embed_r."):
+        parts += [g(te + "linear_1.weight"), g(te + "linear_1.bias"), g(te + "linear_2.weight"),
+                  g(te + "linear_2.bias"), g(te + "time_proj.weight"), g(te + "time_proj.bias")]
+    parts += [g("condition_embedder.weight"), g("condition_embedder.bias"), g("norm_out.weight"),
+              g("scale_shift_table").reshape(2, -1)]
+    w_out = g("proj_out.1.weight")  # [D, 64, 2] -> [(k, o), D]
+    parts += [w_out.permute(2, 1, 0).reshape(-1, w_out.shape[0]), g("proj_out.1.bias")]
+    parts += [torch.stack([g(f"layers.{l}.scale_shift_table").reshape(6, -1) for l in range(num_layers)])]
+    for l in range(num_layers):
+        p = f"layers.{l}."
+        gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
+        inter, d = gate.shape
+        gate_up = torch.stack([gate.view(inter // 64, 64, d), up.view(inter // 64, 64, d)], dim=1).reshape(2 * inter, d)
+        parts += [
+            g(p + "self_attn_norm.weight"), g(p + "cross_attn_norm.weight"), g(p + "mlp_norm.weight"),
+            torch.cat([g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"),
+                       g(p + "self_attn.v_proj.weight")], dim=0),
+            g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight"), g(p + "self_attn.o_proj.weight"),
+            g(p + "cross_attn.q_proj.weight"),
+            torch.cat([g(p + "cross_attn.k_proj.weight"), g(p + "cross_attn.v_proj.weight")], dim=0),
+            g(p + "cross_attn.q_norm.weight"), g(p + "cross_attn.k_norm.weight"), g(p + "cross_attn.o_proj.weight"),
+            gate_up, g(p + "mlp.down_proj.weight"),
+        ]
+    return torch.cat([t.reshape(-1) for t in parts]).to(torch.bfloat16).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# VAE
+# --------------------------------------------------------------------------------------------
+def fold_weight_norm(sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:
+    """w = g * v / ||v|| over all dims but 0 (torch weight_norm; mlx/vae_convert.py:18-34)."""
+    if name + ".weight" in sd:
+        return _get(sd, name + ".weight").float()
+    gsc, v = _get(sd, name + ".weight_g").float(), _get(sd, name + ".weight_v").float()
+    nrm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return gsc * v / nrm
+
+
+def folded_vae_state(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """State dict with weight-norm folded and every tensor rounded through bf16 (fp32 storage):
+    exactly the parameter values the CUDA path computes with (used by the parity tests)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k in sd:
+        if k.endswith(".weight_g"):
+            base = k[: -len(".weight_g")]
+            out[base + ".weight"] = fold_weight_norm(sd, base).to(torch.bfloat16).float()
+        elif k.endswith(".weight_v"):
+            continue
+        else:
+            out[k] = _get(sd, k).to(torch.bfloat16).float()
+    return out
+
+
+class _Blob:
+    def __init__(self):
+        self.chunks: List[bytes] = []
+        self.off = 0
+
+    def _align(self):
+        pad = (-self.off) % 256
+        if pad:
+            self.chunks.append(b"\0" * pad)
+            self.off += pad
+
+    def bf16(self, t: torch.Tensor):
+        self._align()
+        b = t.contiguous().to(torch.bfloat16).view(torch.int16).numpy().tobytes()
+        self.chunks.append(b)
+        self.off += len(b)
+
+    def f32(self, t: torch.Tensor):
+        self._align()
+        b = t.contiguous().to(torch.bfloat16).float().numpy().tobytes()  # bf16-representable values
+        self.chunks.append(b)
+        self.off += len(b)
+
+    def raw_f32(self, t: torch.Tensor):
+        self._align()
+        b = t.contiguous().float().numpy().tobytes()
+        self.chunks.append(b)
+        self.off += len(b)
+
+    def finish(self) -> torch.Tensor:
+        self._align()
+        import numpy as np
+
+        return torch.from_numpy(np.frombuffer(b"".join(self.chunks), dtype=np.uint8).copy())
+
+
+def pack_vae(sd: Dict[str, torch.Tensor], ratios: Sequence[int], channel_multiples: Sequence[int],
+             encoder_hidden: int = 128, decoder_channels: int = 128) -> torch.Tensor:
+    """Returns a uint8 CPU tensor laid out as csrc/vae.cu:walk_blob expects.
+
+    `sd` is `AutoencoderOobleck.state_dict()` (keys encoder./decoder.*, weight_g/weight_v pairs).
+    """
+    b = _Blob()
+    n = len(ratios)
+
+    def conv(name, bias=True):  # Conv1d [Cout, Cin, K] -> tap-major [Cout, K*Cin]
+        w = fold_weight_norm(sd, name)
+        b.bf16(w.permute(0, 2, 1).reshape(w.shape[0], -1))
+        if bias:
+            b.f32(_get(sd, name + ".bias"))
+
+    def conv_t(name, s):  # ConvTranspose1d [Cin, Cout, 2s] -> [(p, co), (tap, ci)], k = tap*s + p
+        w = fold_weight_norm(sd, name)
+        cin, cout, k = w.shape
+        assert k == 2 * s
+        b.bf16(w.view(cin, cout, 2, s).permute(3, 1, 2, 0).reshape(s * cout, 2 * cin))
+        b.f32(_get(sd, name + ".bias"))
+
+    def snake(name):
+        alpha = _get(sd, name + ".alpha").to(torch.bfloat16).float().reshape(-1)
+        beta = _get(sd, name + ".beta").to(torch.bfloat16).float().reshape(-1)
+        b.raw_f32(torch.exp(alpha))
+        b.raw_f32(1.0 / (torch.exp(beta) + 1e-9))
+
+    def res_unit(name):
+        snake(name + ".snake1")
+        conv(name + ".conv1")
+        snake(name + ".snake2")
+        conv(name + ".conv2")
+
+    # decoder (upsampling ratios = reversed downsampling ratios)
+    conv("decoder.conv1")
+    for i in range(n):
+        s = ratios[n - 1 - i]
+        blk = f"decoder.block.{i}"
+        snake(blk + ".snake1")
+        conv_t(blk + ".conv_t1", s)
+        for j in (1, 2, 3):
+            res_unit(f"{blk}.res_unit{j}")
+    snake("decoder.snake1")
+    w2 = fold_weight_norm(sd, "decoder.conv2")  # [2, C, 7] -> [2][7][C]
+    b.f32(w2.permute(0, 2, 1))
+    # encoder
+    b.f32(fold_weight_norm(sd, "encoder.conv1"))  # [C][2][7]
+    b.f32(_get(sd, "encoder.conv1.bias"))
+    for i in range(n):
+        blk = f"encoder.block.{i}"
+        for j in (1, 2, 3):
+            res_unit(f"{blk}.res_unit{j}")
+        snake(blk + ".snake1")
+        conv(blk + ".conv1")
+    snake("encoder.snake1")
+    conv("encoder.conv2")
+    return b.finish()

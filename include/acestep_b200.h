@@ -1,0 +1,153 @@
+/* acestep_b200.h — C ABI of libacestep_b200.so (B200 / sm_100a only).
+ *
+ * Drop-in boundary for the ONE hot path of ACE-Step 1.5: the diffusion-transformer denoising loop
+ * and the Oobleck VAE decode/encode.  The reference is 100 % Python and has no FFI of its own; the
+ * entry points below are what its backend seam binds (the seam the MLX backend already uses):
+ *
+ *   DiT   : AceStepHandler._mlx_run_diffusion            acestep/core/generation/handler/diffusion.py:18-140
+ *           selected in _execute_service_generate_diffusion   handler/service_generate_execute.py:144-194
+ *           replaces model.generate_audio                 models/turbo/modeling_acestep_v15_turbo.py:1780-2001
+ *                                                         models/base/modeling_acestep_v15_base.py:1783-1989
+ *   codec : AceStepHandler.tiled_decode / _mlx_vae_decode handler/vae_decode.py:16-48, mlx_vae_decode_native.py:31-76
+ *           AceStepHandler.tiled_encode / _mlx_vae_encode_sample   handler/vae_encode.py:15-43
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive AceStatus otherwise; ace_last_error() gives
+ *     the message of the calling thread's last failure.  No exceptions, no exit().
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  bf16 is passed as uint16_t.
+ *   - the caller owns inputs, outputs and the workspace; a handle owns only its packed weights,
+ *     the cross-attention K/V cache (inside the bound workspace) and its CUDA graphs.
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream` (0 = default stream);
+ *     nothing synchronises unless documented.  A handle is single-caller (like the reference's
+ *     handler, acestep_v15_pipeline.py:395-399) but independent handles may run concurrently.
+ *   - there is NO CPU fallback: every entry point fails with ACE_ERR_CUDA on a non-sm_100 device.
+ */
+#ifndef ACESTEP_B200_H_
+#define ACESTEP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum AceStatus {
+  ACE_STATUS_OK = 0,
+  ACE_STATUS_INVALID = 1,
+  ACE_STATUS_CUDA = 2,
+  ACE_STATUS_NOMEM = 3,
+  ACE_STATUS_UNSUPPORTED = 4
+} AceStatus;
+
+const char* ace_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int ace_abi_version(void);
+/* Checks that device `device` is compute capability 10.x and makes it current. */
+int ace_init(int device);
+
+/* ------------------------------------------------------------------------------------------ */
+/* DiT (AceStepDiTModel, turbo modeling :1237-1504; config configuration_acestep_v15.py:148-260) */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct AceDitConfig {
+  int hidden_size;          /* 2048; multiple of 256 */
+  int intermediate_size;    /* 6144; multiple of 64 */
+  int num_layers;           /* 24 */
+  int num_heads;            /* 16 */
+  int num_kv_heads;         /* 8 */
+  int head_dim;             /* must be 128 */
+  int sliding_window;       /* 128 */
+  int layer_is_sliding[64]; /* per layer: 1 = +-window band, 0 = full attention */
+  float rope_theta;         /* 1e6 */
+  float rms_eps;            /* 1e-6 */
+} AceDitConfig;
+
+typedef struct AceDit AceDit;
+
+/* Number of bf16 elements ace_dit_create expects in `weights` (layout: DESIGN.md "Packed DiT weights",
+ * produced by acestep_b200.pack.pack_dit from decoder.state_dict(), cf. models/mlx/dit_convert.py:33-66). */
+size_t ace_dit_packed_elems(const AceDitConfig* cfg);
+/* `weights` may be a host or a device pointer; it is copied. */
+int ace_dit_create(AceDit** out, const AceDitConfig* cfg, const uint16_t* weights, size_t n_elems);
+void ace_dit_destroy(AceDit* dit);
+
+/* Workspace for an effective batch `bc` (songs x (2 if CFG)), `t` latent frames, `e` condition tokens. */
+size_t ace_dit_workspace_bytes(const AceDit* dit, int bc, int t, int e);
+/* Binds shapes + workspace: encodes all TMA descriptors and (unless ACE_NO_GRAPH=1) captures the
+ * denoising step into a CUDA graph on first use.  Re-bind when bc / t / e or the workspace change. */
+int ace_dit_bind(AceDit* dit, int bc, int t, int e, void* d_workspace, size_t workspace_bytes);
+
+/* condition_embedder + cross-attention K/V of all layers for d_enc [bc, e, hidden] (bf16); replaces
+ * the EncoderDecoderCache fill of the first decoder call (turbo modeling :307-330, 1356).
+ * `bc_offset`/`bc_count` select which batch rows are written (CFG: cond rows then null rows). */
+int ace_dit_set_condition(AceDit* dit, const uint16_t* d_enc, void* stream);
+
+/* One velocity prediction: d_xt [bc,t,64], d_ctx [bc,t,128] (bf16), h_t [bc] (host floats, already
+ * rounded to the model dtype by the caller) -> d_vt [bc,t,64] (bf16). */
+int ace_dit_step(AceDit* dit, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t,
+                 uint16_t* d_vt, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Sampler update kernels (base :1945-1979, turbo :1975-1991, apg_guidance.py)                  */
+/* ------------------------------------------------------------------------------------------ */
+/* xt <- xt - vt * dt over n bf16 elements (n % 8 == 0) */
+int ace_euler_step(uint16_t* d_xt, const uint16_t* d_vt, float dt, size_t n, void* stream);
+/* xt <- t_next * eps + (1 - t_next) * (xt - vt * t_cur) */
+int ace_sde_step(uint16_t* d_xt, const uint16_t* d_vt, const uint16_t* d_eps, float t_cur,
+                 float t_next, size_t n, void* stream);
+/* APG over [b, t, 64]: d_momentum is the persistent running average (bf16, same shape);
+ * first_update != 0 on the first guided step of a run. */
+int ace_apg(const uint16_t* d_cond, const uint16_t* d_uncond, uint16_t* d_momentum, int first_update,
+            float momentum, float norm_threshold, float guidance_scale, uint16_t* d_out, int b, int t,
+            void* stream);
+/* ADG over [b, t, 64] with per-frame angles. */
+int ace_adg(const uint16_t* d_xt, const uint16_t* d_cond, const uint16_t* d_uncond, float sigma,
+            float guidance_scale, float angle_clip, uint16_t* d_out, int b, int t, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Oobleck VAE (diffusers.AutoencoderOobleck; structure acestep/models/mlx/vae_model.py:149-230) */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct AceVaeConfig {
+  int num_stages;           /* 5 */
+  int ratios[8];            /* encoder downsampling ratios, e.g. {2,4,4,6,10}; decoder uses reverse */
+  int channel_multiples[8]; /* {1,2,4,8,16} */
+  int encoder_hidden;       /* 128 */
+  int decoder_channels;     /* 128 */
+  int latent_channels;      /* 64 */
+  int audio_channels;       /* 2 */
+} AceVaeConfig;
+
+typedef struct AceVae AceVae;
+
+size_t ace_vae_packed_bytes(const AceVaeConfig* cfg);
+/* `weights`: packed blob from acestep_b200.pack.pack_vae (weight-norm folded, tap-major bf16 conv
+ * matrices, fp32 bias / Snake tables); host or device pointer; copied. */
+int ace_vae_create(AceVae** out, const AceVaeConfig* cfg, const void* weights, size_t n_bytes);
+void ace_vae_destroy(AceVae* vae);
+
+size_t ace_vae_decode_workspace_bytes(const AceVae* vae, int frames);
+size_t ace_vae_encode_workspace_bytes(const AceVae* vae, int samples);
+/* d_z [frames, 64] bf16 (channels-last == the sampler's [T,64] layout) -> d_wav [2, frames*hop] fp32. */
+int ace_vae_decode(AceVae* vae, const uint16_t* d_z, int frames, float* d_wav, void* d_workspace,
+                   size_t workspace_bytes, void* stream);
+/* d_wav [2, samples] fp32 (samples % hop == 0), d_eps [samples/hop, 64] bf16 posterior noise (may be
+ * NULL: return the mean) -> d_z [samples/hop, 64] bf16 = mean + (softplus(scale) + 1e-4) * eps. */
+int ace_vae_encode(AceVae* vae, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Test / bring-up hooks (never used by the product path)                                       */
+/* ------------------------------------------------------------------------------------------ */
+/* 1: route every GEMM through the scalar reference kernels (validates epilogues independently). */
+void ace_debug_set_gemm_reference(int on);
+/* D = A[m,k] * B[n,k]^T + bias, bf16 in/out, through the tcgen05 path (tests/bench). */
+int ace_debug_linear(const uint16_t* d_a, const uint16_t* d_b, const uint16_t* d_bias, uint16_t* d_out,
+                     int m, int n, int k, void* stream);
+/* softmax(q k^T * scale [band]) v on token-major buffers (tests). */
+int ace_debug_attention(const uint16_t* d_q, const uint16_t* d_k, const uint16_t* d_v, uint16_t* d_o,
+                        int batch, int heads, int kv_heads, int sq, int skv, int window, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACESTEP_B200_H_ */

@@ -99,19 +99,23 @@ def attention(q, k, v, mask, n_rep: int, scaling: float) -> torch.Tensor:
     return torch.matmul(p, v)
 
 
-def timestep_sinusoid(t: torch.Tensor, dim: int = 256, scale: float = 1000.0, max_period: float = 10000.0):
+def timestep_sinusoid(t: torch.Tensor, dim: int = 256, scale: float = 1000.0, max_period: float = 10000.0,
+                      bf16_time: bool = False):
     """TimestepEmbedding.timestep_embedding (:222-243).  NOTE the `t * scale` happens in t's own
-    dtype before the .float() (so a bf16 t gives the bf16-rounded 1000*t)."""
-    t = t * scale
+    dtype before the .float() (so a bf16 t gives the bf16-rounded 1000*t).  `bf16_time=True`
+    reproduces that quirk of the reference's bf16 execution while the rest stays fp32."""
+    t = (t.to(torch.bfloat16) * scale).float() if bf16_time else t * scale
     half = dim // 2
     freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
-def timestep_embedding(w: Dict[str, torch.Tensor], prefix: str, t: torch.Tensor):
+def timestep_embedding(w: Dict[str, torch.Tensor], prefix: str, t: torch.Tensor, bf16_time: bool = False):
     """TimestepEmbedding.forward (:245-251) -> (temb [B,D], proj [B,6,D])."""
-    e = timestep_sinusoid(t).to(t.dtype)
+    e = timestep_sinusoid(t, bf16_time=bf16_time).to(t.dtype)
+    if bf16_time:
+        e = e.to(torch.bfloat16).to(t.dtype)  # t_freq.to(t.dtype) with a bf16 t (:247)
     x = F.linear(e, w[prefix + "linear_1.weight"], w[prefix + "linear_1.bias"])
     x = F.silu(x)
     temb = F.linear(x, w[prefix + "linear_2.weight"], w[prefix + "linear_2.bias"])
@@ -175,14 +179,15 @@ class CrossCache:
 
 
 def dit_forward(w: Dict[str, torch.Tensor], cfg: DiTConfig, xt: torch.Tensor, t: torch.Tensor,
-                ctx: torch.Tensor, enc: torch.Tensor, cache: Optional[CrossCache] = None) -> torch.Tensor:
+                ctx: torch.Tensor, enc: torch.Tensor, cache: Optional[CrossCache] = None,
+                bf16_time: bool = False) -> torch.Tensor:
     """AceStepDiTModel.forward (:1300-1504) with timestep_r == timestep (inference).
 
     xt [B,T,64], t [B], ctx [B,T,128], enc [B,E,hidden] -> vt [B,T,64].
     """
     B, T, _ = xt.shape
-    temb_t, proj_t = timestep_embedding(w, "time_embed.", t)
-    temb_r, proj_r = timestep_embedding(w, "time_embed_r.", t - t)
+    temb_t, proj_t = timestep_embedding(w, "time_embed.", t, bf16_time)
+    temb_r, proj_r = timestep_embedding(w, "time_embed_r.", t - t, bf16_time)
     temb, tproj = temb_t + temb_r, proj_t + proj_r
 
     x = torch.cat([ctx, xt], dim=-1)  # [ctx(128) | xt(64)] (:1344)
