@@ -58,6 +58,11 @@ SIGNATURES = {
     "ace_vae_encode_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
     "ace_vae_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "ace_vae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "ace_dit_io_slots": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "ace_launch_count": (C.c_uint64, []),
+    "ace_profile_start": (None, []),
+    "ace_profile_stop": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int)]),
     "ace_debug_set_gemm_reference": (None, [C.c_int]),
     "ace_debug_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ace_debug_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

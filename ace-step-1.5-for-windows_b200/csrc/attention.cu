@@ -251,7 +251,14 @@ int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t str
   }
   if (p.Sq <= 0 || p.Skv <= 0 || batch <= 0) return ACE_OK;
   dim3 grid(ceil_div(p.Sq, BM), heads, batch);
+  // algorithmic work: 4 * Sq * (keys a query may see) * head_dim per head
+  const double keys = p.window >= 0 ? (double)(p.Skv < 2 * p.window + 1 ? p.Skv : 2 * p.window + 1)
+                                    : (double)p.Skv;
+  const int kvh = heads / p.group;
+  prof_begin(PROF_ATTN, 4.0 * p.Sq * keys * HD * heads * batch,
+             2.0 * HD * batch * ((double)p.Sq * heads * 2 + (double)p.Skv * kvh * 2), stream);
   attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
+  prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -59,6 +59,20 @@ const char* get_error();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ----------------------------------------------------------------------------
+// launch accounting + opt-in per-launch event profiling (runtime.cu)
+//   every kernel launch site brackets itself with prof_begin / prof_end; prof_begin also bumps
+//   the launch counter.  When profiling is off this is two predictable branches.
+// ----------------------------------------------------------------------------
+enum ProfCat : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ELEM = 2, PROF_CONV_SIMT = 3, PROF_NCAT = 4 };
+void add_launches(uint64_t n);
+uint64_t launch_count();
+void prof_begin(int cat, double flops, double bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+bool prof_active();
+void prof_start();
+int prof_stop(float* ms, double* flops, double* bytes, int* launches);
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------
 // bf16 helpers

@@ -57,6 +57,7 @@ struct AceDit {
   GemmPlan plan_in, plan_out;
   std::vector<LayerPlans> lp;
   cudaGraphExec_t graph = nullptr;
+  uint64_t graph_nodes = 0;
   bool use_graph = true;
   bool rope_ready = false;
 };
@@ -186,6 +187,21 @@ int ace_init(int device) {
 }
 
 void ace_debug_set_gemm_reference(int on) { set_gemm_debug_reference(on != 0); }
+
+uint64_t ace_launch_count(void) { return launch_count(); }
+void ace_profile_start(void) { prof_start(); }
+int ace_profile_stop(float* ms, double* flops, double* bytes, int* launches) {
+  ACE_REQUIRE(ms && flops && bytes && launches, "ace_profile_stop: null argument");
+  return prof_stop(ms, flops, bytes, launches);
+}
+
+int ace_dit_io_slots(AceDit* d, uint16_t** xt, uint16_t** ctx, uint16_t** vt) {
+  ACE_REQUIRE(d && d->ws, "ace_dit_io_slots: handle not bound");
+  if (xt) *xt = (uint16_t*)d->xin;
+  if (ctx) *ctx = (uint16_t*)d->ctxin;
+  if (vt) *vt = (uint16_t*)d->vout;
+  return ACE_OK;
+}
 
 size_t ace_dit_packed_elems(const AceDitConfig* c) {
   const size_t D = c->hidden_size, I = c->intermediate_size, L = c->num_layers;
@@ -395,9 +411,11 @@ int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const f
     ACE_CUDA_CHECK(cudaMemcpyAsync(d->ctxin, d_ctx, nx * 4, cudaMemcpyDeviceToDevice, st));
   TVals tv;
   for (int i = 0; i < 16; ++i) tv.v[i] = i < d->Bc ? h_t[i] : 0.f;
+  prof_begin(PROF_ELEM, 0.0, 64.0, st);
   set_t_kernel<<<1, 32, 0, st>>>(d->t_dev, tv, d->Bc);
+  prof_end(st);
 
-  const bool graph_ok = d->use_graph && !gemm_debug_reference();
+  const bool graph_ok = d->use_graph && !gemm_debug_reference() && !prof_active();
   if (!graph_ok) {
     ACE_PROPAGATE(enqueue_forward(d, st));
   } else {
@@ -412,7 +430,10 @@ int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const f
       cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
       int s = ACE_OK;
       if (e == cudaSuccess) {
+        const uint64_t before = launch_count();
         s = enqueue_forward(d, cs);
+        d->graph_nodes = launch_count() - before;
+        add_launches(0 - d->graph_nodes);  // captured, not executed
         e = cudaStreamEndCapture(cs, &g);
       }
       if (e == cudaSuccess && s == ACE_OK) e = cudaGraphInstantiate(&d->graph, g, 0);
@@ -425,6 +446,7 @@ int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const f
       }
     } else {
       ACE_CUDA_CHECK(cudaGraphLaunch(d->graph, st));
+      add_launches(d->graph_nodes);
     }
   }
   if ((bf16*)d_vt != d->vout)

@@ -351,11 +351,21 @@ __global__ void adg_kernel(const bf16* __restrict__ xt, const bf16* __restrict__
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// Launchers.  ELEM(bytes, launch) brackets a launch for the launch counter / event profiler with
+// its algorithmic HBM bytes (these kernels are all memory- or latency-bound).
+#define ELEM(bytes, ...)                                 \
+  do {                                                   \
+    prof_begin(PROF_ELEM, 0.0, (double)(bytes), stream); \
+    __VA_ARGS__;                                         \
+    prof_end(stream);                                    \
+  } while (0)
+
 int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,
                           cudaStream_t stream) {
   const long total = (long)B * Tpad * 24;
   if (total == 0) return ACE_OK;
-  concat_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ctx, xt, out, B, T, Tpad);
+  ELEM(total * 32, concat_patches_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ctx, xt, out, B, T,
+                                                                                          Tpad));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -365,8 +375,9 @@ int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, co
                          int D, int rows_per_batch, float eps, cudaStream_t stream) {
   ACE_REQUIRE(D % 8 == 0, "adaln_rmsnorm: D %d must be a multiple of 8", D);
   if (rows == 0) return ACE_OK;
-  adaln_rmsnorm_kernel<<<rows, 256, 0, stream>>>(h, w, shift_tab, scale_tab, shift_t, scale_t, t_ld,
-                                                 out, D, rows_per_batch, eps);
+  ELEM((double)rows * D * 4, adaln_rmsnorm_kernel<<<rows, 256, 0, stream>>>(h, w, shift_tab, scale_tab, shift_t,
+                                                                         scale_t, t_ld, out, D,
+                                                                         rows_per_batch, eps));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -374,7 +385,8 @@ int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, co
 int launch_gate_table(const bf16* tables, const bf16* tproj, bf16* out, int L, int B, int D,
                       cudaStream_t stream) {
   const long total = (long)L * B * 2 * (D / 8);
-  gate_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tables, tproj, out, L, B, D);
+  ELEM(total * 48, gate_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(tables, tproj, out, L, B,
+                                                                                      D));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -387,19 +399,21 @@ int launch_time_embed(const TimeEmbedWeights& w, const float* t, int B, int D, b
   bf16* e = scratch;                  // [B, 256]
   bf16* x1 = scratch + (long)B * 256;  // [B, D]
   bf16* s2 = x1 + (long)B * D;        // [B, D] silu(temb)
-  sinusoid_kernel<<<B, 128, 0, stream>>>(t, e, B);
-  gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w1, w.b1, e, B, 256, D, 1, nullptr, 0, x1, nullptr);
+  ELEM(B * 256 * 2, sinusoid_kernel<<<B, 128, 0, stream>>>(t, e, B));
+  ELEM(2.0 * D * 256, gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w1, w.b1, e, B, 256, D, 1, nullptr, 0, x1,
+                                                                    nullptr));
   // y = temb_t + temb_r (what the model uses), y2 = SiLU(temb_t) (what time_proj consumes)
-  gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w2, w.b2, x1, B, D, D, 2, add_temb, 0, temb, s2);
-  gemv_kernel<<<ceil_div(6 * D, 8), 256, 0, stream>>>(w.wp, w.bp, s2, B, D, 6 * D, 0, add_proj, 0, tproj,
-                                                     nullptr);
+  ELEM(2.0 * D * D, gemv_kernel<<<ceil_div(D, 8), 256, 0, stream>>>(w.w2, w.b2, x1, B, D, D, 2, add_temb, 0, temb,
+                                                                  s2));
+  ELEM(12.0 * D * D, gemv_kernel<<<ceil_div(6 * D, 8), 256, 0, stream>>>(w.wp, w.bp, s2, B, D, 6 * D, 0, add_proj,
+                                                                       0, tproj, nullptr));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
 
 int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStream_t stream) {
   if (S == 0) return ACE_OK;
-  rope_tables_kernel<<<ceil_div(S * 64, 256), 256, 0, stream>>>(cos_tab, sin_tab, S, theta);
+  ELEM(S * 256, rope_tables_kernel<<<ceil_div(S * 64, 256), 256, 0, stream>>>(cos_tab, sin_tab, S, theta));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -407,7 +421,7 @@ int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStr
 int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream) {
   ACE_REQUIRE(n % 8 == 0, "euler: n must be a multiple of 8");
   if (n == 0) return ACE_OK;
-  euler_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, dt, n / 8);
+  ELEM(n * 6, euler_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, dt, n / 8));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -416,7 +430,7 @@ int launch_sde(bf16* xt, const bf16* vt, const bf16* eps, float t_cur, float t_n
                cudaStream_t stream) {
   ACE_REQUIRE(n % 8 == 0, "sde: n must be a multiple of 8");
   if (n == 0) return ACE_OK;
-  sde_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, eps, t_cur, t_next, n / 8);
+  ELEM(n * 8, sde_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, stream>>>(xt, vt, eps, t_cur, t_next, n / 8));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -425,8 +439,9 @@ int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum, int first_u
                float momentum_coef, float norm_threshold, float guidance_scale, bf16* vt_out, int B,
                int T, cudaStream_t stream) {
   if (B == 0 || T == 0) return ACE_OK;
-  apg_kernel<<<B, 1024, 0, stream>>>(cond, uncond, momentum, first_update, momentum_coef,
-                                     norm_threshold, guidance_scale, vt_out, T);
+  ELEM((double)B * T * 64 * 10, apg_kernel<<<B, 1024, 0, stream>>>(cond, uncond, momentum, first_update,
+                                                               momentum_coef, norm_threshold, guidance_scale,
+                                                               vt_out, T));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -436,8 +451,9 @@ int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma
                cudaStream_t stream) {
   const long frames = (long)B * T;
   if (frames == 0) return ACE_OK;
-  adg_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, stream>>>(xt, cond, uncond, sigma, guidance_scale,
-                                                              angle_clip, vt_out, frames);
+  ELEM(frames * 64 * 8, adg_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, stream>>>(xt, cond, uncond, sigma,
+                                                                                 guidance_scale, angle_clip,
+                                                                                 vt_out, frames));
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -264,6 +264,7 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
                                                    n_pad, m_pad, n_pad);
     gemm_ref_epilogue_kernel<BN, Epi>
         <<<dim3(m_pad / GEMM_BM, n_pad / BN), 128, 0, stream>>>(scratch, n_pad, p.shp, epi);
+    add_launches(2);
     ACE_CUDA_CHECK(cudaGetLastError());
     return ACE_OK;
   }
@@ -276,8 +277,14 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   }
   const int tiles = ceil_div(p.shp.M, GEMM_BM) * ceil_div(p.shp.N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
+  prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,
+             2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
+                    (double)p.shp.M * p.shp.N),
+             stream);
   gemm_tc_kernel<BN, STAGES, Epi><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p.tma_a, p.tma_b, p.shp,
                                                                            epi);
+  prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -30,6 +32,69 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---- launch accounting + per-launch event profiling -------------------------------------------
+struct ProfRec {
+  int cat;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+static uint64_t g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+void add_launches(uint64_t n) { g_launches += n; }
+uint64_t launch_count() { return g_launches; }
+bool prof_active() { return g_prof_on; }
+void prof_begin(int cat, double flops, double bytes, cudaStream_t st) {
+  ++g_launches;
+  if (!g_prof_on) return;
+  ProfRec r{cat, nullptr, nullptr, flops, bytes};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
+void prof_start() {
+  for (ProfRec& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+}
+// Sums per category: ms, flops, bytes, launches (arrays of PROF_NCAT).  Synchronises the device.
+int prof_stop(float* ms, double* flops, double* bytes, int* launches) {
+  g_prof_on = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  for (int c = 0; c < PROF_NCAT; ++c) {
+    ms[c] = 0.f;
+    flops[c] = bytes[c] = 0.0;
+    launches[c] = 0;
+  }
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cat >= 0 &&
+        r.cat < PROF_NCAT) {
+      ms[r.cat] += t;
+      flops[r.cat] += r.flops;
+      bytes[r.cat] += r.bytes;
+      launches[r.cat] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  if (e != cudaSuccess) {
+    set_error("profile stop: %s", cudaGetErrorString(e));
+    return ACE_ERR_CUDA;
+  }
+  return ACE_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -425,7 +425,9 @@ int ace_vae_decode(AceVae* v, const uint16_t* d_z, int frames, float* d_wav, voi
     ACE_CUDA_CHECK(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
+  prof_begin(PROF_CONV_SIMT, 2.0 * L * 14 * C, (double)L * (C * 2 + 8), st);
   final_conv_kernel<<<(unsigned)((L + 255) / 256), 256, smem, st>>>(xs, v->dec_conv2, d_wav, L, C);
+  prof_end(st);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -449,8 +451,10 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
   {
     const SnakeW& s1 = v->enc[0].ru[0].s1;
     const long total = L * (H / 8);
+    prof_begin(PROF_CONV_SIMT, 2.0 * L * 14 * H, (double)L * (8 + 4.0 * H), st);
     first_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_wav, v->enc_conv1_w, v->enc_conv1_b,
                                                                       s1.a, s1.ib, x, xs, L, H);
+    prof_end(st);
     ACE_CUDA_CHECK(cudaGetLastError());
   }
   for (int i = 0; i < n; ++i) {
@@ -479,7 +483,9 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
     ACE_PROPAGATE(conv_gemm(xs, L, Cin, Cin, v->enc_conv2, H, L, 3, sh3, e, st));
     const int Cz = v->cfg.latent_channels;
     const long tot = L * Cz;
+    prof_begin(PROF_ELEM, 0.0, (double)tot * 8, st);
     posterior_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(hs, (const bf16*)d_eps, (bf16*)d_z, L, Cz);
+    prof_end(st);
     ACE_CUDA_CHECK(cudaGetLastError());
   }
   return ACE_OK;

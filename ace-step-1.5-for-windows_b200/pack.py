@@ -15,7 +15,7 @@ import torch
 def _get(sd: Dict[str, torch.Tensor], key: str) -> torch.Tensor:
     if key not in sd:
         raise KeyError(f"state_dict is missing '{key}'")
-    return sd[key].detach().to("cpu")
+    return sd[key].detach()
 
 
 # --------------------------------------------------------------------------------------------
@@ -27,7 +27,7 @@ def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> 
     `sd` is `model.decoder.state_dict()` of the reference AceStepDiTModel
     (modeling_acestep_v15_turbo.py:1237-1298); `prefix` e.g. "decoder." for the full model dict.
     """
-    g = lambda k: _get(sd, prefix + k).float()
+    g = lambda k: _get(sd, prefix + k)
     parts: List[torch.Tensor] = []
     w_in = g("proj_in.1.weight")  # [D, 192, 2] -> [D, (k, c)]
     parts += [w_in.permute(0, 2, 1).reshape(w_in.shape[0], -1), g("proj_in.1.bias")]
@@ -54,7 +54,7 @@ def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> 
             g(p + "cross_attn.q_norm.weight"), g(p + "cross_attn.k_norm.weight"), g(p + "cross_attn.o_proj.weight"),
             gate_up, g(p + "mlp.down_proj.weight"),
         ]
-    return torch.cat([t.reshape(-1) for t in parts]).to(torch.bfloat16).contiguous()
+    return torch.cat([t.reshape(-1).to(torch.bfloat16) for t in parts]).contiguous()
 
 
 # --------------------------------------------------------------------------------------------
@@ -97,19 +97,19 @@ class _Blob:
 
     def bf16(self, t: torch.Tensor):
         self._align()
-        b = t.contiguous().to(torch.bfloat16).view(torch.int16).numpy().tobytes()
+        b = t.detach().cpu().contiguous().to(torch.bfloat16).view(torch.int16).numpy().tobytes()
         self.chunks.append(b)
         self.off += len(b)
 
     def f32(self, t: torch.Tensor):
         self._align()
-        b = t.contiguous().to(torch.bfloat16).float().numpy().tobytes()  # bf16-representable values
+        b = t.detach().cpu().contiguous().to(torch.bfloat16).float().numpy().tobytes()  # bf16-representable values
         self.chunks.append(b)
         self.off += len(b)
 
     def raw_f32(self, t: torch.Tensor):
         self._align()
-        b = t.contiguous().float().numpy().tobytes()
+        b = t.detach().cpu().contiguous().float().numpy().tobytes()
         self.chunks.append(b)
         self.off += len(b)
 

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ACE-Step hot path on B200 (contract: see DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3]
+
+A "step" is one pass of the hot path over one batch of synthetic input: ONE SONG per GPU —
+denoising loop (base sampler, CFG + APG) on synthetic text-conditioning embeddings + VAE decode to
+a 48 kHz stereo waveform.  Default workload = BASELINE.json configs[1]: text2music 60 s, 27 steps,
+bf16, batch 1 (effective batch 2 with CFG), E = 512 condition tokens.
+
+Metric: generated-audio seconds per wall second (whole job, all GPUs).
+  value : inputs resident in HBM, timed with CUDA events, max over ranks.
+  e2e   : same work through the public API (acestep_b200.pipeline.B200Pipeline.generate) with
+          pinned HOST inputs and a HOST waveform result (H2D + D2H inside the timed region).
+  roofline : tcgen05 GEMM launches of one song, event-timed per launch inside this run
+             (ace_profile_start/stop), algorithmic FLOPs / summed duration vs the measured bf16 peak.
+  cpu_baseline / --impl reference : the oracle port of the reference's PyTorch CPU path on this
+             box's host cores, on a bounded sample of the same workload (stated in `sample`).
+Weights are random-init of the reference architecture, data synthetic (no checkpoints / network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (seconds, frames T, steps, guidance, shift, cond tokens E, turbo)
+    "c1": dict(seconds=10, T=250, steps=8, guidance=1.0, shift=3.0, E=512, turbo=True,
+               desc="text2music 10 s, turbo 8 steps, batch 1 (no CFG)"),
+    "c2": dict(seconds=60, T=1500, steps=27, guidance=7.0, shift=3.0, E=512, turbo=False,
+               desc="text2music 60 s, base sampler 27 steps, CFG 7.0 + APG, batch 1 (effective 2)"),
+    "c3": dict(seconds=240, T=6000, steps=60, guidance=7.0, shift=3.0, E=512, turbo=False,
+               desc="text2music 240 s, base sampler 60 steps, CFG 7.0 + APG, batch 1 (effective 2)"),
+}
+
+
+def dit_flops(Bc, S, E, L=24, D=2048, I=6144, NQ=2048, NKV=1024, window=128):
+    """Algorithmic FLOPs of one DiT forward."""
+    lin = 2 * ((NQ + 2 * NKV) * D + NQ * D + NQ * D + NQ * D + 2 * I * D + D * I)  # per token per layer
+    per_tok = L * lin + 2 * (384 * D + D * 128)
+    attn = (L // 2) * 4 * S * S * NQ + (L - L // 2) * 4 * S * min(S, 2 * window + 1) * NQ + L * 4 * S * E * NQ
+    return Bc * (S * per_tok + attn)
+
+
+def vae_flops_per_frame():
+    return 4.874e9
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(wl, threads=None):
+    """Bounded CPU sample of the workload with the oracle port (fp32, all host threads):
+    one DiT forward at the workload's (Bc, T, E) + one 64-frame VAE decode window, extrapolated
+    linearly to the whole song.  Returns (audio_s_per_s, sample_seconds, description)."""
+    import torch
+
+    from oracle import vae as ovae
+    from oracle.dit import CrossCache, DiTConfig, dit_forward
+    from oracle.weights import make_dit_weights, make_vae_weights
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = DiTConfig()
+    w = make_dit_weights(cfg, seed=0)
+    vcfg = ovae.VaeConfig()
+    vw = make_vae_weights(vcfg, seed=0)
+    vw = {k: v for k, v in vw.items()}
+    Bc = 2 if wl["guidance"] > 1.0 else 1
+    g = torch.Generator().manual_seed(1)
+    xt = torch.randn(Bc, wl["T"], 64, generator=g)
+    ctx = torch.randn(Bc, wl["T"], 128, generator=g)
+    enc = torch.randn(Bc, wl["E"], cfg.hidden_size, generator=g)
+    t = torch.full((Bc,), 0.5)
+    z = torch.randn(1, 64, 64, generator=g)
+    state = {"cache": CrossCache()}
+
+    def one_sample():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            dit_forward(w, cfg, xt, t, ctx, enc, state["cache"])
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            ovae.decode(vw, vcfg, z)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    return one_sample, threads
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
+    itself is pure Python on torch CPU ops, and /root/reference does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    one_sample, threads = cpu_sample(wl)
+    for _ in range(max(args.warmup, 1)):
+        one_sample()
+    fw, dec = [], []
+    for _ in range(args.steps):
+        a, b = one_sample()
+        fw.append(a)
+        dec.append(b)
+    t_fwd, t_win = statistics.mean(fw), statistics.mean(dec)
+    song = wl["steps"] * t_fwd + (wl["T"] / 64.0) * t_win
+    value = wl["seconds"] / song
+    sample = (f"per step: 1 DiT forward at effective batch {2 if wl['guidance'] > 1 else 1}, T={wl['T']}, "
+              f"E={wl['E']} (cross-KV cached) + one 64-frame VAE decode window; extrapolated to "
+              f"{wl['steps']} forwards + {wl['T']}/64 windows per song")
+    line = {
+        "impl": "reference", "metric": "generated-audio-sec/wall-sec", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": (t_fwd + t_win) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "extrapolated_song_seconds": song},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+
+    from acestep_b200 import _lib
+    from acestep_b200.dit import DiTShape
+    from acestep_b200.pipeline import B200Pipeline
+    from acestep_b200.synthetic import random_dit_state, random_vae_state, synthetic_conditioning
+    from acestep_b200.vae import VaeShape
+
+    lib = _lib.load()
+    dshape, vshape = DiTShape(), VaeShape()
+    pipe = B200Pipeline(random_dit_state(dshape, 0, dev), random_vae_state(vshape, 0, dev), dshape, vshape,
+                        device=dev, turbo=wl["turbo"])
+    torch.cuda.empty_cache()
+    T, E = wl["T"], wl["E"]
+    host = synthetic_conditioning(1, T, E, dshape.hidden_size, seed=1234 + rank, device="cpu", pin=True)
+    noise_h = torch.randn(1, T, 64, generator=torch.Generator().manual_seed(rank)).to(torch.bfloat16).pin_memory()
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    noise_d = noise_h.to(dev)
+    pipe.sampler.null_condition_emb = dev_in["null_emb"]
+    if wl["turbo"]:
+        skw = dict(shift=wl["shift"])
+    else:
+        skw = dict(infer_steps=wl["steps"], diffusion_guidance_sale=wl["guidance"], shift=wl["shift"])
+    n_samples = T * vshape.hop
+    gathered = [torch.empty(1, 2, n_samples, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def song_device():
+        out = pipe.generate(dev_in["enc"], dev_in["ctx"], dev_in["src"], None, noise=noise_d, to_host=False, **skw)
+        if world > 1:  # the one collective of the path: waveform gather to rank 0 over NVLink
+            dist.gather(out["audio"], gathered, dst=0)
+        return out
+
+    def song_host():
+        out = pipe.generate(host["enc"], host["ctx"], host["src"], None, noise=noise_h, to_host=True, **skw)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        song_device()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.ace_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = song_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.ace_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(out["audio"]).all())
+
+    # end-to-end through the public API with host buffers
+    song_host()
+    barrier()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oh = song_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "ctx", "src")) + noise_h.numel() * 2
+    d2h = oh["audio"].numel() * 4
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+
+    line = None
+    if rank == 0:
+        # per-launch event profile of one song (rank 0 only)
+        import ctypes as C
+
+        lib.ace_profile_start()
+        song_device()
+        pms, pfl, pby, pln = (C.c_float * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int * 4)()
+        _lib.check(lib.ace_profile_stop(pms, pfl, pby, pln))
+        peaks, peak_kind = measured_peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        gemm_tf = (pfl[0] / (pms[0] * 1e-3)) / 1e12 if pms[0] > 0 else 0.0
+        Bc = 2 if wl["guidance"] > 1.0 else 1
+        S = (T + 1) // 2
+        song_flops = wl["steps"] * dit_flops(Bc, S, E) + vae_flops_per_frame() * T
+        audio_s = wl["seconds"] * world * args.steps
+        value = audio_s / (ms * 1e-3)
+        line = {
+            "metric": "generated-audio-sec/wall-sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (random-init weights, N(0,1) text-conditioning embeddings, seeded noise)",
+            "config": {"workload": wl["desc"], "songs_per_gpu_per_step": 1, "latent_frames": T,
+                       "cond_tokens": E, "parallelism": f"songs sharded 1/GPU x{world}, waveform gather",
+                       "l2_policy": "working set per step (3.2 GB weights) exceeds the 126 MB L2",
+                       "outputs_finite": finite},
+            "e2e": {"value": audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all tcgen05 GEMM launches of one song)",
+                         "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tf / peak,
+                         "peak_source": f"{peak_kind} bf16_tflops_sustained", "traffic": None,
+                         "launches": int(pln[0]), "kernel_ms_per_song": float(pms[0])},
+            "breakdown_ms_per_song": {"gemm": float(pms[0]), "attention": float(pms[1]),
+                                      "elementwise": float(pms[2]), "simt_conv": float(pms[3]),
+                                      "attention_tflops": (pfl[1] / (pms[1] * 1e-3)) / 1e12 if pms[1] > 0 else 0.0,
+                                      "elementwise_gbs": (pby[2] / (pms[2] * 1e-3)) / 1e9 if pms[2] > 0 else 0.0},
+            "dit_step_tensor_util": {"algorithmic_tflop_per_song": song_flops / 1e12,
+                                     "whole_song_tflops": song_flops / (ms / args.steps * 1e-3) / 1e12,
+                                     "frac_of_peak": song_flops / (ms / args.steps * 1e-3) / 1e12 / peak},
+        }
+    pipe.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            one_sample, threads = cpu_sample(wl)
+            one_sample()
+            a, b = one_sample()
+            song = wl["steps"] * a + (T / 64.0) * b
+            line["cpu_baseline"] = {
+                "value": wl["seconds"] / song, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                "sample": (f"1 DiT forward (effective batch {2 if wl['guidance'] > 1 else 1}, T={T}, E={E}) = {a:.2f} s and one "
+                           f"64-frame VAE decode window = {b:.2f} s on the host CPU (fp32 oracle port), "
+                           f"extrapolated to {wl['steps']} forwards + {T}/64 windows")}
+        except Exception as exc:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {exc}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    return run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -79,7 +79,7 @@ int ace_dit_bind(AceDit* dit, int bc, int t, int e, void* d_workspace, size_t wo
 
 /* condition_embedder + cross-attention K/V of all layers for d_enc [bc, e, hidden] (bf16); replaces
  * the EncoderDecoderCache fill of the first decoder call (turbo modeling :307-330, 1356).
- * `bc_offset`/`bc_count` select which batch rows are written (CFG: cond rows then null rows). */
+ * With CFG the caller passes rows [cond ; null_condition_emb] (base modeling :1905-1911). */
 int ace_dit_set_condition(AceDit* dit, const uint16_t* d_enc, void* stream);
 
 /* One velocity prediction: d_xt [bc,t,64], d_ctx [bc,t,128] (bf16), h_t [bc] (host floats, already
@@ -134,6 +134,23 @@ int ace_vae_decode(AceVae* vae, const uint16_t* d_z, int frames, float* d_wav, v
  * NULL: return the mean) -> d_z [samples/hop, 64] bf16 = mean + (softplus(scale) + 1e-4) * eps. */
 int ace_vae_encode(AceVae* vae, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z,
                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Device addresses of the handle's static I/O slots inside the bound workspace (xt [bc,t,64],
+ * ctx [bc,t,128], vt [bc,t,64]).  Passing these to ace_dit_step skips the staging copies, so a
+ * sampler that keeps its state there runs the whole step from one CUDA graph launch. */
+int ace_dit_io_slots(AceDit* dit, uint16_t** d_xt, uint16_t** d_ctx, uint16_t** d_vt);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Measurement hooks (bench.py): launch counter and per-launch CUDA-event profiling              */
+/* ------------------------------------------------------------------------------------------ */
+/* Number of kernels this library has launched in the calling process (graph replays included). */
+uint64_t ace_launch_count(void);
+/* Between start and stop every launch is bracketed by CUDA events on its own stream (CUDA graphs
+ * are bypassed).  stop() synchronises and fills 4-element arrays indexed by category
+ * {0: tcgen05 GEMM, 1: attention, 2: elementwise, 3: SIMT conv}: summed milliseconds, algorithmic
+ * FLOPs, algorithmic HBM bytes and launch counts. */
+void ace_profile_start(void);
+int ace_profile_stop(float* ms, double* flops, double* bytes, int* launches);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Test / bring-up hooks (never used by the product path)                                       */
