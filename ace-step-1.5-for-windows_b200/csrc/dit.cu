@@ -360,19 +360,19 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
   carve_workspace(d, d->ws, bc, t, e);
   const int D = d->D, I = d->I, NQ = d->NQ, NKV = d->NKV, M = d->M;
   const int ME = bc * e;
-  ACE_PROPAGATE(make_gemm_plan(&d->plan_in, d->xcat, M, 384, 384, d->proj_in_w, D, 384, M, 1, nullptr, 128));
-  ACE_PROPAGATE(make_gemm_plan(&d->plan_out, d->hn, M, D, D, d->proj_out_w, 128, D, M, 1, nullptr, 128));
+  ACE_PROPAGATE(make_gemm_plan(&d->plan_in, d->xcat, M, 384, 384, d->proj_in_w, D, 384, M, 1, nullptr, 0));
+  ACE_PROPAGATE(make_gemm_plan(&d->plan_out, d->hn, M, D, D, d->proj_out_w, 128, D, M, 1, nullptr, 0));
   d->lp.resize(d->L);
   for (int l = 0; l < d->L; ++l) {
     const LayerWeights& w = d->lw[l];
     LayerPlans& p = d->lp[l];
-    ACE_PROPAGATE(make_gemm_plan(&p.qkv, d->hn, M, D, D, w.self_qkv, NQ + 2 * NKV, D, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->hn, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, 128));
-    ACE_PROPAGATE(make_gemm_plan(&p.cross_kv, d->enc_e, ME, D, D, w.cross_kv, 2 * NKV, D, ME, 1, nullptr, 128));
+    ACE_PROPAGATE(make_gemm_plan(&p.qkv, d->hn, M, D, D, w.self_qkv, NQ + 2 * NKV, D, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->hn, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_kv, d->enc_e, ME, D, D, w.cross_kv, 2 * NKV, D, ME, 1, nullptr, 0));
   }
   d->rope_ready = false;
   return ACE_OK;
@@ -384,7 +384,7 @@ int ace_dit_set_condition(AceDit* d, const uint16_t* d_enc, void* stream) {
   const int D = d->D, NKV = d->NKV, ME = d->Bc * d->E;
   // condition_embedder (:1356) straight from the caller's buffer
   GemmPlan pc;
-  ACE_PROPAGATE(make_gemm_plan(&pc, (const bf16*)d_enc, ME, D, D, d->cond_w, D, D, ME, 1, nullptr, 128));
+  ACE_PROPAGATE(make_gemm_plan(&pc, (const bf16*)d_enc, ME, D, D, d->cond_w, D, D, ME, 1, nullptr, 0));
   ACE_PROPAGATE(launch_gemm(pc, EpiBias{d->enc_e, (long)D, d->cond_b}, st));
   for (int l = 0; l < d->L; ++l) {
     bf16* kv = d->ckv + (size_t)l * ME * 2 * NKV;
@@ -475,7 +475,7 @@ int ace_adg(const uint16_t* xt, const uint16_t* cond, const uint16_t* uncond, fl
 int ace_debug_linear(const uint16_t* a, const uint16_t* b, const uint16_t* bias, uint16_t* out, int m, int n,
                      int k, void* stream) {
   GemmPlan p;
-  ACE_PROPAGATE(make_gemm_plan(&p, (const bf16*)a, m, k, k, (const bf16*)b, n, k, m, 1, nullptr, 128));
+  ACE_PROPAGATE(make_gemm_plan(&p, (const bf16*)a, m, k, k, (const bf16*)b, n, k, m, 1, nullptr, 0));
   return launch_gemm(p, EpiBias{(bf16*)out, (long)n, (const bf16*)bias}, (cudaStream_t)stream);
 }
 

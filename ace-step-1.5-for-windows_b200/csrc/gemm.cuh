@@ -232,6 +232,168 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant: a 2-CTA cluster computes one 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256).  CTA r of the pair stages rows [128r, 128r+128) of the
+// A tile and rows [128r, 128r+128) of the B tile (half of N); the tensor core reads both halves of
+// B from the two CTAs' shared memories, so each CTA pulls 32 KB from L2 per 64-deep K block for
+// 2 x 128 x 256 x 64 FLOPs — twice the arithmetic intensity of the 128 x 128 single-CTA tile,
+// which measured L2-bandwidth-bound (profiles/r1_notes.md).  Accumulators: CTA r's TMEM holds its
+// 128 rows x 256 columns, double-buffered (2 x 256 = all 512 TMEM columns).
+//   barriers: full[s]  (leader only, 2 arrivals: leader expect_tx + peer remote arrive; all four
+//                       TMA loads credit the leader's barrier)
+//             empty[s], tmem_full[a]  (both CTAs, signalled by multicast tcgen05.commit)
+//             tmem_empty[a]           (leader only, 8 arrivals = 4 epilogue warps x 2 CTAs)
+// ---------------------------------------------------------------------------------------------
+template <int STAGES, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                const GemmShape shp, const Epi epi) {
+  constexpr int BN = 256;
+  using L = GemmSmem<128, STAGES>;  // per-CTA stage: 128 A rows + 128 B rows
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (shp.M + 255) / 256;
+  const int n_tiles = (shp.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int total_kb = shp.ntaps * shp.kblocks_per_tap;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
+        const int n0 = (tile / m_tiles) * BN + (int)rank * 128;
+        int tap = 0, kk = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          } else {
+            mbar_arrive_remote(&full_bar[stage], 0);
+          }
+          tma_load_2d_pair(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK,
+                           m0 + shp.shift[tap]);
+          tma_load_2d_pair(sB + stage * L::B_BYTES, &tma_b, &full_bar[stage],
+                           tap * shp.b_tap_stride + kk * GEMM_BK, n0);
+          if (++kk == shp.kblocks_per_tap) {
+            kk = 0;
+            ++tap;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (one thread of the leader CTA) ----------------
+      constexpr uint32_t idesc = make_umma_idesc_bf16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_umma_desc_k128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t db = make_umma_desc_k128(smem_u32(sB + stage * L::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_bf16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (kb == total_kb - 1) umma_commit_pair(&tfull_bar[as], 3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (both CTAs, each on its own 128 accumulator rows) ----------------
+    const int quarter = warp - 4;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
+      const int n0 = (tile / m_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tcgen05_fence_after();
+      __syncwarp();
+#pragma unroll 1
+      for (int sub = 0; sub < BN; sub += 128) {
+        if (n0 + sub < shp.N) {
+          AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
+          epi.template run<128>(acc, m0 + quarter * 32 + lane, n0 + sub, shp.M, shp.N);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Scalar reference path (tests / bring-up only; selected with ace_debug_set_gemm_reference).
 // ---------------------------------------------------------------------------------------------
 __global__ void gemm_ref_kernel(const bf16* __restrict__ A, long lda, int a_rows,
@@ -290,15 +452,38 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
 }
 
 template <class Epi>
+int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  constexpr int STAGES = 6;
+  using L = GemmSmem<128, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, Epi>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(p.shp.M, 256) * ceil_div(p.shp.N, 256);
+  const int max_clusters = num_sms() / 2;
+  const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
+  const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
+  prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,
+             2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
+                    (double)p.shp.M * p.shp.N),
+             stream);
+  gemm_tc2_kernel<STAGES, Epi><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p.tma_a, p.tma_b, p.shp, epi);
+  prof_end(stream);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+// bn selects the tile: 128 -> single-CTA 128 x 128 tiles, 256 -> CTA-pair 256 x 256 tiles.
+// (The scalar debug path always runs the epilogue per 128-column sub-tile, like both kernels do.)
+template <class Epi>
 int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   if (p.shp.M <= 0 || p.shp.N <= 0) return ACE_OK;
-  switch (p.bn) {
-    case 128:
-      return launch_gemm_bn<128, 6, Epi>(p, epi, stream);
-    default:
-      set_error("launch_gemm: unsupported BLOCK_N %d", p.bn);
-      return ACE_ERR_UNSUPPORTED;
-  }
+  if (gemm_debug_reference() || p.bn == 128) return launch_gemm_bn<128, 6, Epi>(p, epi, stream);
+  if (p.bn == 256) return launch_gemm_pair<Epi>(p, epi, stream);
+  set_error("launch_gemm: unsupported BLOCK_N %d", p.bn);
+  return ACE_ERR_UNSUPPORTED;
 }
 
 #endif  // __CUDACC__

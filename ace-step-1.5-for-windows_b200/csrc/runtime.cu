@@ -4,6 +4,7 @@
 // used only by the bring-up/debug switch.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -145,7 +146,17 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
   ACE_REQUIRE(kc > 0 && kc % GEMM_BK == 0, "gemm: per-tap K %d must be a multiple of %d", kc,
               GEMM_BK);
   ACE_REQUIRE(ntaps >= 1 && ntaps <= GEMM_MAX_TAPS, "gemm: ntaps %d", ntaps);
-  ACE_REQUIRE(bn == 128, "gemm: BLOCK_N %d unsupported", bn);
+  if (bn == 0) {
+    // auto: CTA-pair 256 x 256 tiles once the problem spans more than one 128-wide tile in both
+    // directions (halves L2 operand traffic per FLOP); ACE_GEMM_BN=128|256 overrides for experiments
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("ACE_GEMM_BN");
+      forced = e ? atoi(e) : 0;
+    }
+    bn = forced ? forced : ((n >= 256 && m > 128) ? 256 : 128);
+  }
+  ACE_REQUIRE(bn == 128 || bn == 256, "gemm: BLOCK_N %d unsupported", bn);
   memset(plan, 0, sizeof(*plan));
   plan->shp.M = m;
   plan->shp.N = n;
@@ -162,8 +173,9 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
   if (m <= 0 || n <= 0) return ACE_OK;
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_a, a, (uint64_t)kc, (uint64_t)a_rows,
                                (uint64_t)a_ld * sizeof(bf16), GEMM_BM));
+  // both kernels stage B in 128-row boxes (the CTA-pair kernel loads one half of N per CTA)
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_b, b, (uint64_t)ntaps * kc, (uint64_t)n,
-                               (uint64_t)b_ld * sizeof(bf16), (uint32_t)bn));
+                               (uint64_t)b_ld * sizeof(bf16), 128u));
   return ACE_OK;
 }
 

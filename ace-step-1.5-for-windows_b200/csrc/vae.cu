@@ -265,7 +265,7 @@ size_t walk_blob(AceVae* v, uint8_t* base) {
 int conv_gemm(const bf16* a, long a_rows, int kc, long a_ld, const ConvW& w, int n, long m, int ntaps,
               const int* shifts, const EpiConv& epi, cudaStream_t st) {
   GemmPlan p;
-  ACE_PROPAGATE(make_gemm_plan(&p, a, (int)a_rows, kc, a_ld, w.w, n, (long)ntaps * kc, (int)m, ntaps, shifts, 128));
+  ACE_PROPAGATE(make_gemm_plan(&p, a, (int)a_rows, kc, a_ld, w.w, n, (long)ntaps * kc, (int)m, ntaps, shifts, 0));
   return launch_gemm(p, epi, st);
 }
 

@@ -36,7 +36,7 @@ static float bf2f(uint16_t b) {
 }
 
 static int run_case(const char* name, int M, int N, int kc, int ntaps, const int* shifts,
-                    int a_rows, bool ref_path, int check_stride, int timing_iters) {
+                    int a_rows, bool ref_path, int check_stride, int timing_iters, int bn = 128) {
   const long Ktot = (long)ntaps * kc;
   std::vector<uint16_t> hA((size_t)a_rows * kc), hB((size_t)N * Ktot), hbias(N);
   for (auto& x : hA) x = f2bf(frand());
@@ -52,7 +52,7 @@ static int run_case(const char* name, int M, int N, int kc, int ntaps, const int
   CK(cudaMemcpy(dbias, hbias.data(), hbias.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dO, 0xff, (size_t)M * N * 2));
   GemmPlan plan;
-  if (make_gemm_plan(&plan, dA, a_rows, kc, kc, dB, N, Ktot, M, ntaps, shifts, 128) != ACE_OK) {
+  if (make_gemm_plan(&plan, dA, a_rows, kc, kc, dB, N, Ktot, M, ntaps, shifts, bn) != ACE_OK) {
     printf("[%s] plan failed: %s\n", name, get_error());
     return 1;
   }
@@ -87,8 +87,8 @@ static int run_case(const char* name, int M, int N, int kc, int ntaps, const int
     ++checked;
   }
   const bool pass = max_err <= 0.02 * (max_ref > 1 ? max_ref : 1);
-  printf("[%s] %s M=%d N=%d Kc=%d taps=%d : checked=%ld max_err=%.4g max_ref=%.4g -> %s\n", name,
-         ref_path ? "ref" : "tc ", M, N, kc, ntaps, checked, max_err, max_ref, pass ? "PASS" : "FAIL");
+  printf("[%s] %s bn=%d M=%d N=%d Kc=%d taps=%d : checked=%ld max_err=%.4g max_ref=%.4g -> %s\n", name,
+         ref_path ? "ref" : "tc ", bn, M, N, kc, ntaps, checked, max_err, max_ref, pass ? "PASS" : "FAIL");
   if (pass && timing_iters > 0 && !ref_path) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -128,6 +128,15 @@ int main() {
   const int convt[2] = {0, -1};
   fails += run_case("convT", 501, 1024, 256, 2, convt, 500, false, 11, 0);
   fails += run_case("conv7-big", 96000, 128, 128, 7, conv7, 96000, false, 9973, 10);
+  // CTA-pair 256 x 256 tiles
+  fails += run_case("pair-1tile", 256, 256, 64, 1, one, 256, false, 1, 0, 256);
+  fails += run_case("pair-small", 300, 384, 128, 1, one, 300, false, 1, 0, 256);
+  fails += run_case("pair-k2048", 1500, 2048, 2048, 1, one, 1500, false, 97, 20, 256);
+  fails += run_case("pair-qkv", 1500, 4096, 2048, 1, one, 1500, false, 997, 20, 256);
+  fails += run_case("pair-gateup", 1500, 12288, 2048, 1, one, 1500, false, 4999, 20, 256);
+  fails += run_case("pair-down", 1500, 2048, 6144, 1, one, 1500, false, 997, 20, 256);
+  fails += run_case("pair-conv7", 5000, 512, 512, 7, conv7, 5000, false, 1013, 10, 256);
+  fails += run_case("pair-conv7-n128", 96000, 128, 128, 7, conv7, 96000, false, 9973, 10, 256);
   printf("gemm_probe: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }
