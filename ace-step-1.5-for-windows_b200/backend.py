@@ -1,0 +1,230 @@
+"""B200 backend for the reference's AceStepHandler — a third sibling of "PyTorch" and "MLX".
+
+The reference selects its DiT / VAE backend at three seams:
+  * `_execute_service_generate_diffusion`   handler/service_generate_execute.py:107-196
+  * `tiled_decode`                           handler/vae_decode.py:16-85
+  * `tiled_encode`                           handler/vae_encode.py:15-82
+with the MLX backend installed as mixin methods + flags on the handler (`use_mlx_dit/mlx_decoder`,
+`use_mlx_vae/mlx_vae`: handler.py:161-168, init_service_setup.py:116-148).  `B200BackendMixin` adds
+the same shape of state (`use_b200_dit/b200_dit`, `use_b200_vae/b200_vae`) and `install()` grafts it
+onto an AceStepHandler class or instance, wrapping exactly those three sites; everything else of
+the handler (request parsing, conditioning, payloads, LoRA, UI plumbing) is reused unchanged.
+
+Unlike the MLX path there is NO silent fallback: when the B200 backend is active and fails, the
+exception propagates (the handler's outer try/except turns it into the usual error payload,
+generate_music.py:181-190).
+"""
+from __future__ import annotations
+
+import types
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+
+from .dit import B200DiT, DiTShape
+from .sampler import B200Sampler
+from .vae import B200Vae, VaeShape
+
+
+class B200BackendMixin:
+    """Methods + flags grafted onto AceStepHandler (mirrors the Mlx*Mixin classes)."""
+
+    use_b200_dit: bool = False
+    use_b200_vae: bool = False
+    b200_dit: Optional[B200DiT] = None
+    b200_sampler: Optional[B200Sampler] = None
+    b200_vae: Optional[B200Vae] = None
+
+    # ------------------------------------------------------------------ init
+    def _init_b200_backends(self, dit: bool = True, vae: bool = True) -> Tuple[str, str]:
+        """Build the engines from the already-loaded PyTorch modules' state_dict()s — the weight
+        source the MLX converters use too (models/mlx/dit_convert.py:33-66).  Call again after a
+        LoRA load/unload/scale change (lora/lifecycle.py:212-252 mutates model.decoder) to repack."""
+        dit_status = vae_status = "Disabled"
+        device = torch.device(self.device if str(self.device).startswith("cuda") else "cuda:0")
+        if dit:
+            decoder = self.model.decoder
+            shape = DiTShape.from_config(self.model.config)
+            if self.b200_dit is not None:
+                self.b200_dit.close()
+            self.b200_dit = B200DiT(decoder.state_dict(), shape, device)
+            self.b200_sampler = B200Sampler(self.b200_dit, getattr(self.model, "null_condition_emb", None))
+            self.use_b200_dit = True
+            dit_status = "Active (B200 tcgen05)"
+        if vae:
+            if self.b200_vae is not None:
+                self.b200_vae.close()
+            self.b200_vae = B200Vae(self.vae.state_dict(), VaeShape.from_config(self.vae.config), device)
+            self.use_b200_vae = True
+            vae_status = "Active (B200 tcgen05)"
+        return dit_status, vae_status
+
+    def _b200_is_turbo(self) -> bool:
+        cfg = getattr(self, "config", None)
+        return bool(getattr(cfg, "is_turbo", False))
+
+    # ------------------------------------------------------------------ DiT
+    def _b200_run_diffusion(
+        self,
+        encoder_hidden_states,
+        encoder_attention_mask,
+        context_latents,
+        src_latents,
+        seed,
+        infer_method: str = "ode",
+        shift: float = 3.0,
+        timesteps=None,
+        audio_cover_strength: float = 1.0,
+        encoder_hidden_states_non_cover=None,
+        encoder_attention_mask_non_cover=None,
+        context_latents_non_cover=None,
+        disable_tqdm: bool = False,
+        *,
+        infer_steps: int = 30,
+        diffusion_guidance_sale: float = 7.0,
+        cfg_interval_start: float = 0.0,
+        cfg_interval_end: float = 1.0,
+        use_adg: bool = False,
+        cover_noise_strength: float = 0.0,
+    ) -> Dict[str, Any]:
+        """Same positional signature and return contract as `_mlx_run_diffusion`
+        (handler/diffusion.py:18-56), extended keyword-only with the base-model knobs the MLX path
+        lacks.  Attention masks are accepted and unused — the DiT drops them (turbo :1381-1382).
+
+        Returns {"target_latents": Tensor[B,T,64] on self.device in self.dtype, "time_costs": {...}}.
+        Raises AttributeError / ValueError / TypeError exactly like the MLX sibling."""
+        _ = encoder_attention_mask, encoder_attention_mask_non_cover, disable_tqdm
+        for required_attr in ("b200_sampler", "device", "dtype"):
+            if not hasattr(self, required_attr) or getattr(self, required_attr) is None:
+                raise AttributeError(f"B200BackendMixin host is missing required attribute '{required_attr}'")
+        s = self.b200_sampler
+        if self._b200_is_turbo():
+            out = s.generate_turbo(
+                encoder_hidden_states, context_latents, src_latents, seed, infer_method=infer_method, shift=shift,
+                timesteps=timesteps, audio_cover_strength=audio_cover_strength,
+                cover_noise_strength=cover_noise_strength,
+                encoder_hidden_states_non_cover=encoder_hidden_states_non_cover,
+                context_latents_non_cover=context_latents_non_cover)
+        else:
+            out = s.generate_base(
+                encoder_hidden_states, context_latents, src_latents, seed, infer_method=infer_method,
+                infer_steps=infer_steps, diffusion_guidance_sale=diffusion_guidance_sale, shift=shift,
+                timesteps=timesteps, cfg_interval_start=cfg_interval_start, cfg_interval_end=cfg_interval_end,
+                use_adg=use_adg, audio_cover_strength=audio_cover_strength,
+                cover_noise_strength=cover_noise_strength,
+                encoder_hidden_states_non_cover=encoder_hidden_states_non_cover,
+                context_latents_non_cover=context_latents_non_cover)
+        out["target_latents"] = out["target_latents"].to(device=self.device, dtype=self.dtype)
+        return out
+
+    # ------------------------------------------------------------------ codec
+    def _b200_vae_decode(self, latents_torch: torch.Tensor) -> torch.Tensor:
+        """latents [B, 64, T] -> audio [B, 2, T*1920] (fp32, on the device); cf. _mlx_vae_decode
+        (handler/mlx_vae_decode_native.py:31-76).  One pass per sample, no overlap-discard waste."""
+        if self.b200_vae is None:
+            raise RuntimeError("B200 VAE decode requested but b200_vae is not initialized.")
+        return self.b200_vae.decode(latents_torch)
+
+    def _b200_vae_encode_sample(self, audio_torch: torch.Tensor) -> torch.Tensor:
+        """audio [B, 2, N] -> sampled latents [B, 64, N // 1920]; cf. _mlx_vae_encode_sample."""
+        if self.b200_vae is None:
+            raise RuntimeError("B200 VAE encode requested but b200_vae is not initialized.")
+        return self.b200_vae.encode(audio_torch, sample=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# The three wrapped selection sites
+# ---------------------------------------------------------------------------------------------
+def _execute_service_generate_diffusion(self, payload, generate_kwargs, seed_param, infer_method, shift,
+                                        audio_cover_strength):
+    """B200 branch of handler/service_generate_execute.py:107-196 (same return 4-tuple)."""
+    if not (getattr(self, "use_b200_dit", False) and self.b200_sampler is not None):
+        return self._ref_execute_service_generate_diffusion(payload, generate_kwargs, seed_param, infer_method,
+                                                            shift, audio_cover_strength)
+    src = payload["src_latents"]
+    ones = lambda x: torch.ones(x.shape[0], x.shape[1], device=x.device, dtype=x.dtype)
+    with torch.inference_mode():
+        with self._load_model_context("model"):
+            cond = dict(
+                lyric_hidden_states=payload["lyric_hidden_states"], lyric_attention_mask=payload["lyric_attention_mask"],
+                refer_audio_acoustic_hidden_states_packed=payload["refer_audio_acoustic_hidden_states_packed"],
+                refer_audio_order_mask=payload["refer_audio_order_mask"], silence_latent=self.silence_latent,
+                chunk_masks=payload["chunk_mask"])
+            enc, enc_mask, ctx = self.model.prepare_condition(
+                text_hidden_states=payload["text_hidden_states"], text_attention_mask=payload["text_attention_mask"],
+                hidden_states=src, attention_mask=ones(src), src_latents=src, is_covers=payload["is_covers"],
+                precomputed_lm_hints_25Hz=payload["precomputed_lm_hints_25Hz"], **cond)
+            enc_nc = mask_nc = ctx_nc = None
+            if audio_cover_strength < 1.0 and payload["non_cover_text_hidden_states"] is not None:
+                sil = self.silence_latent[:, : src.shape[1], :].expand(src.shape[0], -1, -1)
+                enc_nc, mask_nc, ctx_nc = self.model.prepare_condition(
+                    text_hidden_states=payload["non_cover_text_hidden_states"],
+                    text_attention_mask=payload["non_cover_text_attention_masks"], hidden_states=sil,
+                    attention_mask=ones(sil), src_latents=sil, is_covers=torch.zeros_like(payload["is_covers"]), **cond)
+            outputs = self._b200_run_diffusion(
+                enc, enc_mask, ctx, src, seed_param, infer_method=infer_method, shift=shift,
+                timesteps=generate_kwargs.get("timesteps"), audio_cover_strength=audio_cover_strength,
+                encoder_hidden_states_non_cover=enc_nc, encoder_attention_mask_non_cover=mask_nc,
+                context_latents_non_cover=ctx_nc,
+                infer_steps=generate_kwargs.get("infer_steps", 30),
+                diffusion_guidance_sale=generate_kwargs.get("diffusion_guidance_sale", 7.0),
+                cfg_interval_start=generate_kwargs.get("cfg_interval_start", 0.0),
+                cfg_interval_end=generate_kwargs.get("cfg_interval_end", 1.0),
+                use_adg=generate_kwargs.get("use_adg", False),
+                cover_noise_strength=generate_kwargs.get("cover_noise_strength", 0.0))
+    return outputs, enc, enc_mask, ctx
+
+
+def tiled_decode(self, latents, chunk_size: Optional[int] = None, overlap: int = 64,
+                 offload_wav_to_cpu: Optional[bool] = None):
+    """B200 fast path of handler/vae_decode.py:16-48 (slot of the MLX fast path)."""
+    if getattr(self, "use_b200_vae", False) and self.b200_vae is not None:
+        return self._b200_vae_decode(latents)
+    return self._ref_tiled_decode(latents, chunk_size, overlap, offload_wav_to_cpu)
+
+
+def tiled_encode(self, audio, chunk_size=None, overlap=None, offload_latent_to_cpu=True):
+    """B200 fast path of handler/vae_encode.py:15-43."""
+    if getattr(self, "use_b200_vae", False) and self.b200_vae is not None:
+        input_was_2d = audio.dim() == 2
+        if input_was_2d:
+            audio = audio.unsqueeze(0)
+        result = self._b200_vae_encode_sample(audio)
+        return result.squeeze(0) if input_was_2d else result
+    return self._ref_tiled_encode(audio, chunk_size, overlap, offload_latent_to_cpu)
+
+
+_WRAPPED = {
+    "_execute_service_generate_diffusion": _execute_service_generate_diffusion,
+    "tiled_decode": tiled_decode,
+    "tiled_encode": tiled_encode,
+}
+_MIXIN_ATTRS = ("_init_b200_backends", "_b200_is_turbo", "_b200_run_diffusion", "_b200_vae_decode",
+                "_b200_vae_encode_sample")
+
+
+def install(target):
+    """Graft the B200 backend onto an AceStepHandler CLASS (affects all instances) or INSTANCE.
+
+    The original selection-site methods stay reachable as `_ref_<name>` and are used whenever the
+    B200 flags are off, so an installed-but-inactive backend is behaviour-neutral (the reference's
+    own plumbing tests keep passing against a grafted handler)."""
+    is_class = isinstance(target, type)
+    cls = target if is_class else type(target)
+    if getattr(target, "_b200_installed", False):
+        return target
+    bind = (lambda f: f) if is_class else (lambda f: types.MethodType(f, target))
+    for name in _MIXIN_ATTRS:
+        setattr(target, name, bind(B200BackendMixin.__dict__[name]))
+    for name, fn in _WRAPPED.items():
+        original = getattr(cls, name, None)
+        if original is None:
+            raise AttributeError(f"{cls.__name__} has no method '{name}' to wrap")
+        setattr(target, "_ref_" + name.lstrip("_"), bind(original))
+        setattr(target, name, bind(fn))
+    for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("b200_dit", None),
+                      ("b200_sampler", None), ("b200_vae", None)):
+        if not hasattr(target, flag):
+            setattr(target, flag, val)
+    setattr(target, "_b200_installed", True)
+    return target

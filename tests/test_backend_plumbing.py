@@ -1,0 +1,196 @@
+"""CPU tests of the drop-in boundary: install() wraps exactly the three selection sites, the B200
+branch forwards the reference's arguments with the MLX sibling's contract, inactive == neutral.
+
+Engines are stubbed (no GPU here); numerics of the real engines are covered by the -m gpu tests.
+When the reference checkout is present (/root/reference, build container only) the graft is also
+applied to the REAL AceStepHandler class and the reference's own hot-path plumbing tests are run
+against it.
+"""
+import os
+import sys
+import types
+import unittest
+
+import pytest
+import torch
+
+from acestep_b200.backend import B200BackendMixin, install
+
+REF = "/root/reference"
+
+
+class _Ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class FakeModel:
+    """prepare_condition stand-in returning recognisable tensors."""
+
+    null_condition_emb = torch.zeros(1, 1, 8)
+
+    def __init__(self):
+        self.calls = []
+
+    def prepare_condition(self, **kw):
+        self.calls.append(kw)
+        b, t = kw["src_latents"].shape[:2]
+        tag = float(len(self.calls))
+        return torch.full((b, 5, 8), tag), torch.ones(b, 5), torch.full((b, t, 128), tag)
+
+
+class FakeHandler:
+    """Minimal host with the three reference selection sites."""
+
+    def __init__(self):
+        self.device, self.dtype = "cpu", torch.float32
+        self.model = FakeModel()
+        self.config = types.SimpleNamespace(is_turbo=False)
+        self.silence_latent = torch.zeros(1, 100, 64)
+        self.ref_calls = []
+
+    def _load_model_context(self, name):
+        return _Ctx()
+
+    def _execute_service_generate_diffusion(self, payload, generate_kwargs, seed_param, infer_method, shift,
+                                            audio_cover_strength):
+        self.ref_calls.append("dit")
+        return {"target_latents": torch.zeros(1)}, None, None, None
+
+    def tiled_decode(self, latents, chunk_size=None, overlap=64, offload_wav_to_cpu=None):
+        self.ref_calls.append("decode")
+        return torch.zeros(latents.shape[0], 2, latents.shape[2] * 1920)
+
+    def tiled_encode(self, audio, chunk_size=None, overlap=None, offload_latent_to_cpu=True):
+        self.ref_calls.append("encode")
+        return torch.zeros(1, 64, 1)
+
+
+class StubSampler:
+    def __init__(self):
+        self.calls = []
+
+    def generate_base(self, enc, ctx, src, seed, **kw):
+        self.calls.append(("base", enc, ctx, src, seed, kw))
+        return {"target_latents": torch.ones(src.shape, dtype=torch.bfloat16),
+                "time_costs": {"diffusion_time_cost": 1.0, "diffusion_per_step_time_cost": 0.1, "total_time_cost": 1.0}}
+
+    def generate_turbo(self, enc, ctx, src, seed, **kw):
+        self.calls.append(("turbo", enc, ctx, src, seed, kw))
+        return {"target_latents": torch.ones(src.shape, dtype=torch.bfloat16),
+                "time_costs": {"diffusion_time_cost": 1.0, "diffusion_per_step_time_cost": 0.1, "total_time_cost": 1.0}}
+
+
+class StubVae:
+    def decode(self, lat):
+        return torch.full((lat.shape[0], 2, lat.shape[2] * 1920), 0.5)
+
+    def encode(self, audio, sample=True):
+        return torch.full((audio.shape[0], 64, audio.shape[2] // 1920), 0.25)
+
+
+def _payload(b=2, t=20):
+    z = torch.zeros(1)
+    return {"text_hidden_states": z, "text_attention_mask": z, "lyric_hidden_states": z, "lyric_attention_mask": z,
+            "refer_audio_acoustic_hidden_states_packed": z, "refer_audio_order_mask": z,
+            "src_latents": torch.zeros(b, t, 64), "chunk_mask": z, "is_covers": torch.zeros(b),
+            "precomputed_lm_hints_25Hz": None, "non_cover_text_hidden_states": z,
+            "non_cover_text_attention_masks": z}
+
+
+def test_install_is_neutral_until_enabled():
+    h = install(FakeHandler())
+    assert h._b200_installed and not h.use_b200_dit and not h.use_b200_vae
+    h._execute_service_generate_diffusion(_payload(), {}, 1, "ode", 3.0, 1.0)
+    h.tiled_decode(torch.zeros(1, 64, 4))
+    h.tiled_encode(torch.zeros(1, 2, 1920))
+    assert h.ref_calls == ["dit", "decode", "encode"]
+    assert install(h) is h  # idempotent
+
+
+def test_dit_seam_forwards_reference_arguments():
+    h = install(FakeHandler())
+    h.b200_sampler, h.use_b200_dit = StubSampler(), True
+    kw = {"infer_steps": 27, "diffusion_guidance_sale": 6.5, "cfg_interval_start": 0.1, "cfg_interval_end": 0.9,
+          "use_adg": True, "cover_noise_strength": 0.2, "timesteps": None}
+    out, enc, mask, ctx = h._execute_service_generate_diffusion(_payload(), kw, [3, 4], "sde", 2.0, 0.5)
+    assert h.ref_calls == []
+    kind, enc_a, ctx_a, src_a, seed, skw = h.b200_sampler.calls[0]
+    assert kind == "base" and seed == [3, 4]
+    assert torch.equal(enc_a, enc) and torch.equal(ctx_a, ctx)
+    assert skw["infer_method"] == "sde" and skw["shift"] == 2.0 and skw["infer_steps"] == 27
+    assert skw["diffusion_guidance_sale"] == 6.5 and skw["use_adg"] is True and skw["cover_noise_strength"] == 0.2
+    assert skw["cfg_interval_start"] == 0.1 and skw["cfg_interval_end"] == 0.9 and skw["audio_cover_strength"] == 0.5
+    # audio_cover_strength < 1 -> the non-cover conditioning is prepared (second prepare_condition call)
+    assert len(h.model.calls) == 2 and skw["encoder_hidden_states_non_cover"] is not None
+    assert float(skw["context_latents_non_cover"][0, 0, 0]) == 2.0
+    # same return contract as the MLX sibling: latents on self.device in self.dtype + the three time_costs keys
+    assert out["target_latents"].dtype == torch.float32 and out["target_latents"].shape == (2, 20, 64)
+    assert {"diffusion_time_cost", "diffusion_per_step_time_cost", "total_time_cost"} <= set(out["time_costs"])
+
+
+def test_turbo_models_use_the_turbo_sampler():
+    h = install(FakeHandler())
+    h.config.is_turbo = True
+    h.b200_sampler, h.use_b200_dit = StubSampler(), True
+    h._execute_service_generate_diffusion(_payload(), {"timesteps": torch.tensor([1.0, 0.5, 0.0])}, 7, "ode", 3.0, 1.0)
+    kind, *_, skw = h.b200_sampler.calls[0]
+    assert kind == "turbo" and skw["timesteps"] is not None and len(h.model.calls) == 1
+
+
+def test_missing_sampler_raises_attribute_error_like_mlx_sibling():
+    h = install(FakeHandler())
+    with pytest.raises(AttributeError):
+        h._b200_run_diffusion(torch.zeros(1, 2, 8), None, torch.zeros(1, 4, 128), torch.zeros(1, 4, 64), 0)
+
+
+def test_codec_seams():
+    h = install(FakeHandler())
+    h.b200_vae, h.use_b200_vae = StubVae(), True
+    wav = h.tiled_decode(torch.zeros(3, 64, 10))
+    assert wav.shape == (3, 2, 19200) and float(wav[0, 0, 0]) == 0.5
+    lat = h.tiled_encode(torch.zeros(2, 3840))  # 2-D input is un-batched again, like the reference
+    assert lat.shape == (64, 2)
+    lat = h.tiled_encode(torch.zeros(4, 2, 3840))
+    assert lat.shape == (4, 64, 2)
+    assert h.ref_calls == []
+
+
+def test_no_silent_fallback_when_active():
+    h = install(FakeHandler())
+
+    class Boom:
+        def decode(self, lat):
+            raise RuntimeError("kernel failure")
+
+    h.b200_vae, h.use_b200_vae = Boom(), True
+    with pytest.raises(RuntimeError):
+        h.tiled_decode(torch.zeros(1, 64, 4))
+    assert h.ref_calls == []  # did NOT quietly route to the PyTorch path
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_graft_onto_real_handler_and_run_reference_plumbing_tests():
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("vector_quantize_pytorch")
+    stub.ResidualFSQ = type("ResidualFSQ", (torch.nn.Module,), {})
+    sys.modules.setdefault("vector_quantize_pytorch", stub)
+    try:
+        from acestep.handler import AceStepHandler
+    except Exception as exc:  # optional deps of the reference missing
+        pytest.skip(f"reference handler not importable here: {exc}")
+    install(AceStepHandler)
+    for name in ("_execute_service_generate_diffusion", "tiled_decode", "tiled_encode"):
+        assert hasattr(AceStepHandler, "_ref_" + name.lstrip("_"))
+    assert AceStepHandler.use_b200_dit is False and AceStepHandler.use_b200_vae is False
+    mods = ["diffusion_test", "vae_decode_chunks_test", "vae_decode_mixin_test", "vae_encode_test",
+            "service_generate_execute_test", "service_generate_test", "generate_music_decode_test",
+            "generate_music_test", "generate_music_execute_test"]
+    suite = unittest.TestSuite()
+    for m in mods:
+        suite.addTests(unittest.defaultTestLoader.loadTestsFromName(f"acestep.core.generation.handler.{m}"))
+    result = unittest.TextTestRunner(verbosity=0, stream=open(os.devnull, "w")).run(suite)
+    assert result.testsRun >= 30 and result.wasSuccessful(), (result.failures, result.errors)

@@ -1,0 +1,54 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: song sharding + ragged waveform gather."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from acestep_b200.multi_gpu import gather_waveforms, generate_sharded, shard_indices
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _song(i):
+    n = 1000 + 37 * i  # ragged lengths
+    return torch.arange(2 * n, dtype=torch.float32).view(2, n) + 1000.0 * i
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = generate_sharded(_song, n_items, dst=0)
+        if rank == 0:
+            ok = len(out) == n_items and all(torch.equal(out[i], _song(i)) for i in range(n_items))
+            q.put(bool(ok))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_indices_partition():
+    for n, w in [(8, 2), (5, 2), (3, 4), (0, 2)]:
+        got = sorted(i for r in range(w) for i in shard_indices(n, r, w))
+        assert got == list(range(n))
+
+
+def test_sharded_generate_and_gather_world2():
+    for n_items in (5, 2):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert q.get(timeout=5) is True
