@@ -83,6 +83,8 @@ attention_kernel(const AttnParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
+  pdl_trigger();
+  pdl_wait();
   const int q0 = blockIdx.x * BM;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / p.group;
@@ -257,7 +259,7 @@ int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t str
   const int kvh = heads / p.group;
   prof_begin(PROF_ATTN, 4.0 * p.Sq * keys * HD * heads * batch,
              2.0 * HD * batch * ((double)p.Sq * heads * 2 + (double)p.Skv * kvh * 2), stream);
-  attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
+  ACE_CUDA_CHECK(launch_kernel(attention_kernel, grid, dim3(ATT_THREADS), (size_t)smem, stream, p));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;

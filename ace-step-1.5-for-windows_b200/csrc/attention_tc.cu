@@ -1,0 +1,373 @@
+// attention_tc.cu — tcgen05 / TMEM flash attention for the DiT (head_dim 128, GQA, bf16).
+//
+// One CTA = 128 query rows of one (batch, head); keys/values are visited in blocks of 64.  The CTA
+// is sized so TWO fit on an SM (112 KB smem, 256 TMEM columns, <= 128 registers): while one CTA's
+// softmax warps run, the other CTA's MMAs keep the tensor core busy — no intra-CTA ping-pong needed.
+//   warp 0      TMA producer: Q once, then K_j / V_j tiles (3-D tensor maps over the token-major
+//               buffers: [columns, tokens, batch], so rows past a batch item's end read as zero)
+//   warp 1      single-thread MMA issuer:
+//                 S_j = Q · K_j^T    (A = Q K-major, B = K_j K-major)      -> TMEM S[j&1]  (128x64)
+//                 O  += P_j · V_j    (A = P_j from smem, B = V_j MN-major) -> TMEM O       (128x128)
+//               S_{j+1} is issued before PV_j so it overlaps softmax_j.
+//   warp 2      TMEM allocator (256 columns: S0 S1 O)
+//   warps 4-7   softmax, one query row per thread (row max / sum are thread-local, no shuffles):
+//               tcgen05.ld S -> scale (+ band / tail mask only on boundary blocks) -> exp2 ->
+//               bf16 P into swizzled smem (A operand of the PV MMA).  O stays in TMEM across the
+//               whole KV loop; it is rescaled (tcgen05.ld/st) only when a row maximum grows by more
+//               than 2^8 (lazy rescale: P and the row sum keep using the stale maximum, which is
+//               exact because the final 1/l normalisation uses the same reference).
+// Semantics = sdpa with the reference's masks (modeling_acestep_v15_turbo.py:286-368, 1405-1437):
+// full, +-window band (|i-j| <= W), or cross attention; softmax in fp32, P rounded to bf16.
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.h"
+
+namespace ace {
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;
+constexpr int BKV = 64;
+constexpr int TC_THREADS = 256;
+constexpr int Q_HALF = 128 * 64 * 2;   // [128 x 64] bf16 box (16 KB)
+constexpr int KV_HALF = 64 * 64 * 2;   // [64 x 64] bf16 box (8 KB)
+constexpr int KV_TILE = 2 * KV_HALF;   // [64 x 128]
+constexpr int P_BYTES = 128 * 64 * 2;  // [128 q x 64 keys]
+// smem: Q (32 KB) | K0 K1 (32 KB) | V0 V1 (32 KB) | P (16 KB) | barriers
+constexpr int OFF_K = 2 * Q_HALF;
+constexpr int OFF_V = OFF_K + 2 * KV_TILE;
+constexpr int OFF_P = OFF_V + 2 * KV_TILE;
+constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;  // 2 CTAs/SM: 2 x (112.25 KB + 1 KB reserved) <= 228 KB
+constexpr float RESCALE_TAU = 8.0f;  // log2 domain
+
+enum Bar {
+  Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11,
+  P_FULL = 13, P_EMPTY = 14, NBAR = 15
+};
+
+// MN-major SWIZZLE_128B operand: atoms of 64 (MN) x 8 (K); SBO = 1024 B between 8-row K groups,
+// LBO = bytes between consecutive 64-wide MN atoms (= one [64 keys x 64 d] box here).
+__device__ __forceinline__ uint64_t make_umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+        "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
+        "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])),
+        "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
+        "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  // No static __shared__ in this kernel, so the dynamic window starts 1024-byte aligned (needed by
+  // SWIZZLE_128B); checked rather than padded so that two CTAs fit on one SM.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + OFF_K;
+  uint8_t* sV = smem + OFF_V;
+  uint8_t* sP = smem + OFF_P;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / p.group;
+
+  pdl_trigger();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar[Q_FULL], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar[K_FULL + i], 1);
+      mbar_init(&bar[K_EMPTY + i], 1);
+      mbar_init(&bar[V_FULL + i], 1);
+      mbar_init(&bar[V_EMPTY + i], 1);
+      mbar_init(&bar[S_FULL + i], 1);
+      mbar_init(&bar[S_EMPTY + i], 4);
+    }
+    mbar_init(&bar[P_FULL], 4);
+    mbar_init(&bar[P_EMPTY], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128u;
+  pdl_wait();
+
+  // keys visited by this query tile
+  int j_lo = 0, j_hi = p.Skv;
+  if (p.window >= 0) {
+    j_lo = q0 - p.window;
+    if (j_lo < 0) j_lo = 0;
+    j_hi = q0 + BQ - 1 + p.window + 1;
+    if (j_hi > p.Skv) j_hi = p.Skv;
+  }
+  const int nblk = (j_hi - j_lo + BKV - 1) / BKV;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_arrive_expect_tx(&bar[Q_FULL], 2 * Q_HALF);
+      tma_load_3d(sQ, &tm_q, &bar[Q_FULL], h * HD, q0, b);
+      tma_load_3d(sQ + Q_HALF, &tm_q, &bar[Q_FULL], h * HD + 64, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int row = j_lo + j * BKV;
+        mbar_wait(&bar[K_EMPTY + s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar[K_FULL + s], KV_TILE);
+        tma_load_3d(sK + s * KV_TILE, &tm_k, &bar[K_FULL + s], hk * HD, row, b);
+        tma_load_3d(sK + s * KV_TILE + KV_HALF, &tm_k, &bar[K_FULL + s], hk * HD + 64, row, b);
+        mbar_wait(&bar[V_EMPTY + s], ph ^ 1);
+        mbar_arrive_expect_tx(&bar[V_FULL + s], KV_TILE);
+        tma_load_3d(sV + s * KV_TILE, &tm_v, &bar[V_FULL + s], hk * HD, row, b);
+        tma_load_3d(sV + s * KV_TILE + KV_HALF, &tm_v, &bar[V_FULL + s], hk * HD + 64, row, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_qk = make_umma_idesc_bf16(128, BKV);               // A, B K-major
+      constexpr uint32_t idesc_pv = make_umma_idesc_bf16(128, 128) | (1u << 16);  // B MN-major
+      mbar_wait(&bar[Q_FULL], 0);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bar[K_FULL + s], ph);
+        mbar_wait(&bar[S_EMPTY + s], ph ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(s * BKV);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // head_dim halves of 64
+          const uint64_t da = make_umma_desc_k128(smem_u32(sQ + half * Q_HALF));
+          const uint64_t db = make_umma_desc_k128(smem_u32(sK + s * KV_TILE + half * KV_HALF));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk,
+                         (half | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar[K_EMPTY + s]);
+        umma_commit(&bar[S_FULL + s]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_s(j + 1);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bar[V_FULL + s], ph);
+        mbar_wait(&bar[P_FULL], (uint32_t)(j & 1));
+        tcgen05_fence_after();
+        const uint64_t da = make_umma_desc_k128(smem_u32(sP));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 keys per MMA: P advances 32 B inside its swizzled row, V advances 16 rows (2048 B)
+          const uint64_t db = make_umma_desc_mn128(smem_u32(sV + s * KV_TILE) + (uint32_t)(k * 2048), KV_HALF);
+          umma_bf16_ss(tmem_o, da + (uint64_t)(2 * k), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar[V_EMPTY + s]);
+        umma_commit(&bar[P_EMPTY]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax + output (one query row per thread) ----------------
+    const int quarter = warp - 4;
+    const int r = quarter * 32 + lane;  // row within the tile
+    const int qi = q0 + r;              // query index within the batch item
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int jb = j_lo + j * BKV;
+      mbar_wait(&bar[S_FULL + s], ph);
+      tcgen05_fence_after();
+      __syncwarp();
+      float v[2][32];
+      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV), v[0]);
+      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV + 32), v[1]);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // S_j now lives in registers
+
+      // boundary blocks only: tail of the key range and the +-window band
+      const bool interior = (jb + BKV <= p.Skv) &&
+                            (p.window < 0 || ((q0 + BQ - 1) - jb <= p.window && (jb + BKV - 1) - q0 <= p.window));
+      float mx = -INFINITY;
+      if (interior) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[c][i] *= p.scale_log2;
+            mx = fmaxf(mx, v[c][i]);
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kj = jb + c * 32 + i;
+            bool ok = kj < p.Skv;
+            if (p.window >= 0) {
+              const int dd = qi - kj;
+              ok = ok && dd <= p.window && dd >= -p.window;
+            }
+            v[c][i] = ok ? v[c][i] * p.scale_log2 : -INFINITY;
+            mx = fmaxf(mx, v[c][i]);
+          }
+      }
+      // lazy rescale: keep the stale reference maximum unless some row of this warp outgrew it
+      const float m_new = fmaxf(m_used, mx);
+      const bool grow = (m_new - m_used > RESCALE_TAU) || (m_used == -INFINITY && m_new != -INFINITY);
+      const bool warp_grow = __any_sync(0xffffffffu, grow);
+      float factor = 1.f;
+      if (warp_grow) {
+        factor = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+        m_used = m_new;
+        l_run *= factor;
+      }
+      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+
+      // P buffer (and O) are free once PV_{j-1} has retired
+      mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
+      if (warp_grow && j > 0) {
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float o[32];
+          tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= factor;
+          tmem_st_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+        }
+      }
+      float rs = 0.f;
+      uint8_t* rowp = sP + r * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(v[c][i] - m_ref);
+          const float p1 = exp2f(v[c][i + 1] - m_ref);
+          rs += p0 + p1;
+          w[i >> 1] = pack_bf16x2(p0, p1);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
+      }
+      l_run += rs;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[P_FULL]);
+    }
+
+    // O is complete once the last PV has retired
+    mbar_wait(&bar[P_EMPTY], (uint32_t)((nblk - 1) & 1));
+    tcgen05_fence_after();
+    __syncwarp();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* op = p.o + ((long)b * p.Sq + qi) * p.ldo + (long)h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float o[32];
+      tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+      if (qi < p.Sq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
+          w.y = pack_bf16x2(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+          w.z = pack_bf16x2(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+          w.w = pack_bf16x2(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+          *reinterpret_cast<uint4*>(op + c * 32 + q * 8) = w;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
+  plan->p = p;
+  plan->heads = heads;
+  plan->batch = batch;
+  const int kvh = heads / p.group;
+  ACE_PROPAGATE(encode_tmap_3d(&plan->tm_q, p.q, (uint64_t)heads * HD, (uint64_t)p.Sq, (uint64_t)batch,
+                               (uint64_t)p.ldq * 2, (uint64_t)p.Sq * p.ldq * 2, BQ));
+  ACE_PROPAGATE(encode_tmap_3d(&plan->tm_k, p.k, (uint64_t)kvh * HD, (uint64_t)p.Skv, (uint64_t)batch,
+                               (uint64_t)p.ldk * 2, (uint64_t)p.Skv * p.ldk * 2, BKV));
+  ACE_PROPAGATE(encode_tmap_3d(&plan->tm_v, p.v, (uint64_t)kvh * HD, (uint64_t)p.Skv, (uint64_t)batch,
+                               (uint64_t)p.ldv * 2, (uint64_t)p.Skv * p.ldv * 2, BKV));
+  return ACE_OK;
+}
+
+int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
+    attr = true;
+  }
+  const AttnParams& p = plan.p;
+  if (p.Sq <= 0 || p.Skv <= 0 || plan.batch <= 0) return ACE_OK;
+  dim3 grid(ceil_div(p.Sq, BQ), plan.heads, plan.batch);
+  const double keys = p.window >= 0 ? (double)(p.Skv < 2 * p.window + 1 ? p.Skv : 2 * p.window + 1)
+                                    : (double)p.Skv;
+  const int kvh = plan.heads / p.group;
+  prof_begin(PROF_ATTN, 4.0 * p.Sq * keys * HD * plan.heads * plan.batch,
+             2.0 * HD * plan.batch * ((double)p.Sq * plan.heads * 2 + (double)p.Skv * kvh * 2), stream);
+  ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel, grid, dim3(TC_THREADS), (size_t)SMEM_BYTES, stream,
+                               plan.tm_q, plan.tm_k, plan.tm_v, p));
+  prof_end(stream);
+  return ACE_OK;
+}
+
+}  // namespace ace

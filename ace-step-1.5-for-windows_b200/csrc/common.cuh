@@ -73,7 +73,35 @@ bool prof_active();
 void prof_start();
 int prof_stop(float* ms, double* flops, double* bytes, int* launches);
 
+bool pdl_enabled();  // programmatic dependent launch (ACE_NO_PDL=1 disables)
+
 #ifdef __CUDACC__
+// ----------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel triggers its dependents at entry and waits for its
+// predecessor right before touching global memory, so the next kernel's launch latency and
+// prologue (barrier init, TMEM alloc, descriptor prefetch) overlap this kernel's tail.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------
 // bf16 helpers
 // ----------------------------------------------------------------------------

@@ -29,6 +29,7 @@ struct LayerWeights {
 
 struct LayerPlans {
   GemmPlan qkv, self_o, cross_q, cross_o, gate_up, down, cross_kv;
+  AttnPlan self_attn, cross_attn;
 };
 
 }  // namespace ace
@@ -108,6 +109,8 @@ struct TVals {
   float v[16];
 };
 __global__ void set_t_kernel(float* dst, TVals t, int n) {
+  pdl_trigger();
+  pdl_wait();
   if ((int)threadIdx.x < n) dst[threadIdx.x] = t.v[threadIdx.x];
 }
 
@@ -149,7 +152,11 @@ int enqueue_forward(AceDit* d, cudaStream_t st) {
                                             d->rope_sin, S, eps}, st));
     AttnParams ap{d->qkv, d->qkv + NQ, d->qkv + NQ + NKV, d->attn, QKVW, QKVW, QKVW, (long)NQ, S, S,
                   d->cfg.layer_is_sliding[l] ? d->cfg.sliding_window : -1, group, scale_log2};
-    ACE_PROPAGATE(launch_attention(ap, d->cfg.num_heads, Bc, st));
+    if (attention_use_legacy()) {
+      ACE_PROPAGATE(launch_attention(ap, d->cfg.num_heads, Bc, st));
+    } else {
+      ACE_PROPAGATE(launch_attention_tc(p.self_attn, st));
+    }
     ACE_PROPAGATE(launch_gemm(p.self_o, EpiGatedResid{d->h, (long)D, gate_msa, 2L * D, S}, st));
     // --- cross attention ---
     ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.cross_norm, nullptr, nullptr, nullptr, nullptr, 0, d->hn, M,
@@ -159,7 +166,11 @@ int enqueue_forward(AceDit* d, cudaStream_t st) {
     const bf16* kv = d->ckv + (size_t)l * Bc * E * 2 * NKV;
     AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, E, -1, group,
                   scale_log2};
-    ACE_PROPAGATE(launch_attention(cp, d->cfg.num_heads, Bc, st));
+    if (attention_use_legacy()) {
+      ACE_PROPAGATE(launch_attention(cp, d->cfg.num_heads, Bc, st));
+    } else {
+      ACE_PROPAGATE(launch_attention_tc(p.cross_attn, st));
+    }
     ACE_PROPAGATE(launch_gemm(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S}, st));
     // --- MLP ---
     ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.mlp_norm, w.table + 3 * D, w.table + 4 * D,
@@ -373,6 +384,19 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
     ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 0));
     ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, 0));
     ACE_PROPAGATE(make_gemm_plan(&p.cross_kv, d->enc_e, ME, D, D, w.cross_kv, 2 * NKV, D, ME, 1, nullptr, 0));
+    {
+      const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
+      const int group = d->cfg.num_heads / d->cfg.num_kv_heads;
+      const long QKVW = NQ + 2 * NKV;
+      const int S = d->S;
+      AttnParams ap{d->qkv, d->qkv + NQ, d->qkv + NQ + NKV, d->attn, QKVW, QKVW, QKVW, (long)NQ, S, S,
+                    d->cfg.layer_is_sliding[l] ? d->cfg.sliding_window : -1, group, scale_log2};
+      ACE_PROPAGATE(make_attn_plan(&p.self_attn, ap, d->cfg.num_heads, bc));
+      const bf16* kv = d->ckv + (size_t)l * bc * e * 2 * NKV;
+      AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, e, -1, group,
+                    scale_log2};
+      ACE_PROPAGATE(make_attn_plan(&p.cross_attn, cp, d->cfg.num_heads, bc));
+    }
   }
   d->rope_ready = false;
   return ACE_OK;
@@ -485,7 +509,10 @@ int ace_debug_attention(const uint16_t* q, const uint16_t* k, const uint16_t* v,
   AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, heads * 128L, kv_heads * 128L,
                kv_heads * 128L, heads * 128L, sq, skv, window, heads / kv_heads,
                (1.0f / sqrtf(128.0f)) * 1.4426950408889634f};
-  return launch_attention(p, heads, batch, (cudaStream_t)stream);
+  if (attention_use_legacy()) return launch_attention(p, heads, batch, (cudaStream_t)stream);
+  AttnPlan plan;
+  ACE_PROPAGATE(make_attn_plan(&plan, p, heads, batch));
+  return launch_attention_tc(plan, (cudaStream_t)stream);
 }
 
 }  // extern "C"

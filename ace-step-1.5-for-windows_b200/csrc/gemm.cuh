@@ -58,6 +58,10 @@ struct GemmPlan {
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
                    uint64_t row_pitch_bytes, uint32_t box_rows);
 
+// 3-D variant [cols, rows, batch] (attention operands); box = [64 x box_rows x 1].
+int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches,
+                   uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes, uint32_t box_rows);
+
 int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
                    int n, long b_ld, int m, int ntaps, const int* shifts, int bn);
 
@@ -117,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -140,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (shp.N + BN - 1) / BN;
@@ -268,6 +274,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -291,6 +298,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int m_tiles = (shp.M + 255) / 256;
   const int n_tiles = (shp.N + BN - 1) / BN;
@@ -444,8 +452,8 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
-  gemm_tc_kernel<BN, STAGES, Epi><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p.tma_a, p.tma_b, p.shp,
-                                                                           epi);
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc_kernel<BN, STAGES, Epi>, dim3(grid), dim3(GEMM_THREADS),
+                               (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
@@ -469,7 +477,8 @@ int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
-  gemm_tc2_kernel<STAGES, Epi><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(p.tma_a, p.tma_b, p.shp, epi);
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<STAGES, Epi>, dim3(grid), dim3(GEMM_THREADS),
+                               (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;

@@ -16,7 +16,18 @@ struct AttnParams {
   int group;                // query heads per KV head
   float scale_log2;         // head_dim^-0.5 * log2(e)
 };
+// legacy mma.sync kernel (attention.cu) — kept for A/B measurements (ACE_ATTN=legacy)
 int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t stream);
+
+// tcgen05 / TMEM kernel (attention_tc.cu): tensor maps are encoded once per bound shape
+struct AttnPlan {
+  CUtensorMap tm_q, tm_k, tm_v;
+  AttnParams p;
+  int heads, batch;
+};
+int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch);
+int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream);
+bool attention_use_legacy();
 
 // x[b, t, :] = [ctx[b, t, 0:128] | xt[b, t, 0:64]] for t < T, zeros for T <= t < Tpad
 int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,

@@ -141,6 +141,30 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
   return ACE_OK;
 }
 
+int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches,
+                   uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return ACE_ERR_CUDA;
+  }
+  ACE_REQUIRE(((uintptr_t)base & 15) == 0, "tensor map base %p not 16-byte aligned", base);
+  ACE_REQUIRE((row_pitch_bytes & 15) == 0 && (batch_pitch_bytes & 15) == 0, "tensor map pitch not a multiple of 16");
+  cuuint64_t dims[3] = {cols, rows, batches};
+  cuuint64_t strides[2] = {row_pitch_bytes, batch_pitch_bytes};
+  cuuint32_t box[3] = {GEMM_BK, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult res = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): cols=%llu rows=%llu batches=%llu", (int)res,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batches);
+    return ACE_ERR_CUDA;
+  }
+  return ACE_OK;
+}
+
 int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
                    int n, long b_ld, int m, int ntaps, const int* shifts, int bn) {
   ACE_REQUIRE(kc > 0 && kc % GEMM_BK == 0, "gemm: per-tap K %d must be a multiple of %d", kc,
@@ -221,4 +245,23 @@ __global__ void gemm_ref_kernel(const bf16* __restrict__ A, long lda, int a_rows
   out[(size_t)m * ld_out + n] = acc;
 }
 
+}  // namespace ace
+
+namespace ace {
+bool attention_use_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACE_ATTN");
+    v = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACE_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 }  // namespace ace

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(256)
 final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[2][7][C]*/, float* __restrict__ out,
                   long L, int C) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* sw = sm;                 // 2*7*C
   float* sx = sm + 2 * 7 * C;     // (256+6) * (C+1)
   const int tid = threadIdx.x;
@@ -102,6 +104,8 @@ first_conv_kernel(const float* __restrict__ wav, const float* __restrict__ w /*[
                   const float* __restrict__ bias, const float* __restrict__ sn_a, const float* __restrict__ sn_ib,
                   bf16* __restrict__ out, bf16* __restrict__ out_snake, long N, int C) {
   // one thread per (sample, 8-channel group)
+  pdl_trigger();
+  pdl_wait();
   const long idx = (long)blockIdx.x * 256 + threadIdx.x;
   const int groups = C / 8;
   if (idx >= N * groups) return;
@@ -139,6 +143,8 @@ first_conv_kernel(const float* __restrict__ wav, const float* __restrict__ w /*[
 // posterior: moments [L, 128] bf16 (mean | scale) -> z = mean + (softplus(scale) + 1e-4) * eps
 __global__ void posterior_kernel(const bf16* __restrict__ mom, const bf16* __restrict__ eps, bf16* __restrict__ z,
                                  long L, int Cz) {
+  pdl_trigger();
+  pdl_wait();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= L * Cz) return;
   const long l = idx / Cz;
