@@ -1,8 +1,6 @@
 // attention_tc.cu — tcgen05 / TMEM flash attention for the DiT (head_dim 128, GQA, bf16).
 //
-// One CTA = 128 query rows of one (batch, head); keys/values are visited in blocks of 64.  The CTA
-// is sized so TWO fit on an SM (112 KB smem, 256 TMEM columns, <= 128 registers): while one CTA's
-// softmax warps run, the other CTA's MMAs keep the tensor core busy — no intra-CTA ping-pong needed.
+// One CTA = 128 query rows of one (batch, head); keys/values are visited in blocks of 64.
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles (3-D tensor maps over the token-major
 //               buffers: [columns, tokens, batch], so rows past a batch item's end read as zero)
 //   warp 1      single-thread MMA issuer:
@@ -10,7 +8,9 @@
 //                 O  += P_j · V_j    (A = P_j from smem, B = V_j MN-major) -> TMEM O       (128x128)
 //               S_{j+1} is issued before PV_j so it overlaps softmax_j.
 //   warp 2      TMEM allocator (256 columns: S0 S1 O)
-//   warps 4-7   softmax, one query row per thread (row max / sum are thread-local, no shuffles):
+//   warps 4-11  softmax, TWO threads per query row (each owns 32 of the block's 64 keys; the row
+//               maximum is combined through smem + a 64-thread named barrier — the single-warp-
+//               per-scheduler version was ALU-latency bound, profiles/r1_notes.md):
 //               tcgen05.ld S -> scale (+ band / tail mask only on boundary blocks) -> exp2 ->
 //               bf16 P into swizzled smem (A operand of the PV MMA).  O stays in TMEM across the
 //               whole KV loop; it is rescaled (tcgen05.ld/st) only when a row maximum grows by more
@@ -18,6 +18,8 @@
 //               exact because the final 1/l normalisation uses the same reference).
 // Semantics = sdpa with the reference's masks (modeling_acestep_v15_turbo.py:286-368, 1405-1437):
 // full, +-window band (|i-j| <= W), or cross attention; softmax in fp32, P rounded to bf16.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
@@ -29,7 +31,7 @@ namespace {
 constexpr int HD = 128;
 constexpr int BQ = 128;
 constexpr int BKV = 64;
-constexpr int TC_THREADS = 256;
+// threads = 4 control warps + NSW softmax warps
 constexpr int Q_HALF = 128 * 64 * 2;   // [128 x 64] bf16 box (16 KB)
 constexpr int KV_HALF = 64 * 64 * 2;   // [64 x 64] bf16 box (8 KB)
 constexpr int KV_TILE = 2 * KV_HALF;   // [64 x 128]
@@ -39,7 +41,9 @@ constexpr int OFF_K = 2 * Q_HALF;
 constexpr int OFF_V = OFF_K + 2 * KV_TILE;
 constexpr int OFF_P = OFF_V + 2 * KV_TILE;
 constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;  // 2 CTAs/SM: 2 x (112.25 KB + 1 KB reserved) <= 228 KB
+constexpr int OFF_XCH = OFF_BAR + 256;  // NSW == 8 only: float [3][2][128] half-row max (x2 parity) / sum exchange
+template <int NSW>
+constexpr int smem_bytes() { return NSW == 8 ? OFF_XCH + 3 * 2 * 128 * 4 : OFF_BAR + 256; }
 constexpr float RESCALE_TAU = 8.0f;  // log2 domain
 
 enum Bar {
@@ -80,7 +84,8 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[3
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int NSW>
+__global__ void __launch_bounds__(128 + 32 * NSW, NSW == 4 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
   // No static __shared__ in this kernel, so the dynamic window starts 1024-byte aligned (needed by
@@ -113,9 +118,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&bar[V_FULL + i], 1);
       mbar_init(&bar[V_EMPTY + i], 1);
       mbar_init(&bar[S_FULL + i], 1);
-      mbar_init(&bar[S_EMPTY + i], 4);
+      mbar_init(&bar[S_EMPTY + i], NSW);
     }
-    mbar_init(&bar[P_FULL], 4);
+    mbar_init(&bar[P_FULL], NSW);
     mbar_init(&bar[P_EMPTY], 1);
     fence_barrier_init();
   }
@@ -205,55 +210,70 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ---------------- softmax + output (one query row per thread) ----------------
-    const int quarter = warp - 4;
-    const int r = quarter * 32 + lane;  // row within the tile
-    const int qi = q0 + r;              // query index within the batch item
+    // ---------------- softmax + output ----------------
+    // NSW = 4: one thread per query row (64 keys of each block), CTA small enough for 2 per SM.
+    // NSW = 8: two threads per row — warps 4-7 take keys [0,32) of each block, warps 8-11 keys
+    //          [32,64); the half-row maxima / sums are combined through smem + a 64-thread named
+    //          barrier.  Warp w may only touch TMEM lanes 32*(w%4)..+31, so both warps of a pair
+    //          share the lane quarter (w-4)&3.
+    constexpr int HPT = 8 / NSW;          // 32-key chunks per thread
+    constexpr int OCH = 4 / (NSW / 4);    // 32-column chunks of O per thread
+    const int quarter = (warp - 4) & 3;
+    const int hsel = (warp - 4) >> 2;     // 0 for NSW == 4
+    const int r = quarter * 32 + lane;    // row within the tile
+    const int qi = q0 + r;                // query index within the batch item
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem + OFF_XCH);  // [2 parity + 1][2 halves][128 rows] (NSW == 8)
+    // keys this row may attend to: [k_lo, k_hi)
+    int k_lo = 0, k_hi = p.Skv;
+    if (p.window >= 0) {
+      k_lo = qi - p.window > 0 ? qi - p.window : 0;
+      k_hi = qi + p.window + 1 < p.Skv ? qi + p.window + 1 : p.Skv;
+    }
+    const unsigned span = k_hi > k_lo ? (unsigned)(k_hi - k_lo) : 0u;
     float m_used = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      const int jb = j_lo + j * BKV;
+      const int jb0 = j_lo + j * BKV;
       mbar_wait(&bar[S_FULL + s], ph);
       tcgen05_fence_after();
       __syncwarp();
-      float v[2][32];
-      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV), v[0]);
-      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV + 32), v[1]);
+      float v[HPT][32];
+#pragma unroll
+      for (int c = 0; c < HPT; ++c)
+        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV + (hsel * HPT + c) * 32), v[c]);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // S_j now lives in registers
+      if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // this warp's slice of S_j is in registers
 
-      // boundary blocks only: tail of the key range and the +-window band
-      const bool interior = (jb + BKV <= p.Skv) &&
-                            (p.window < 0 || ((q0 + BQ - 1) - jb <= p.window && (jb + BKV - 1) - q0 <= p.window));
-      float mx = -INFINITY;
-      if (interior) {
+      // boundary blocks only: tail of the key range and the +-window band (tile-uniform test)
+      const bool interior = (jb0 + BKV <= p.Skv) &&
+                            (p.window < 0 || ((q0 + BQ - 1) - jb0 <= p.window && (jb0 + BKV - 1) - q0 <= p.window));
+      if (!interior) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < HPT; ++c) {
+          const unsigned lo = (unsigned)(k_lo - (jb0 + (hsel * HPT + c) * 32));
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[c][i] *= p.scale_log2;
-            mx = fmaxf(mx, v[c][i]);
-          }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kj = jb + c * 32 + i;
-            bool ok = kj < p.Skv;
-            if (p.window >= 0) {
-              const int dd = qi - kj;
-              ok = ok && dd <= p.window && dd >= -p.window;
-            }
-            v[c][i] = ok ? v[c][i] * p.scale_log2 : -INFINITY;
-            mx = fmaxf(mx, v[c][i]);
-          }
+          for (int i = 0; i < 32; ++i)
+            if ((unsigned)i - lo >= span) v[c][i] = -INFINITY;  // key outside [k_lo, k_hi)
+        }
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < HPT; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[c][i]);
+      if (NSW == 8) {  // combine the two half-row maxima (raw score domain; scale > 0 commutes with max)
+        xch[(s * 2 + hsel) * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, xch[(s * 2 + (hsel ^ 1)) * 128 + r]);
+      }
+      mx *= p.scale_log2;
+
       // lazy rescale: keep the stale reference maximum unless some row of this warp outgrew it
+      // (both warps of a pair see identical per-row values, so they take the same branch)
       const float m_new = fmaxf(m_used, mx);
       const bool grow = (m_new - m_used > RESCALE_TAU) || (m_used == -INFINITY && m_new != -INFINITY);
       const bool warp_grow = __any_sync(0xffffffffu, grow);
@@ -263,44 +283,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         m_used = m_new;
         l_run *= factor;
       }
-      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+      const float neg_ref = (m_used == -INFINITY) ? 0.f : -m_used;
 
       // P buffer (and O) are free once PV_{j-1} has retired
       mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
       if (warp_grow && j > 0) {
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < OCH; ++c) {  // this thread's share of the 128 output columns
           float o[32];
-          tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+          tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] *= factor;
-          tmem_st_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+          tmem_st_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
         }
       }
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f;
       uint8_t* rowp = sP + r * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < HPT; ++c) {
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(v[c][i] - m_ref);
-          const float p1 = exp2f(v[c][i + 1] - m_ref);
-          rs += p0 + p1;
+          const float p0 = exp2f(fmaf(v[c][i], p.scale_log2, neg_ref));
+          const float p1 = exp2f(fmaf(v[c][i + 1], p.scale_log2, neg_ref));
+          rs0 += p0;
+          rs1 += p1;
           w[i >> 1] = pack_bf16x2(p0, p1);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (c * 4 + q) ^ (r & 7);
+          const int chunk = ((hsel * HPT + c) * 4 + q) ^ (r & 7);
           *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
       }
-      l_run += rs;
+      l_run += rs0 + rs1;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[P_FULL]);
+    }
+
+    if (NSW == 8) {  // row sums: add the partner's partial (both are relative to the same m_used)
+      xch[(2 * 2 + hsel) * 128 + r] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      l_run += xch[(2 * 2 + (hsel ^ 1)) * 128 + r];
     }
 
     // O is complete once the last PV has retired
@@ -308,11 +335,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tcgen05_fence_after();
     __syncwarp();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    bf16* op = p.o + ((long)b * p.Sq + qi) * p.ldo + (long)h * HD;
+    bf16* op = p.o + ((long)b * p.Sq + qi) * p.ldo + (long)h * HD + hsel * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < OCH; ++c) {
       float o[32];
-      tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(c * 32), o);
+      tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
       if (qi < p.Sq) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -349,13 +376,20 @@ int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
   return ACE_OK;
 }
 
-int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
+template <int NSW>
+static int launch_attention_tc_n(const AttnPlan& plan, dim3 grid, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    ACE_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SMEM_BYTES));
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem_bytes<NSW>()));
     attr = true;
   }
+  ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel<NSW>, grid, dim3(128 + 32 * NSW), (size_t)smem_bytes<NSW>(),
+                               stream, plan.tm_q, plan.tm_k, plan.tm_v, plan.p));
+  return ACE_OK;
+}
+
+int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
   const AttnParams& p = plan.p;
   if (p.Sq <= 0 || p.Skv <= 0 || plan.batch <= 0) return ACE_OK;
   dim3 grid(ceil_div(p.Sq, BQ), plan.heads, plan.batch);
@@ -364,10 +398,19 @@ int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
   const int kvh = plan.heads / p.group;
   prof_begin(PROF_ATTN, 4.0 * p.Sq * keys * HD * plan.heads * plan.batch,
              2.0 * HD * plan.batch * ((double)p.Sq * plan.heads * 2 + (double)p.Skv * kvh * 2), stream);
-  ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel, grid, dim3(TC_THREADS), (size_t)SMEM_BYTES, stream,
-                               plan.tm_q, plan.tm_k, plan.tm_v, p));
+  // Default: the 4-softmax-warp CTA (two co-resident CTAs per SM overlap each other's softmax and
+  // MMA phases).  It measured faster than the 8-softmax-warp / 1-CTA-per-SM variant at both the
+  // 60 s (6.19 vs 6.42 ms per step) and 240 s (21.7 vs 22.7 ms) shapes; ACE_ATTN_NSW=8 selects the
+  // latter for experiments.
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("ACE_ATTN_NSW");
+    forced = e ? atoi(e) : 0;
+  }
+  const int nsw = forced == 8 ? 8 : 4;
+  const int st = nsw == 8 ? launch_attention_tc_n<8>(plan, grid, stream) : launch_attention_tc_n<4>(plan, grid, stream);
   prof_end(stream);
-  return ACE_OK;
+  return st;
 }
 
 }  // namespace ace

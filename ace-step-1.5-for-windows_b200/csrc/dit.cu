@@ -52,7 +52,7 @@ struct AceDit {
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
   bf16 *xin, *ctxin, *vout;  // static I/O slots so the graph never sees caller pointers
-  bf16 *xcat, *h, *hn, *qkv, *attn, *qc, *act, *enc_e, *ckv, *temb, *tproj, *gates, *te_scratch;
+  bf16 *xcat, *h, *hn, *qkv, *attn, *qc, *act, *enc_e, *ckv, *temb, *tproj, *mods, *outmod, *te_scratch;
   bf16 *rope_cos, *rope_sin;
   float* t_dev;
   GemmPlan plan_in, plan_out;
@@ -97,7 +97,8 @@ size_t carve_workspace(AceDit* d, uint8_t* base, int Bc, int T, int E) {
   d->ckv = c.take<bf16>((size_t)L * Bc * E * 2 * NKV);
   d->temb = c.take<bf16>((size_t)Bc * D);
   d->tproj = c.take<bf16>((size_t)Bc * 6 * D);
-  d->gates = c.take<bf16>((size_t)L * Bc * 2 * D);
+  d->mods = c.take<bf16>((size_t)L * Bc * 6 * D);
+  d->outmod = c.take<bf16>((size_t)Bc * 2 * D);
   d->te_scratch = c.take<bf16>((size_t)Bc * (256 + 2 * D));
   d->rope_cos = c.take<bf16>((size_t)S * 64);
   d->rope_sin = c.take<bf16>((size_t)S * 64);
@@ -126,8 +127,18 @@ int check_device() {
   return ACE_OK;
 }
 
+// Timing experiments only (results become garbage): ACE_SKIP=attn,norm,gemm drops a kernel class
+// from the step so its share of the REAL (graph + PDL) step time can be read off by difference.
+bool skip_class(const char* what) {
+  const char* e = getenv("ACE_SKIP");
+  return e != nullptr && strstr(e, what) != nullptr;
+}
+#define LAUNCH_GEMM(...) do { if (!skip_gemm) ACE_PROPAGATE(launch_gemm(__VA_ARGS__)); } while (0)
+#define LAUNCH_NORM(...) do { if (!skip_norm) ACE_PROPAGATE(launch_adaln_rmsnorm(__VA_ARGS__)); } while (0)
+
 // Enqueue one full forward (everything after the inputs sit in xin/ctxin/t_dev).
 int enqueue_forward(AceDit* d, cudaStream_t st) {
+  const bool skip_gemm = skip_class("gemm"), skip_norm = skip_class("norm"), skip_attn = skip_class("attn");
   const int D = d->D, NQ = d->NQ, NKV = d->NKV, S = d->S, Bc = d->Bc, M = d->M, E = d->E;
   const float eps = d->cfg.rms_eps;
   const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;
@@ -136,52 +147,53 @@ int enqueue_forward(AceDit* d, cudaStream_t st) {
 
   ACE_PROPAGATE(launch_time_embed(d->te, d->t_dev, Bc, D, d->te_scratch, d->temb, d->tproj, d->r_const,
                                   d->r_const + D, st));
-  ACE_PROPAGATE(launch_gate_table(d->lw[0].table, d->tproj, d->gates, d->L, Bc, D, st));
+  // per-step modulation vectors of all layers ([L][Bc][6][D], scales as 1+scale) and of the output norm
+  ACE_PROPAGATE(launch_mod_table(d->lw[0].table, d->tproj, 6L * D, (long)D, d->mods, d->L, Bc, 6, D, 0x12u, st));
+  ACE_PROPAGATE(launch_mod_table(d->out_table, d->temb, (long)D, 0, d->outmod, 1, Bc, 2, D, 0x2u, st));
   ACE_PROPAGATE(launch_concat_patches(d->ctxin, d->xin, d->xcat, Bc, d->T, d->Tpad, st));
-  ACE_PROPAGATE(launch_gemm(d->plan_in, EpiBias{d->h, (long)D, d->proj_in_b}, st));
+  LAUNCH_GEMM(d->plan_in, EpiBias{d->h, (long)D, d->proj_in_b}, st);
 
   for (int l = 0; l < d->L; ++l) {
     const LayerWeights& w = d->lw[l];
     const LayerPlans& p = d->lp[l];
-    const bf16* gate_msa = d->gates + ((size_t)l * Bc * 2 + 0) * D;
-    const bf16* gate_mlp = d->gates + ((size_t)l * Bc * 2 + 1) * D;
+    const bf16* mod = d->mods + (size_t)l * Bc * 6 * D;  // [Bc][6][D]: shift, 1+scale, gate, c_shift, 1+c_scale, c_gate
+    const bf16* gate_msa = mod + 2 * D;
+    const bf16* gate_mlp = mod + 5 * D;
     // --- self attention ---
-    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.self_norm, w.table + 0 * D, w.table + 1 * D,
-                                       d->tproj + 0 * D, d->tproj + 1 * D, 6L * D, d->hn, M, D, S, eps, st));
-    ACE_PROPAGATE(launch_gemm(p.qkv, EpiQKV{d->qkv, QKVW, NQ, NKV, w.self_qn, w.self_kn, d->rope_cos,
-                                            d->rope_sin, S, eps}, st));
+    LAUNCH_NORM(d->h, w.self_norm, mod + 0 * D, mod + 1 * D, 6L * D, d->hn, M, D, S, eps, st);
+    LAUNCH_GEMM(p.qkv, EpiQKV{d->qkv, QKVW, NQ, NKV, w.self_qn, w.self_kn, d->rope_cos,
+                                            d->rope_sin, S, eps}, st);
     AttnParams ap{d->qkv, d->qkv + NQ, d->qkv + NQ + NKV, d->attn, QKVW, QKVW, QKVW, (long)NQ, S, S,
                   d->cfg.layer_is_sliding[l] ? d->cfg.sliding_window : -1, group, scale_log2};
-    if (attention_use_legacy()) {
+    if (skip_attn) {
+    } else if (attention_use_legacy()) {
       ACE_PROPAGATE(launch_attention(ap, d->cfg.num_heads, Bc, st));
     } else {
       ACE_PROPAGATE(launch_attention_tc(p.self_attn, st));
     }
-    ACE_PROPAGATE(launch_gemm(p.self_o, EpiGatedResid{d->h, (long)D, gate_msa, 2L * D, S}, st));
+    LAUNCH_GEMM(p.self_o, EpiGatedResid{d->h, (long)D, gate_msa, 6L * D, S}, st);
     // --- cross attention ---
-    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.cross_norm, nullptr, nullptr, nullptr, nullptr, 0, d->hn, M,
-                                       D, S, eps, st));
-    ACE_PROPAGATE(launch_gemm(p.cross_q, EpiQKV{d->qc, (long)NQ, NQ, 0, w.cross_qn, w.cross_kn, nullptr,
-                                                nullptr, S, eps}, st));
+    LAUNCH_NORM(d->h, w.cross_norm, nullptr, nullptr, 0, d->hn, M, D, S, eps, st);
+    LAUNCH_GEMM(p.cross_q, EpiQKV{d->qc, (long)NQ, NQ, 0, w.cross_qn, w.cross_kn, nullptr,
+                                                nullptr, S, eps}, st);
     const bf16* kv = d->ckv + (size_t)l * Bc * E * 2 * NKV;
     AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, E, -1, group,
                   scale_log2};
-    if (attention_use_legacy()) {
+    if (skip_attn) {
+    } else if (attention_use_legacy()) {
       ACE_PROPAGATE(launch_attention(cp, d->cfg.num_heads, Bc, st));
     } else {
       ACE_PROPAGATE(launch_attention_tc(p.cross_attn, st));
     }
-    ACE_PROPAGATE(launch_gemm(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S}, st));
+    LAUNCH_GEMM(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S}, st);
     // --- MLP ---
-    ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, w.mlp_norm, w.table + 3 * D, w.table + 4 * D,
-                                       d->tproj + 3 * D, d->tproj + 4 * D, 6L * D, d->hn, M, D, S, eps, st));
-    ACE_PROPAGATE(launch_gemm(p.gate_up, EpiSwiGLU{d->act, (long)d->I}, st));
-    ACE_PROPAGATE(launch_gemm(p.down, EpiGatedResid{d->h, (long)D, gate_mlp, 2L * D, S}, st));
+    LAUNCH_NORM(d->h, w.mlp_norm, mod + 3 * D, mod + 4 * D, 6L * D, d->hn, M, D, S, eps, st);
+    LAUNCH_GEMM(p.gate_up, EpiSwiGLU{d->act, (long)d->I}, st);
+    LAUNCH_GEMM(p.down, EpiGatedResid{d->h, (long)D, gate_mlp, 6L * D, S}, st);
   }
   // output AdaLN: shift = table[0] + temb, scale = table[1] + temb  (:1488-1493)
-  ACE_PROPAGATE(launch_adaln_rmsnorm(d->h, d->norm_out_w, d->out_table, d->out_table + D, d->temb, d->temb,
-                                     (long)D, d->hn, M, D, S, eps, st));
-  ACE_PROPAGATE(launch_gemm(d->plan_out, EpiProjOut{d->vout, d->proj_out_b, S, d->T}, st));
+  LAUNCH_NORM(d->h, d->norm_out_w, d->outmod, d->outmod + D, 2L * D, d->hn, M, D, S, eps, st);
+  LAUNCH_GEMM(d->plan_out, EpiProjOut{d->vout, d->proj_out_b, S, d->T}, st);
   return ACE_OK;
 }
 
@@ -396,6 +408,23 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
       AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, e, -1, group,
                     scale_log2};
       ACE_PROPAGATE(make_attn_plan(&p.cross_attn, cp, d->cfg.num_heads, bc));
+    }
+  }
+  // chain the weight prefetches: every GEMM pulls the next GEMM's weights into L2
+  if (!(getenv("ACE_NO_PREFETCH") && getenv("ACE_NO_PREFETCH")[0] == '1')) {
+    auto chain = [](GemmPlan& cur, const GemmPlan& next) {
+      cur.shp.pf_ptr = reinterpret_cast<const uint8_t*>(next.b_ptr);
+      cur.shp.pf_bytes = (unsigned long long)next.shp.N * next.b_ld * sizeof(bf16);
+    };
+    for (int l = 0; l < d->L; ++l) {
+      LayerPlans& p = d->lp[l];
+      if (l == 0) chain(d->plan_in, p.qkv);
+      chain(p.qkv, p.self_o);
+      chain(p.self_o, p.cross_q);
+      chain(p.cross_q, p.cross_o);
+      chain(p.cross_o, p.gate_up);
+      chain(p.gate_up, p.down);
+      if (l + 1 < d->L) chain(p.down, d->lp[l + 1].qkv); else chain(p.down, d->plan_out);
     }
   }
   d->rope_ready = false;

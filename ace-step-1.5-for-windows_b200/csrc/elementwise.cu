@@ -60,11 +60,13 @@ __global__ void concat_patches_kernel(const bf16* __restrict__ ctx, const bf16* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// RMSNorm (+ AdaLN modulation).  One 256-thread block per row.
+// RMSNorm (+ AdaLN modulation): out = bf16(bf16(bf16(w * x_hat) * scale1p[b]) + shift[b]) where
+// scale1p = bf16(1 + bf16(table + tproj)) and shift = bf16(table + tproj) are precombined once per
+// step by mod_table_kernel (same roundings as the reference's bf16 expression, :490-496).
+// Generic fallback: one 256-thread block per row, any D % 8 == 0.
 __global__ void __launch_bounds__(256)
 adaln_rmsnorm_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
-                     const bf16* __restrict__ shift_tab, const bf16* __restrict__ scale_tab,
-                     const bf16* __restrict__ shift_t, const bf16* __restrict__ scale_t, long t_ld,
+                     const bf16* __restrict__ shift, const bf16* __restrict__ scale1p, long mod_ld,
                      bf16* __restrict__ out, int D, int rows_per_batch, float eps) {
   pdl_trigger();
   pdl_wait();
@@ -73,15 +75,10 @@ adaln_rmsnorm_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
   const int b = row / rows_per_batch;
   const bf16* hp = h + (long)row * D;
   const int nchunk = D >> 3;
-  float first[8];
   float ss = 0.f;
   for (int c = threadIdx.x; c < nchunk; c += 256) {
     float v[8];
     ld8(hp + c * 8, v);
-    if (c == (int)threadIdx.x) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) first[i] = v[i];
-    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
   }
@@ -94,40 +91,28 @@ adaln_rmsnorm_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
   const float rstd = rsqrtf(tot / (float)D + eps);
   for (int c = threadIdx.x; c < nchunk; c += 256) {
     float v[8], wv[8];
-    if (c == (int)threadIdx.x) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = first[i];
-    } else {
-      ld8(hp + c * 8, v);
-    }
+    ld8(hp + c * 8, v);
     ld8(w + c * 8, wv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = bf16_round(wv[i] * bf16_round(v[i] * rstd));
-    if (scale_tab != nullptr) {
-      float st[8], sv[8], ht[8], hv[8];
-      ld8(scale_tab + c * 8, st);
-      ld8(scale_t + (long)b * t_ld + c * 8, sv);
-      ld8(shift_tab + c * 8, ht);
-      ld8(shift_t + (long)b * t_ld + c * 8, hv);
+    if (scale1p != nullptr) {
+      float sc[8], sh[8];
+      ld8(scale1p + (long)b * mod_ld + c * 8, sc);
+      ld8(shift + (long)b * mod_ld + c * 8, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float sc = bf16_round(1.0f + bf16_round(st[i] + sv[i]));
-        const float sh = bf16_round(ht[i] + hv[i]);
-        v[i] = bf16_round(bf16_round(v[i] * sc) + sh);
-      }
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(bf16_round(v[i] * sc[i]) + sh[i]);
     }
     st8(out + (long)row * D + c * 8, v);
   }
 }
 
-// Warp-per-row variant for D = 256 * NJ: all of a row's 16-byte loads are issued up front (NJ
-// independent loads per lane), the reduction is shuffle-only, and 8 rows share a block — the
-// block-per-row kernel above was latency-bound at ~1.2 TB/s on the DiT's [1500, 2048] activations.
-template <int NJ>
+// Warp-per-row variant for D = 256 * NJ.  EVERY load of the row (activations, norm weight,
+// modulation vectors) is issued before the first dependent instruction, so the kernel pays one
+// memory round trip instead of one per chunk (the first version took 14 us per launch that way).
+template <int NJ, bool MOD>
 __global__ void __launch_bounds__(256)
 adaln_rmsnorm_warp_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
-                          const bf16* __restrict__ shift_tab, const bf16* __restrict__ scale_tab,
-                          const bf16* __restrict__ shift_t, const bf16* __restrict__ scale_t, long t_ld,
+                          const bf16* __restrict__ shift, const bf16* __restrict__ scale1p, long mod_ld,
                           bf16* __restrict__ out, int rows, int rows_per_batch, float eps) {
   pdl_trigger();
   pdl_wait();
@@ -137,59 +122,77 @@ adaln_rmsnorm_warp_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w
   if (row >= rows) return;
   const int b = row / rows_per_batch;
   const bf16* hp = h + (long)row * D;
-  float v[NJ][8];
+  uint4 xv[NJ], wv[NJ], sc[MOD ? NJ : 1], sh[MOD ? NJ : 1];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) xv[j] = *reinterpret_cast<const uint4*>(hp + (lane + 32 * j) * 8);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) wv[j] = *reinterpret_cast<const uint4*>(w + (lane + 32 * j) * 8);
+  if (MOD) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      sc[j] = *reinterpret_cast<const uint4*>(scale1p + (long)b * mod_ld + (lane + 32 * j) * 8);
+      sh[j] = *reinterpret_cast<const uint4*>(shift + (long)b * mod_ld + (lane + 32 * j) * 8);
+    }
+  }
   float ss = 0.f;
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) ld8(hp + (lane + 32 * j) * 8, v[j]);
+  for (int j = 0; j < NJ; ++j) {
+    float v[8];
+    unpack_bf16x2(xv[j].x, v[0], v[1]); unpack_bf16x2(xv[j].y, v[2], v[3]);
+    unpack_bf16x2(xv[j].z, v[4], v[5]); unpack_bf16x2(xv[j].w, v[6], v[7]);
 #pragma unroll
-  for (int j = 0; j < NJ; ++j)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ss += v[j][i] * v[j][i];
+    for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+  }
   ss = warp_sum(ss);
   const float rstd = rsqrtf(ss / (float)D + eps);
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int c = (lane + 32 * j) * 8;
-    float wv[8];
-    ld8(w + c, wv);
+    float v[8], ww[8];
+    unpack_bf16x2(xv[j].x, v[0], v[1]); unpack_bf16x2(xv[j].y, v[2], v[3]);
+    unpack_bf16x2(xv[j].z, v[4], v[5]); unpack_bf16x2(xv[j].w, v[6], v[7]);
+    unpack_bf16x2(wv[j].x, ww[0], ww[1]); unpack_bf16x2(wv[j].y, ww[2], ww[3]);
+    unpack_bf16x2(wv[j].z, ww[4], ww[5]); unpack_bf16x2(wv[j].w, ww[6], ww[7]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[j][i] = bf16_round(wv[i] * bf16_round(v[j][i] * rstd));
-    if (scale_tab != nullptr) {
-      float st[8], sv[8], ht[8], hv[8];
-      ld8(scale_tab + c, st);
-      ld8(scale_t + (long)b * t_ld + c, sv);
-      ld8(shift_tab + c, ht);
-      ld8(shift_t + (long)b * t_ld + c, hv);
+    for (int i = 0; i < 8; ++i) v[i] = bf16_round(ww[i] * bf16_round(v[i] * rstd));
+    if (MOD) {
+      float s1[8], s0[8];
+      unpack_bf16x2(sc[j].x, s1[0], s1[1]); unpack_bf16x2(sc[j].y, s1[2], s1[3]);
+      unpack_bf16x2(sc[j].z, s1[4], s1[5]); unpack_bf16x2(sc[j].w, s1[6], s1[7]);
+      unpack_bf16x2(sh[j].x, s0[0], s0[1]); unpack_bf16x2(sh[j].y, s0[2], s0[3]);
+      unpack_bf16x2(sh[j].z, s0[4], s0[5]); unpack_bf16x2(sh[j].w, s0[6], s0[7]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float sc = bf16_round(1.0f + bf16_round(st[i] + sv[i]));
-        const float sh = bf16_round(ht[i] + hv[i]);
-        v[j][i] = bf16_round(bf16_round(v[j][i] * sc) + sh);
-      }
+      for (int i = 0; i < 8; ++i) v[i] = bf16_round(bf16_round(v[i] * s1[i]) + s0[i]);
     }
-    st8(out + (long)row * D + c, v[j]);
+    st8(out + (long)row * D + (lane + 32 * j) * 8, v);
   }
 }
 
-__global__ void gate_table_kernel(const bf16* __restrict__ tables, const bf16* __restrict__ tproj,
-                                  bf16* __restrict__ out, int L, int B, int D) {
+// mods[l][b][i][:] = bf16(table[l][i] + tvec[b][i])  (i in scale_mask: bf16(1 + that)), i < n.
+// Layers: n = 6 (shift, scale, gate, c_shift, c_scale, c_gate; mask 0b010010); output norm: n = 2
+// with the same temb for both entries (t_i_stride = 0; mask 0b10).
+__global__ void mod_table_kernel(const bf16* __restrict__ tables, const bf16* __restrict__ tvec, long t_b_stride,
+                                 long t_i_stride, bf16* __restrict__ out, int L, int B, int n, int D,
+                                 unsigned scale_mask) {
   pdl_trigger();
   pdl_wait();
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over L*B*2*(D/8)
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over L*B*n*(D/8)
   const int nchunk = D >> 3;
-  const long total = (long)L * B * 2 * nchunk;
+  const long total = (long)L * B * n * nchunk;
   if (idx >= total) return;
   const int c = idx % nchunk;
-  const int which = (idx / nchunk) % 2;
-  const int b = (idx / (2 * nchunk)) % B;
-  const int l = idx / ((long)2 * nchunk * B);
-  const int mod = which == 0 ? 2 : 5;  // gate_msa, c_gate_msa
+  const int i = (idx / nchunk) % n;
+  const int b = (idx / ((long)n * nchunk)) % B;
+  const int l = idx / ((long)n * nchunk * B);
   float a[8], t[8];
-  ld8(tables + ((long)l * 6 + mod) * D + c * 8, a);
-  ld8(tproj + ((long)b * 6 + mod) * D + c * 8, t);
+  ld8(tables + ((long)l * n + i) * D + c * 8, a);
+  ld8(tvec + (long)b * t_b_stride + (long)i * t_i_stride + c * 8, t);
+  const bool one_plus = (scale_mask >> i) & 1u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] += t[i];
-  st8(out + (((long)l * B + b) * 2 + which) * D + c * 8, a);
+  for (int k = 0; k < 8; ++k) {
+    a[k] = bf16_round(a[k] + t[k]);
+    if (one_plus) a[k] = 1.0f + a[k];
+  }
+  st8(out + (((long)l * B + b) * n + i) * D + c * 8, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -441,34 +444,39 @@ int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int
   return ACE_OK;
 }
 
-int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, const bf16* scale_tab,
-                         const bf16* shift_t, const bf16* scale_t, long t_ld, bf16* out, int rows,
-                         int D, int rows_per_batch, float eps, cudaStream_t stream) {
+int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift, const bf16* scale1p, long mod_ld,
+                         bf16* out, int rows, int D, int rows_per_batch, float eps, cudaStream_t stream) {
   ACE_REQUIRE(D % 8 == 0, "adaln_rmsnorm: D %d must be a multiple of 8", D);
   if (rows == 0) return ACE_OK;
-#define ADALN_WARP(NJ)                                                                             \
-  ELEM((double)rows * D * 4, adaln_rmsnorm_warp_kernel<NJ>, ceil_div(rows, 8), 256, h, w, shift_tab, \
-       scale_tab, shift_t, scale_t, t_ld, out, rows, rows_per_batch, eps)
+  const double bytes = (double)rows * D * 4;
+#define ADALN_WARP(NJ)                                                                                   \
+  do {                                                                                                   \
+    if (scale1p)                                                                                         \
+      ELEM(bytes, (adaln_rmsnorm_warp_kernel<NJ, true>), ceil_div(rows, 8), 256, h, w, shift, scale1p,   \
+           mod_ld, out, rows, rows_per_batch, eps);                                                      \
+    else                                                                                                 \
+      ELEM(bytes, (adaln_rmsnorm_warp_kernel<NJ, false>), ceil_div(rows, 8), 256, h, w, shift, scale1p,  \
+           mod_ld, out, rows, rows_per_batch, eps);                                                      \
+  } while (0)
   switch (D) {
     case 256: ADALN_WARP(1); break;
     case 512: ADALN_WARP(2); break;
     case 1024: ADALN_WARP(4); break;
     case 2048: ADALN_WARP(8); break;
-    case 4096: ADALN_WARP(16); break;
     default:
-      ELEM((double)rows * D * 4, adaln_rmsnorm_kernel, rows, 256, h, w, shift_tab, scale_tab, shift_t, scale_t,
-           t_ld, out, D, rows_per_batch, eps);
+      ELEM(bytes, adaln_rmsnorm_kernel, rows, 256, h, w, shift, scale1p, mod_ld, out, D, rows_per_batch, eps);
   }
 #undef ADALN_WARP
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
 
-int launch_gate_table(const bf16* tables, const bf16* tproj, bf16* out, int L, int B, int D,
-                      cudaStream_t stream) {
-  const long total = (long)L * B * 2 * (D / 8);
-  ELEM(total * 48, gate_table_kernel, (unsigned)((total + 255) / 256), 256, tables, tproj, out, L, B,
-                                                                                      D);
+int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long t_i_stride, bf16* out, int L,
+                     int B, int n, int D, unsigned scale_mask, cudaStream_t stream) {
+  const long total = (long)L * B * n * (D / 8);
+  if (total == 0) return ACE_OK;
+  ELEM(total * 48, mod_table_kernel, (unsigned)((total + 255) / 256), 256, tables, tvec, t_b_stride, t_i_stride,
+       out, L, B, n, D, scale_mask);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -45,6 +45,7 @@ struct EpiBias {
   bf16* out;
   long ldo;
   const bf16* bias;  // may be null
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
 #pragma unroll 1
@@ -79,6 +80,7 @@ struct EpiQKV {
   const bf16* sin_tab;   // [S, 64]
   int S;                 // tokens per batch item (position = row % S)
   float eps;
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
     static_assert(BN == 128, "EpiQKV needs one head per tile");
@@ -149,6 +151,18 @@ struct EpiGatedResid {
   const bf16* gate;  // [Bc, gate_ld] or null
   long gate_ld;
   int S;  // rows per batch item
+  // pull this thread's residual row segment (and its gate vector) into L1 ahead of the accumulator
+  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N) const {
+    if (row >= M) return;
+    const bf16* hp = h + (size_t)row * ldh + n0;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(hp));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(hp + 64));
+    if (gate) {
+      const bf16* gp = gate + (size_t)(row / S) * gate_ld + n0;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gp));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + 64));
+    }
+  }
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
     const bool ok = row < M;
@@ -181,6 +195,7 @@ struct EpiGatedResid {
 struct EpiSwiGLU {
   bf16* out;
   long ldo;
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
     static_assert(BN == 128, "EpiSwiGLU packs 64 gate + 64 up columns per tile");
@@ -209,6 +224,7 @@ struct EpiProjOut {
   bf16* vt;  // [Bc, T, 64]
   const bf16* bias;  // [64]
   int S, T;
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
     static_assert(BN == 128, "EpiProjOut");
@@ -254,6 +270,7 @@ struct EpiConv {
   float* out_f32;        // may be null
   long ldo, off, total;
   int chan_mod;          // channel of column n is n % chan_mod (a multiple of 32)
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
 #pragma unroll 1

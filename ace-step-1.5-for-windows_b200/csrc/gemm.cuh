@@ -31,6 +31,7 @@ constexpr int GEMM_BM = 128;      // UMMA M (one TMEM lane per accumulator row)
 constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int GEMM_MAX_TAPS = 8;
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM2_THREADS = 384;  // CTA-pair kernel: 4 control warps + 8 epilogue warps
 
 struct GemmShape {
   int M, N;             // output extent
@@ -38,7 +39,28 @@ struct GemmShape {
   int ntaps;
   int b_tap_stride;     // elements between taps along B's K axis (= Kc)
   int shift[GEMM_MAX_TAPS];
+  // Optional L2 prefetch of the NEXT kernel's weights (read-only, so it may start before the
+  // programmatic-dependency wait): each CTA's idle warp 3 issues cp.async.bulk.prefetch.L2 for its
+  // slice.  The DiT streams 3.2 GB of weights per step through a 126 MB L2, so without this every
+  // B-operand TMA load pays DRAM latency and the 6-stage ring cannot cover it (profiles/r1_notes.md).
+  const uint8_t* pf_ptr;
+  unsigned long long pf_bytes;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void gemm_prefetch_next(const GemmShape& shp, int lane) {
+  if (shp.pf_ptr == nullptr) return;
+  constexpr unsigned long long CH = 8192;
+  const unsigned long long per_cta = ((shp.pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
+  const unsigned long long lo = (unsigned long long)blockIdx.x * per_cta;
+  unsigned long long hi = lo + per_cta;
+  if (hi > shp.pf_bytes) hi = shp.pf_bytes;
+  for (unsigned long long off = lo + (unsigned long long)lane * CH; off < hi; off += 32ull * CH) {
+    const unsigned long long n = hi - off < CH ? hi - off : CH;
+    l2_prefetch_bulk(shp.pf_ptr + off, (uint32_t)(n & ~15ull));
+  }
+}
+#endif
 
 // Host-side description of one GEMM problem; tensor maps are encoded once (at bind time) so a
 // launch does no host work besides cudaLaunchKernel and the whole step can live in a CUDA graph.
@@ -122,6 +144,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   pdl_trigger();
+  if (warp == 3) gemm_prefetch_next(shp, lane);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -251,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 //             tmem_empty[a]           (leader only, 8 arrivals = 4 epilogue warps x 2 CTAs)
 // ---------------------------------------------------------------------------------------------
 template <int STAGES, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const GemmShape shp, const Epi epi) {
   constexpr int BN = 256;
@@ -275,6 +298,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const bool leader = rank == 0;
 
   pdl_trigger();
+  if (warp == 3) gemm_prefetch_next(shp, lane);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -286,7 +310,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -372,22 +396,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ---------------- epilogue (both CTAs, each on its own 128 accumulator rows) ----------------
-    const int quarter = warp - 4;
+    // warps 4-7 take tile columns [0,128), warps 8-11 columns [128,256); warp w reads TMEM lanes
+    // 32*(w%4)..+31.  Operands the epilogue needs from HBM/L2 (residual rows, gates) are prefetched
+    // into L1 while the main loop is still running.
+    const int quarter = (warp - 4) & 3;
+    const int sub = ((warp - 4) >> 2) * 128;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-      const int n0 = (tile / m_tiles) * BN;
+      const int n0 = (tile / m_tiles) * BN + sub;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const bool live = n0 < shp.N;
+      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
       __syncwarp();
-#pragma unroll 1
-      for (int sub = 0; sub < BN; sub += 128) {
-        if (n0 + sub < shp.N) {
-          AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
-          epi.template run<128>(acc, m0 + quarter * 32 + lane, n0 + sub, shp.M, shp.N);
-        }
+      if (live) {
+        AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
+        epi.template run<128>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -477,7 +504,7 @@ int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
-  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<STAGES, Epi>, dim3(grid), dim3(GEMM_THREADS),
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<STAGES, Epi>, dim3(grid), dim3(GEMM2_THREADS),
                                (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());

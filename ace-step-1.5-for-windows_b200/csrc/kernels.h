@@ -33,17 +33,15 @@ bool attention_use_legacy();
 int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,
                           cudaStream_t stream);
 
-// out[r, :] = bf16( rmsnorm(h[r, :]) * w ) [* (1 + scale[b]) + shift[b]]
-//   with scale[b] = bf16(scale_tab + scale_t[b * t_ld ..]) and shift likewise when scale_tab != null
-//   (AdaLN: scale_shift_table + timestep_proj, modeling_acestep_v15_turbo.py:490-496, 1488-1493).
-int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift_tab, const bf16* scale_tab,
-                         const bf16* shift_t, const bf16* scale_t, long t_ld, bf16* out, int rows,
-                         int D, int rows_per_batch, float eps, cudaStream_t stream);
+// out[r, :] = bf16( rmsnorm(h[r, :]) * w ) [* scale1p[b] + shift[b]]  (AdaLN, :490-496, 1488-1493)
+//   shift / scale1p point at this op's rows of the per-step modulation table built by
+//   launch_mod_table (batch stride mod_ld); scale1p == null -> plain RMSNorm.
+int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift, const bf16* scale1p, long mod_ld,
+                         bf16* out, int rows, int D, int rows_per_batch, float eps, cudaStream_t stream);
 
-// gate[b, :] = bf16(table[idx, :] + tproj[b, idx, :]) for every layer: out [L, B, 2, D] holding
-// (gate_msa, c_gate_msa) so GEMM epilogues read one contiguous vector per (layer, batch).
-int launch_gate_table(const bf16* tables /*[L,6,D]*/, const bf16* tproj /*[B,6,D]*/, bf16* out,
-                      int L, int B, int D, cudaStream_t stream);
+// mods[l][b][i][:] = bf16(tables[l][i] + tvec[b*t_b_stride + i*t_i_stride]) (+1 where scale_mask bit i)
+int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long t_i_stride, bf16* out, int L,
+                     int B, int n, int D, unsigned scale_mask, cudaStream_t stream);
 
 // Timestep embedding (TimestepEmbedding.forward): sinusoid -> linear_1 -> SiLU -> linear_2 -> temb;
 // SiLU -> time_proj -> proj.  Weights bf16 row-major [out, in].
