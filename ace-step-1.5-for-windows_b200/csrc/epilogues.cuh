@@ -42,6 +42,7 @@ __device__ __forceinline__ void load_bf16x32(const bf16* p, float (&v)[32]) {
 
 // out[row, n] = bf16(acc + bias[n])                       (proj_in, condition_embedder)
 struct EpiBias {
+  static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out;
   long ldo;
   const bf16* bias;  // may be null
@@ -71,6 +72,7 @@ struct EpiBias {
 //   columns [nq + nk, N)   : value heads  -> plain bf16
 // Follows AceStepAttention.forward (modeling_acestep_v15_turbo.py:301, 317-318, 335-340).
 struct EpiQKV {
+  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
   bf16* out;
   long ldo;
   int nq, nk;
@@ -146,6 +148,7 @@ struct EpiQKV {
 // h[row, n] = bf16(h + bf16(bf16(acc) * gate[b, n]))   (gate == null: plain residual)
 // AceStepDiTLayer.forward lines 508, 523, 530.
 struct EpiGatedResid {
+  static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* h;  // read-modify-write in place
   long ldh;
   const bf16* gate;  // [Bc, gate_ld] or null
@@ -193,6 +196,7 @@ struct EpiGatedResid {
 // SwiGLU: B is packed so that tile columns [0,64) are gate features f0..f0+63 and [64,128) the
 // matching up features; out[row, f0 + i] = bf16(bf16(silu(g)) * u).   (Qwen3MLP.forward)
 struct EpiSwiGLU {
+  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
   bf16* out;
   long ldo;
   __device__ __forceinline__ void prefetch(int, int, int, int) const {}
@@ -221,6 +225,7 @@ struct EpiSwiGLU {
 // proj_out (ConvTranspose1d k=2 s=2 as a GEMM with N = 2*64): column n = k*64 + o lands at
 // vt[b, 2*s + k, o]; frames >= T (the odd-length pad) are cropped.  (turbo modeling :1284-1294,1498)
 struct EpiProjOut {
+  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
   bf16* vt;  // [Bc, T, 64]
   const bf16* bias;  // [64]
   int S, T;
@@ -261,6 +266,7 @@ __device__ __forceinline__ float snake_f(float x, float a, float ib) {
 // Flat element index = row*ldo + n + off must lie in [0, total) — this is how the transposed
 // convolution's "-padding" shift and its ragged ends are cropped.
 struct EpiConv {
+  static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out_main;        // may be null
   bf16* out_snake;       // may be null
   const bf16* resid;     // may be null; same indexing as out
@@ -270,27 +276,48 @@ struct EpiConv {
   float* out_f32;        // may be null
   long ldo, off, total;
   int chan_mod;          // channel of column n is n % chan_mod (a multiple of 32)
-  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  // residual rows are re-read by the thread that produces the output row: pull them into L1 early
+  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N) const {
+    if (resid == nullptr || row >= M) return;
+    const long idx = (long)row * ldo + n0 + off;
+    if (idx < 0 || idx >= total) return;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(resid + idx));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(resid + idx + 64));
+  }
   template <int BN, class Acc>
   __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
+      const long idx = (long)row * ldo + n0 + c + off;
+      const bool ok = row < M && n0 + c < N && idx >= 0 && idx < total;
+      const int ch = (n0 + c) % chan_mod;
+      // issue the global loads first so they overlap the TMEM read
+      uint4 rq[4];
+      if (ok && resid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rq[i] = reinterpret_cast<const uint4*>(resid + idx)[i];
+      }
       float v[32];
       acc.load32(c, v);
-      const long idx = (long)row * ldo + n0 + c + off;
-      if (row < M && n0 + c < N && idx >= 0 && idx < total) {
-        const int ch = (n0 + c) % chan_mod;
+      if (ok) {
         if (bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += bias[ch + i];
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch) + i);
+            v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
         if (resid) {
-          float r[32];
-          load_bf16x32(resid + idx, r);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + r[i]);
+          for (int i = 0; i < 4; ++i) {
+            float r[8];
+            unpack_bf16x2(rq[i].x, r[0], r[1]); unpack_bf16x2(rq[i].y, r[2], r[3]);
+            unpack_bf16x2(rq[i].z, r[4], r[5]); unpack_bf16x2(rq[i].w, r[6], r[7]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[8 * i + k] = bf16_round(v[8 * i + k] + r[k]);
+          }
         }
         if (out_main) store_bf16x32(out_main + idx, v);
         if (out_f32) {
@@ -299,7 +326,14 @@ struct EpiConv {
         }
         if (out_snake) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = snake_f(v[i], sn_a[ch + i], sn_ib[ch + i]);
+          for (int i = 0; i < 8; ++i) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(sn_a + ch) + i);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(sn_ib + ch) + i);
+            v[4 * i + 0] = snake_f(v[4 * i + 0], a4.x, b4.x);
+            v[4 * i + 1] = snake_f(v[4 * i + 1], a4.y, b4.y);
+            v[4 * i + 2] = snake_f(v[4 * i + 2], a4.z, b4.z);
+            v[4 * i + 3] = snake_f(v[4 * i + 3], a4.w, b4.w);
+          }
           store_bf16x32(out_snake + idx, v);
         }
       }

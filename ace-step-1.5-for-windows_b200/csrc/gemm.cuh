@@ -121,7 +121,7 @@ struct GemmSmem {
 };
 
 template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmShape shp, const Epi epi) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -156,7 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], Epi::kHalfTile ? 8 : 4);  // one arrive per active epilogue warp
     }
     fence_barrier_init();
   }
@@ -235,19 +235,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (Epi::kHalfTile || warp < 8)) {
     // ---------------- epilogue: TMEM -> registers -> fused op -> HBM ----------------
-    const int quarter = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // warp w reads TMEM lanes 32*(w%4)..+31.  Epilogues that work on 64-column half tiles use all
+    // eight warps (4-7: columns [0,BN/2), 8-11: [BN/2,BN)); head-structured ones use warps 4-7.
+    const int quarter = (warp - 4) & 3;
+    constexpr int EBN = Epi::kHalfTile ? BN / 2 : BN;
+    const int sub = Epi::kHalfTile ? ((warp - 4) >> 2) * EBN : 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile % m_tiles) * GEMM_BM;
-      const int n0 = (tile / m_tiles) * BN;
+      const int n0 = (tile / m_tiles) * BN + sub;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const bool live = n0 < shp.N;
+      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
-      AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN)};
-      epi.template run<BN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+      __syncwarp();
+      if (live) {
+        AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
+        epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -479,7 +488,7 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
-  ACE_CUDA_CHECK(launch_kernel(gemm_tc_kernel<BN, STAGES, Epi>, dim3(grid), dim3(GEMM_THREADS),
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc_kernel<BN, STAGES, Epi>, dim3(grid), dim3(GEMM2_THREADS),
                                (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
