@@ -72,6 +72,8 @@ void prof_end(cudaStream_t st);
 bool prof_active();
 void prof_start();
 int prof_stop(float* ms, double* flops, double* bytes, int* launches);
+void prof_tag_gemm(int m, int n, int k);  // shape of the next GEMM launch (profiling only)
+int prof_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms);
 
 bool pdl_enabled();  // programmatic dependent launch (ACE_NO_PDL=1 disables)
 
@@ -118,6 +120,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& lo, float& hi) {
   lo = __uint_as_float(w << 16);
   hi = __uint_as_float(w & 0xffff0000u);
+}
+// Packed bf16 arithmetic (HMUL2/HADD2.BF16): one correctly rounded bf16 result per lane.  For bf16
+// inputs this equals the reference's "compute in fp32, round to bf16": a bf16 x bf16 product is exact
+// in fp32, and a bf16 + bf16 sum that is inexact in fp32 has an addend below 2^-16 of the other, far
+// from any bf16 rounding boundary the fp32 rounding could move it across.
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
 
 // ----------------------------------------------------------------------------

@@ -218,6 +218,11 @@ int ace_profile_stop(float* ms, double* flops, double* bytes, int* launches) {
   return prof_stop(ms, flops, bytes, launches);
 }
 
+int ace_profile_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms) {
+  if (!m || !n || !k || !launches || !ms || max_out <= 0) return 0;
+  return prof_gemm_shapes(max_out, m, n, k, launches, ms);
+}
+
 int ace_dit_io_slots(AceDit* d, uint16_t** xt, uint16_t** ctx, uint16_t** vt) {
   ACE_REQUIRE(d && d->ws, "ace_dit_io_slots: handle not bound");
   if (xt) *xt = (uint16_t*)d->xin;
@@ -390,11 +395,11 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
     const LayerWeights& w = d->lw[l];
     LayerPlans& p = d->lp[l];
     ACE_PROPAGATE(make_gemm_plan(&p.qkv, d->hn, M, D, D, w.self_qkv, NQ + 2 * NKV, D, M, 1, nullptr, 0));
-    ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, -192));
     ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->hn, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 0));
-    ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, -192));
     ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 0));
-    ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, -192));
     ACE_PROPAGATE(make_gemm_plan(&p.cross_kv, d->enc_e, ME, D, D, w.cross_kv, 2 * NKV, D, ME, 1, nullptr, 0));
     {
       const float scale_log2 = (1.0f / sqrtf(128.0f)) * 1.4426950408889634f;

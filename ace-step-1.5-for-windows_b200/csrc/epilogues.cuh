@@ -1,8 +1,17 @@
 // epilogues.cuh — fused GEMM epilogues (run on fp32 accumulator rows read from TMEM).
 //
-// Contract (see gemm.cuh): `run<BN>(acc, row, n0, M, N)` is called by every thread of an epilogue
-// warp (acc.load32 is warp-collective, so loads are never predicated); `row` is this thread's
-// global output row and may be >= M, in which case nothing may be stored.
+// Contract (see gemm.cuh): `run<BN>(acc, row, n0, M, N, stg)` is called by every thread of an
+// epilogue warp (acc.load32 is warp-collective, so TMEM loads are never predicated); `row` is this
+// thread's global output row (row - lane is the warp's first row) and may be >= M, in which case
+// nothing may be stored.  `stg` is a 4 KB per-warp shared-memory slab.
+//
+// Memory access pattern: tcgen05.ld hands each THREAD one accumulator ROW, so storing straight from
+// registers makes every 16-byte store of a warp hit 32 different 128-byte lines.  Measured on the
+// DiT's o_proj GEMM that made the epilogue LSU-bound at 6.4 us — 30 % of the kernel
+// (profiles/r1_notes.md).  The DiT epilogues therefore go through the warp's slab: the thread-per-row
+// side writes/reads 16-byte chunks XOR-swizzled by row (bank-conflict free), and the global side
+// moves the slab with 8 lanes per row (4 rows x 128 contiguous bytes per instruction).  The codec's
+// EpiConv stays thread-per-row (measured faster there, see its comment).
 //
 // The roundings mirror the reference's bf16 execution where that is free: a Linear output is
 // rounded to bf16 before the next elementwise op, RMSNorm rounds x*rsqrt(var) and then w*x_hat,
@@ -16,6 +25,11 @@ namespace ace {
 
 #ifdef __CUDACC__
 
+constexpr int EPI_STAGE_BYTES = 4096;  // per warp: 32 rows x 64 bf16
+
+__device__ __forceinline__ void l1_prefetch(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void store_bf16x32(bf16* p, const float (&v)[32]) {
   uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
@@ -40,28 +54,107 @@ __device__ __forceinline__ void load_bf16x32(const bf16* p, float (&v)[32]) {
   }
 }
 
+// One warp's [32 rows x 64 bf16 columns] slab: 128-byte rows, 16-byte chunks XOR-swizzled by row.
+struct WarpStage {
+  uint8_t* base;
+  __device__ __forceinline__ uint4* at(int row, int chunk) const {
+    return reinterpret_cast<uint4*>(base + row * 128 + ((chunk ^ (row & 7)) << 4));
+  }
+  // thread-per-row side: columns [32*c32, 32*c32 + 32) of row `lane`
+  __device__ __forceinline__ void put32(int lane, int c32, const float (&v)[32]) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 w;
+      w.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+      w.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+      w.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+      w.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      *at(lane, c32 * 4 + q) = w;
+    }
+  }
+  __device__ __forceinline__ void get32(int lane, int c32, float (&v)[32]) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 w = *at(lane, c32 * 4 + q);
+      unpack_bf16x2(w.x, v[8 * q + 0], v[8 * q + 1]);
+      unpack_bf16x2(w.y, v[8 * q + 2], v[8 * q + 3]);
+      unpack_bf16x2(w.z, v[8 * q + 4], v[8 * q + 5]);
+      unpack_bf16x2(w.w, v[8 * q + 6], v[8 * q + 7]);
+    }
+  }
+  // global side: 8 lanes per row, 4 rows per instruction.  `addr(r)` returns the address of slab
+  // row r's first element, or nullptr when that row must be skipped; ncols (multiple of 8) = valid
+  // columns of the slab.
+  template <class AddrFn>
+  __device__ __forceinline__ void load_rows(int lane, int ncols, AddrFn addr) const {
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      const bf16* p = addr(r);
+      if (p != nullptr && ch * 8 < ncols) *at(r, ch) = *reinterpret_cast<const uint4*>(p + ch * 8);
+    }
+    __syncwarp();
+  }
+  // split version of load_rows: global -> registers now, registers -> slab later (lets the loads of
+  // the next slab fly while the current one is being computed on)
+  template <class AddrFn>
+  __device__ __forceinline__ void fetch_rows(int lane, int ncols, AddrFn addr, uint4 (&regs)[8]) const {
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bf16* p = addr(i * 4 + (lane >> 3));
+      regs[i] = (p != nullptr && ch * 8 < ncols) ? *reinterpret_cast<const uint4*>(p + ch * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  __device__ __forceinline__ void commit_rows(int lane, const uint4 (&regs)[8]) const {
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *at(i * 4 + (lane >> 3), ch) = regs[i];
+    __syncwarp();
+  }
+  template <class AddrFn>
+  __device__ __forceinline__ void store_rows(int lane, int ncols, AddrFn addr) const {
+    __syncwarp();
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      bf16* p = addr(r);
+      if (p != nullptr && ch * 8 < ncols) *reinterpret_cast<uint4*>(p + ch * 8) = *at(r, ch);
+    }
+    __syncwarp();
+  }
+};
+
 // out[row, n] = bf16(acc + bias[n])                       (proj_in, condition_embedder)
 struct EpiBias {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out;
   long ldo;
   const bf16* bias;  // may be null
-  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+    const int lane = threadIdx.x & 31, row0 = row - lane;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      acc.load32(c, v);
-      if (row < M && n0 + c < N) {
-        if (bias) {
+    for (int s = 0; s < BN; s += 64) {
+#pragma unroll
+      for (int c32 = 0; c32 < 2; ++c32) {
+        float v[32];
+        acc.load32(s + c32 * 32, v);
+        if (bias && n0 + s + c32 * 32 < N) {
           float b[32];
-          load_bf16x32(bias + n0 + c, b);
+          load_bf16x32(bias + n0 + s + c32 * 32, b);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += b[i];
         }
-        store_bf16x32(out + (size_t)row * ldo + n0 + c, v);
+        stg.put32(lane, c32, v);
       }
+      const int ncols = N - (n0 + s) < 64 ? N - (n0 + s) : 64;
+      stg.store_rows(lane, ncols, [&](int r) -> bf16* {
+        return row0 + r < M ? out + (size_t)(row0 + r) * ldo + n0 + s : nullptr;
+      });
     }
   }
 };
@@ -72,7 +165,7 @@ struct EpiBias {
 //   columns [nq + nk, N)   : value heads  -> plain bf16
 // Follows AceStepAttention.forward (modeling_acestep_v15_turbo.py:301, 317-318, 335-340).
 struct EpiQKV {
-  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kHalfTile = false;
   bf16* out;
   long ldo;
   int nq, nk;
@@ -82,113 +175,169 @@ struct EpiQKV {
   const bf16* sin_tab;   // [S, 64]
   int S;                 // tokens per batch item (position = row % S)
   float eps;
-  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  // norm weights and this row's RoPE table lines -> L1 while the main loop is still running
+  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    if (n0 >= nq + nk || row >= M) return;
+    const bf16* w = (n0 < nq) ? q_norm_w : k_norm_w;
+    l1_prefetch(w);
+    l1_prefetch(w + 64);
+    if (cos_tab != nullptr) {
+      l1_prefetch(cos_tab + (size_t)(row % S) * 64);
+      l1_prefetch(sin_tab + (size_t)(row % S) * 64);
+    }
+  }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
     static_assert(BN == 128, "EpiQKV needs one head per tile");
-    const bool ok = row < M;
+    const int lane = threadIdx.x & 31, row0 = row - lane;
+    auto out_addr = [&](int col0) {
+      return [=](int r) -> bf16* { return row0 + r < M ? out + (size_t)(row0 + r) * ldo + n0 + col0 : nullptr; };
+    };
     if (n0 >= nq + nk) {  // value head: tile-uniform branch
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        acc.load32(c, v);
-        if (ok) store_bf16x32(out + (size_t)row * ldo + n0 + c, v);
+      for (int s = 0; s < BN; s += 64) {
+#pragma unroll
+        for (int c32 = 0; c32 < 2; ++c32) {
+          float v[32];
+          acc.load32(s + c32 * 32, v);
+          stg.put32(lane, c32, v);
+        }
+        stg.store_rows(lane, 64, out_addr(s));
       }
       return;
     }
     const bf16* w = (n0 < nq) ? q_norm_w : k_norm_w;
-    // pass 1: mean of squares of the bf16-rounded projection
+    // pass 1: round the projection to bf16 (kept packed, 64 registers) and take its mean of squares
+    uint32_t xp[64];
     float ss = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      acc.load32(c, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = bf16_round(v[i]);
-        ss += x * x;
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      acc.load32(c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t t = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        float x0, x1;
+        unpack_bf16x2(t, x0, x1);
+        ss = fmaf(x0, x0, ss);
+        ss = fmaf(x1, x1, ss);
+        xp[c * 16 + i] = t;
       }
     }
     const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
-    const int pos = ok ? (row % S) : 0;
-    // pass 2: normalise, rotate pairs (i, i + 64)
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      float lo[32], hi[32], wl[32], wh[32];
-      acc.load32(c, lo);
-      acc.load32(c + 64, hi);
-      load_bf16x32(w + c, wl);
-      load_bf16x32(w + c + 64, wh);
+    const int pos = row < M ? (row % S) : 0;
+    // pass 2: normalise, rotate pairs (i, i + 64) in packed bf16; word j of xp holds columns 2j, 2j+1.
+    // The first 64-column half is staged and flushed while the second half waits in xp[32..63].
+    const uint4* wv = reinterpret_cast<const uint4*>(w);
+    const uint4* cv = reinterpret_cast<const uint4*>(cos_tab + (size_t)pos * 64);
+    const uint4* sv = reinterpret_cast<const uint4*>(sin_tab + (size_t)pos * 64);
+    auto norm2 = [&](uint32_t x, uint32_t wgt) {  // bf16(w * bf16(x * rstd)) on two lanes
+      float x0, x1;
+      unpack_bf16x2(x, x0, x1);
+      return bmul2(wgt, pack_bf16x2(x0 * rstd, x1 * rstd));
+    };
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        lo[i] = bf16_round(wl[i] * bf16_round(bf16_round(lo[i]) * rstd));
-        hi[i] = bf16_round(wh[i] * bf16_round(bf16_round(hi[i]) * rstd));
+    for (int q = 0; q < 8; ++q) {  // 8 columns of each half per iteration
+      const uint4 wl = __ldg(wv + q), wh = __ldg(wv + 8 + q);
+      const uint32_t wls[4] = {wl.x, wl.y, wl.z, wl.w}, whs[4] = {wh.x, wh.y, wh.z, wh.w};
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lo[k] = norm2(xp[4 * q + k], wls[k]);
+        hi[k] = norm2(xp[32 + 4 * q + k], whs[k]);
       }
       if (cos_tab != nullptr) {
-        float cs[32], sn[32];
-        load_bf16x32(cos_tab + (size_t)pos * 64 + c, cs);
-        load_bf16x32(sin_tab + (size_t)pos * 64 + c, sn);
+        const uint4 c4 = __ldg(cv + q), s4 = __ldg(sv + q);
+        const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int k = 0; k < 4; ++k) {
           // q*cos + rotate_half(q)*sin, every product and the sum rounded to bf16
-          float a = bf16_round(bf16_round(lo[i] * cs[i]) + bf16_round(-hi[i] * sn[i]));
-          float b = bf16_round(bf16_round(hi[i] * cs[i]) + bf16_round(lo[i] * sn[i]));
-          lo[i] = a;
-          hi[i] = b;
+          const uint32_t a = bsub2(bmul2(lo[k], cs[k]), bmul2(hi[k], sn[k]));
+          const uint32_t b = badd2(bmul2(hi[k], cs[k]), bmul2(lo[k], sn[k]));
+          lo[k] = a;
+          hi[k] = b;
         }
       }
-      if (ok) {
-        store_bf16x32(out + (size_t)row * ldo + n0 + c, lo);
-        store_bf16x32(out + (size_t)row * ldo + n0 + c + 64, hi);
-      }
+      *stg.at(lane, q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xp[32 + 4 * q + k] = hi[k];
     }
+    stg.store_rows(lane, 64, out_addr(0));
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *stg.at(lane, q) = make_uint4(xp[32 + 4 * q], xp[33 + 4 * q], xp[34 + 4 * q], xp[35 + 4 * q]);
+    stg.store_rows(lane, 64, out_addr(64));
   }
 };
 
 // h[row, n] = bf16(h + bf16(bf16(acc) * gate[b, n]))   (gate == null: plain residual)
 // AceStepDiTLayer.forward lines 508, 523, 530.
 struct EpiGatedResid {
-  static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kHalfTile = true;
   bf16* h;  // read-modify-write in place
   long ldh;
   const bf16* gate;  // [Bc, gate_ld] or null
   long gate_ld;
   int S;  // rows per batch item
-  // pull this thread's residual row segment (and its gate vector) into L1 ahead of the accumulator
-  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N) const {
-    if (row >= M) return;
-    const bf16* hp = h + (size_t)row * ldh + n0;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(hp));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(hp + 64));
-    if (gate) {
-      const bf16* gp = gate + (size_t)(row / S) * gate_ld + n0;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(gp));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(gp + 64));
+  // called BEFORE the accumulator is ready (the main loop is still running): stage the first
+  // residual slab so its L2 latency is off the critical path
+  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage& stg) const {
+    const int lane = threadIdx.x & 31, row0 = row - lane;
+    if (n0 >= N) return;
+    const int ncols = N - n0 < 64 ? N - n0 : 64;
+    if (gate != nullptr && row < M) {  // this row's gate vector: pulled into L1 for the loads in run()
+      const bf16* g = gate + (size_t)(row / S) * gate_ld + n0;
+      l1_prefetch(g);
+      if (n0 + 64 < N) l1_prefetch(g + 64);
     }
+    stg.load_rows(lane, ncols, [&](int r) -> const bf16* {
+      return row0 + r < M ? h + (size_t)(row0 + r) * ldh + n0 : nullptr;
+    });
   }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
-    const bool ok = row < M;
-    const int b = ok ? row / S : 0;
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+    const int lane = threadIdx.x & 31, row0 = row - lane;
+    const int b = row < M ? row / S : 0;
+    uint4 nxt[8];
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      acc.load32(c, v);
-      if (ok && n0 + c < N) {
-        float r[32];
-        bf16* hp = h + (size_t)row * ldh + n0 + c;
-        load_bf16x32(hp, r);
-        if (gate) {
-          float g[32];
-          load_bf16x32(gate + (size_t)b * gate_ld + n0 + c, g);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = r[i] + bf16_round(bf16_round(v[i]) * g[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = r[i] + bf16_round(v[i]);
-        }
-        store_bf16x32(hp, v);
+    for (int s = 0; s < BN; s += 64) {
+      if (n0 + s >= N) break;  // warp-uniform
+      const int ncols = N - (n0 + s) < 64 ? N - (n0 + s) : 64;
+      auto addr = [&](int r) -> bf16* { return row0 + r < M ? h + (size_t)(row0 + r) * ldh + n0 + s : nullptr; };
+      const bool has_next = s + 64 < BN && n0 + s + 64 < N;
+      if (has_next) {  // next residual slab: global -> registers while this slab is processed
+        const int nn = N - (n0 + s + 64) < 64 ? N - (n0 + s + 64) : 64;
+        stg.fetch_rows(lane, nn, [&](int r) -> const bf16* {
+          return row0 + r < M ? h + (size_t)(row0 + r) * ldh + n0 + s + 64 : nullptr;
+        }, nxt);
       }
+#pragma unroll
+      for (int c32 = 0; c32 < 2; ++c32) {
+        float v[32];
+        acc.load32(s + c32 * 32, v);
+        const bool gl = gate != nullptr && row < M && n0 + s + c32 * 32 < N;
+        const uint4* gp = reinterpret_cast<const uint4*>(gate + (size_t)b * gate_ld + n0 + s + c32 * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4* slot = stg.at(lane, c32 * 4 + q);
+          uint4 r = *slot;
+          uint4 pv;
+          pv.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+          pv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+          pv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+          pv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+          if (gate != nullptr) {
+            const uint4 g = gl ? __ldg(gp + q) : make_uint4(0, 0, 0, 0);
+            pv.x = bmul2(pv.x, g.x); pv.y = bmul2(pv.y, g.y);
+            pv.z = bmul2(pv.z, g.z); pv.w = bmul2(pv.w, g.w);
+          }
+          r.x = badd2(r.x, pv.x); r.y = badd2(r.y, pv.y);
+          r.z = badd2(r.z, pv.z); r.w = badd2(r.w, pv.w);
+          *slot = r;
+        }
+      }
+      stg.store_rows(lane, ncols, addr);
+      if (has_next) stg.commit_rows(lane, nxt);
     }
   }
 };
@@ -196,58 +345,68 @@ struct EpiGatedResid {
 // SwiGLU: B is packed so that tile columns [0,64) are gate features f0..f0+63 and [64,128) the
 // matching up features; out[row, f0 + i] = bf16(bf16(silu(g)) * u).   (Qwen3MLP.forward)
 struct EpiSwiGLU {
-  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kHalfTile = false;
   bf16* out;
   long ldo;
-  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
     static_assert(BN == 128, "EpiSwiGLU packs 64 gate + 64 up columns per tile");
+    const int lane = threadIdx.x & 31, row0 = row - lane;
     const int f0 = (n0 >> 7) << 6;
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      float g[32], u[32];
-      acc.load32(c, g);
-      acc.load32(c + 64, u);
-      if (row < M) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = bf16_round(g[i]);
-          float s = bf16_round(x / (1.0f + __expf(-x)));
-          g[i] = s * bf16_round(u[i]);
+    for (int c32 = 0; c32 < 2; ++c32) {
+      float g[32], u[32];
+      acc.load32(c32 * 32, g);
+      acc.load32(c32 * 32 + 64, u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float x0, x1;
+          unpack_bf16x2(pack_bf16x2(g[8 * q + 2 * k], g[8 * q + 2 * k + 1]), x0, x1);
+          const uint32_t sl = pack_bf16x2(__fdividef(x0, 1.0f + __expf(-x0)), __fdividef(x1, 1.0f + __expf(-x1)));
+          o[k] = bmul2(sl, pack_bf16x2(u[8 * q + 2 * k], u[8 * q + 2 * k + 1]));
         }
-        store_bf16x32(out + (size_t)row * ldo + f0 + c, g);
+        *stg.at(lane, c32 * 4 + q) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
+    stg.store_rows(lane, 64, [&](int r) -> bf16* {
+      return row0 + r < M ? out + (size_t)(row0 + r) * ldo + f0 : nullptr;
+    });
   }
 };
 
 // proj_out (ConvTranspose1d k=2 s=2 as a GEMM with N = 2*64): column n = k*64 + o lands at
 // vt[b, 2*s + k, o]; frames >= T (the odd-length pad) are cropped.  (turbo modeling :1284-1294,1498)
 struct EpiProjOut {
-  static constexpr bool kHalfTile = false;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kHalfTile = false;
   bf16* vt;  // [Bc, T, 64]
   const bf16* bias;  // [64]
   int S, T;
-  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
     static_assert(BN == 128, "EpiProjOut");
-    const bool ok = row < M;
-    const int b = ok ? row / S : 0;
-    const int s = ok ? row % S : 0;
+    const int lane = threadIdx.x & 31, row0 = row - lane;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32], bb[32];
-      acc.load32(c, v);
-      const int k = c >> 6;
-      const int t = 2 * s + k;
-      if (ok && t < T) {
-        load_bf16x32(bias + (c & 63), bb);
+    for (int k = 0; k < 2; ++k) {  // kernel tap k = 64-column half k
+#pragma unroll
+      for (int c32 = 0; c32 < 2; ++c32) {
+        float v[32], bb[32];
+        acc.load32(k * 64 + c32 * 32, v);
+        load_bf16x32(bias + c32 * 32, bb);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += bb[i];
-        store_bf16x32(vt + ((size_t)b * T + t) * 64 + (c & 63), v);
+        stg.put32(lane, c32, v);
       }
+      stg.store_rows(lane, 64, [&](int r) -> bf16* {
+        const int gr = row0 + r;
+        if (gr >= M) return nullptr;
+        const int b = gr / S, t = 2 * (gr % S) + k;
+        return t < T ? vt + ((size_t)b * T + t) * 64 : nullptr;
+      });
     }
   }
 };
@@ -262,9 +421,12 @@ __device__ __forceinline__ float snake_f(float x, float a, float ib) {
 }
 
 // Codec convolution epilogue.  v = bf16(acc + bias[c]) (+ resid) -> optional main store,
-// optional Snake'd copy for the next conv's A operand, optional fp32 store.
+// optional Snake'd copy for the next conv's A operand.
 // Flat element index = row*ldo + n + off must lie in [0, total) — this is how the transposed
 // convolution's "-padding" shift and its ragged ends are cropped.
+// Thread-per-row on purpose: the codec's rows are short (128..2048 channels) and its GEMMs have few
+// k-blocks, so the epilogue's latency is exposed; the staged/coalesced variant measured 11 % slower
+// on the whole decode (profiles/r1_notes.md), the 16-byte-per-thread stores merge in L2.
 struct EpiConv {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out_main;        // may be null
@@ -273,19 +435,18 @@ struct EpiConv {
   const float* bias;     // [chan_mod] or null
   const float* sn_a;     // [chan_mod] (used when out_snake)
   const float* sn_ib;    // [chan_mod]
-  float* out_f32;        // may be null
   long ldo, off, total;
   int chan_mod;          // channel of column n is n % chan_mod (a multiple of 32)
   // residual rows are re-read by the thread that produces the output row: pull them into L1 early
-  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage&) const {
     if (resid == nullptr || row >= M) return;
     const long idx = (long)row * ldo + n0 + off;
     if (idx < 0 || idx >= total) return;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(resid + idx));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(resid + idx + 64));
+    l1_prefetch(resid + idx);
+    l1_prefetch(resid + idx + 64);
   }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage&) const {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       const long idx = (long)row * ldo + n0 + c + off;
@@ -320,10 +481,6 @@ struct EpiConv {
           }
         }
         if (out_main) store_bf16x32(out_main + idx, v);
-        if (out_f32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) out_f32[idx + i] = v[i];
-        }
         if (out_snake) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {

@@ -24,6 +24,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "epilogues.cuh"  // WarpStage + the epilogue functors
 
 namespace ace {
 
@@ -116,8 +117,10 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual align
+  static constexpr int BAR_BYTES = 256;                 // (2 * STAGES + 4) mbarriers + TMEM slot
+  static constexpr int EPI_BYTES = 8 * 4096;            // one 32 x 64 bf16 staging slab per epilogue warp
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int TOTAL = OFF_EPI + EPI_BYTES + 1024;  // +1024: manual align
 };
 
 template <int BN, int STAGES, class Epi>
@@ -249,13 +252,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
-      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+      const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
+      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
       __syncwarp();
       if (live) {
         AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
-        epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+        epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -282,12 +286,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 //             empty[s], tmem_full[a]  (both CTAs, signalled by multicast tcgen05.commit)
 //             tmem_empty[a]           (leader only, 8 arrivals = 4 epilogue warps x 2 CTAs)
 // ---------------------------------------------------------------------------------------------
-template <int STAGES, class Epi>
+#ifdef ACE_GEMM_TIMING
+// probe builds only: per-phase globaltimer stamps of cluster 0 / CTA 0 (ns)
+__device__ unsigned long long g_gemm_stamps[16];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ACE_STAMP(i) do { if (blockIdx.x == 0) g_gemm_stamps[i] = gtimer(); } while (0)
+#else
+#define ACE_STAMP(i) do { } while (0)
+#endif
+
+template <int BN, int STAGES, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const GemmShape shp, const Epi epi) {
-  constexpr int BN = 256;
-  using L = GemmSmem<128, STAGES>;  // per-CTA stage: 128 A rows + 128 B rows
+  // BN = 256, or 192 for epilogues that accept 64-column sub-tiles: 256 x 192 pair tiles turn the
+  // 48-tile N = 2048 problems of the DiT (48 of 74 clusters busy) into 66 tiles (66 of 74).
+  static_assert(BN == 256 || (BN == 192 && Epi::kHalfTile), "pair tile width");
+  constexpr int HALF = BN / 2;       // B rows staged by each CTA of the pair
+  using L = GemmSmem<HALF, STAGES>;  // per-CTA stage: 128 A rows + HALF B rows
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -305,6 +325,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  if (threadIdx.x == 0) ACE_STAMP(0);
 
   pdl_trigger();
   if (warp == 3) gemm_prefetch_next(shp, lane);
@@ -332,6 +353,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (threadIdx.x == 0) ACE_STAMP(1);
 
   const int m_tiles = (shp.M + 255) / 256;
   const int n_tiles = (shp.N + BN - 1) / BN;
@@ -347,7 +369,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-        const int n0 = (tile / m_tiles) * BN + (int)rank * 128;
+        const int n0 = (tile / m_tiles) * BN + (int)rank * HALF;
         int tap = 0, kk = 0;
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -356,6 +378,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           } else {
             mbar_arrive_remote(&full_bar[stage], 0);
           }
+          if (kb == 0 && tile == cluster_id) ACE_STAMP(2);
           tma_load_2d_pair(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK,
                            m0 + shp.shift[tap]);
           tma_load_2d_pair(sB + stage * L::B_BYTES, &tma_b, &full_bar[stage],
@@ -386,6 +409,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (kb == 0 && it == 0) ACE_STAMP(3);
           tcgen05_fence_after();
           const uint64_t da = make_umma_desc_k128(smem_u32(sA + stage * L::A_BYTES));
           const uint64_t db = make_umma_desc_k128(smem_u32(sB + stage * L::B_BYTES));
@@ -395,7 +419,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
                               (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_pair(&empty_bar[stage], 3);
-          if (kb == total_kb - 1) umma_commit_pair(&tfull_bar[as], 3);
+          if (kb == total_kb - 1) {
+            umma_commit_pair(&tfull_bar[as], 3);
+            ACE_STAMP(4);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -417,17 +444,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
-      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+      const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
+      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);
+      if (threadIdx.x == 128) ACE_STAMP(5);
       tcgen05_fence_after();
       __syncwarp();
       if (live) {
         AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
-        epi.template run<128>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N);
+        if (BN == 256 || sub == 0) {
+          epi.template run<128>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+        } else {
+          epi.template run<(BN == 256 ? 128 : BN - 128)>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+      if (threadIdx.x == 128) ACE_STAMP(6);
     }
   }
 
@@ -435,6 +469,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   cluster_sync_all();
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 64) ACE_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,9 +484,12 @@ __global__ void __launch_bounds__(128)
 gemm_ref_epilogue_kernel(const float* __restrict__ scratch, int ld, GemmShape shp, const Epi epi) {
   const int m0 = blockIdx.x * GEMM_BM;
   const int n0 = blockIdx.y * BN;
+  __shared__ __align__(16) uint8_t stage_mem[4 * 4096];
   const int row = m0 + threadIdx.x;
   AccGlobal acc{scratch + (size_t)row * ld + n0};
-  epi.template run<BN>(acc, row, n0, shp.M, shp.N);
+  const WarpStage stg{stage_mem + (threadIdx.x >> 5) * 4096};
+  epi.prefetch(row, n0, shp.M, shp.N, stg);
+  epi.template run<BN>(acc, row, n0, shp.M, shp.N, stg);
 }
 
 template <int BN, int STAGES, class Epi>
@@ -484,6 +522,7 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   const int tiles = ceil_div(p.shp.M, GEMM_BM) * ceil_div(p.shp.N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
+  prof_tag_gemm(p.shp.M, p.shp.N, (int)ktot);
   prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
@@ -495,38 +534,49 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   return ACE_OK;
 }
 
-template <class Epi>
+template <int BN, int STAGES, class Epi>
 int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
-  constexpr int STAGES = 6;
-  using L = GemmSmem<128, STAGES>;
+  using L = GemmSmem<BN / 2, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ACE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, Epi>,
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, Epi>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = ceil_div(p.shp.M, 256) * ceil_div(p.shp.N, 256);
+  const int tiles = ceil_div(p.shp.M, 256) * ceil_div(p.shp.N, BN);
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
   const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
+  prof_tag_gemm(p.shp.M, p.shp.N, (int)ktot);
   prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
-  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<STAGES, Epi>, dim3(grid), dim3(GEMM2_THREADS),
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<BN, STAGES, Epi>, dim3(grid), dim3(GEMM2_THREADS),
                                (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
 
-// bn selects the tile: 128 -> single-CTA 128 x 128 tiles, 256 -> CTA-pair 256 x 256 tiles.
+template <class Epi>
+int launch_gemm_pair192(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+  if constexpr (Epi::kHalfTile) {
+    return launch_gemm_pair<192, 6, Epi>(p, epi, stream);
+  } else {
+    set_error("launch_gemm: BLOCK_N 192 needs a half-tile capable epilogue");
+    return ACE_ERR_UNSUPPORTED;
+  }
+}
+
+// bn selects the tile: 128 -> single-CTA 128 x 128 tiles, 256 / 192 -> CTA-pair 256 x bn tiles.
 // (The scalar debug path always runs the epilogue per 128-column sub-tile, like both kernels do.)
 template <class Epi>
 int launch_gemm(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   if (p.shp.M <= 0 || p.shp.N <= 0) return ACE_OK;
   if (gemm_debug_reference() || p.bn == 128) return launch_gemm_bn<128, 6, Epi>(p, epi, stream);
-  if (p.bn == 256) return launch_gemm_pair<Epi>(p, epi, stream);
+  if (p.bn == 256) return launch_gemm_pair<256, 6, Epi>(p, epi, stream);
+  if (p.bn == 192) return launch_gemm_pair192<Epi>(p, epi, stream);
   set_error("launch_gemm: unsupported BLOCK_N %d", p.bn);
   return ACE_ERR_UNSUPPORTED;
 }

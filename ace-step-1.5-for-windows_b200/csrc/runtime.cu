@@ -40,7 +40,15 @@ struct ProfRec {
   int cat;
   cudaEvent_t a, b;
   double flops, bytes;
+  int m, n, k;  // GEMM launches only (0 otherwise)
 };
+struct ShapeAgg {
+  int m, n, k, launches;
+  double ms;
+};
+static std::vector<ShapeAgg> g_shapes;  // per-(M,N,K) totals of the last profiling window
+static int g_tag_m = 0, g_tag_n = 0, g_tag_k = 0;
+void prof_tag_gemm(int m, int n, int k) { g_tag_m = m; g_tag_n = n; g_tag_k = k; }
 static uint64_t g_launches = 0;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -51,7 +59,12 @@ bool prof_active() { return g_prof_on; }
 void prof_begin(int cat, double flops, double bytes, cudaStream_t st) {
   ++g_launches;
   if (!g_prof_on) return;
-  ProfRec r{cat, nullptr, nullptr, flops, bytes};
+  ProfRec r{cat, nullptr, nullptr, flops, bytes, 0, 0, 0};
+  if (cat == PROF_GEMM) {
+    r.m = g_tag_m;
+    r.n = g_tag_n;
+    r.k = g_tag_k;
+  }
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, st);
@@ -78,6 +91,7 @@ int prof_stop(float* ms, double* flops, double* bytes, int* launches) {
     flops[c] = bytes[c] = 0.0;
     launches[c] = 0;
   }
+  g_shapes.clear();
   for (ProfRec& r : g_prof) {
     float t = 0.f;
     if (e == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cat >= 0 &&
@@ -86,6 +100,17 @@ int prof_stop(float* ms, double* flops, double* bytes, int* launches) {
       flops[r.cat] += r.flops;
       bytes[r.cat] += r.bytes;
       launches[r.cat] += 1;
+      if (r.cat == PROF_GEMM) {
+        bool found = false;
+        for (ShapeAgg& s : g_shapes)
+          if (s.m == r.m && s.n == r.n && s.k == r.k) {
+            s.launches += 1;
+            s.ms += t;
+            found = true;
+            break;
+          }
+        if (!found) g_shapes.push_back(ShapeAgg{r.m, r.n, r.k, 1, (double)t});
+      }
     }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -96,6 +121,25 @@ int prof_stop(float* ms, double* flops, double* bytes, int* launches) {
     return ACE_ERR_CUDA;
   }
   return ACE_OK;
+}
+
+// Top GEMM shapes (by total time) of the last profiling window; returns how many were written.
+int prof_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms) {
+  std::vector<ShapeAgg> v = g_shapes;
+  for (size_t i = 0; i < v.size(); ++i)
+    for (size_t j = i + 1; j < v.size(); ++j)
+      if (v[j].ms > v[i].ms) std::swap(v[i], v[j]);
+  int cnt = 0;
+  for (const ShapeAgg& s : v) {
+    if (cnt >= max_out) break;
+    m[cnt] = s.m;
+    n[cnt] = s.n;
+    k[cnt] = s.k;
+    launches[cnt] = s.launches;
+    ms[cnt] = (float)s.ms;
+    ++cnt;
+  }
+  return cnt;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -179,8 +223,26 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
       forced = e ? atoi(e) : 0;
     }
     bn = forced ? forced : ((n >= 256 && m > 128) ? 256 : 128);
+  } else if (bn == -192) {
+    // auto among {128, 256, 192}: the caller's epilogue accepts 64-column sub-tiles.  Cost model:
+    // waves of CTA pairs x tile width (the main loop time of one pair tile is proportional to bn).
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("ACE_GEMM_BN");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced) {
+      bn = forced;
+    } else if (!(n >= 256 && m > 128)) {
+      bn = 128;
+    } else {
+      const int clusters = num_sms() / 2, mt = ceil_div(m, 256);
+      const long c256 = (long)ceil_div(mt * ceil_div(n, 256), clusters) * 256;
+      const long c192 = (long)ceil_div(mt * ceil_div(n, 192), clusters) * 192;
+      bn = c192 < c256 ? 192 : 256;
+    }
   }
-  ACE_REQUIRE(bn == 128 || bn == 256, "gemm: BLOCK_N %d unsupported", bn);
+  ACE_REQUIRE(bn == 128 || bn == 256 || bn == 192, "gemm: BLOCK_N %d unsupported", bn);
   memset(plan, 0, sizeof(*plan));
   plan->shp.M = m;
   plan->shp.N = n;
@@ -197,9 +259,10 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
   if (m <= 0 || n <= 0) return ACE_OK;
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_a, a, (uint64_t)kc, (uint64_t)a_rows,
                                (uint64_t)a_ld * sizeof(bf16), GEMM_BM));
-  // both kernels stage B in 128-row boxes (the CTA-pair kernel loads one half of N per CTA)
+  // B is staged in 128-row boxes (the 256-wide pair kernel loads one half of N per CTA), 96-row
+  // boxes for the 192-wide pair tile
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_b, b, (uint64_t)ntaps * kc, (uint64_t)n,
-                               (uint64_t)b_ld * sizeof(bf16), 128u));
+                               (uint64_t)b_ld * sizeof(bf16), bn == 192 ? 96u : 128u));
   return ACE_OK;
 }
 

@@ -282,9 +282,9 @@ int res_unit(const ResUnitW& r, int dil, long L, int C, const bf16* x, const bf1
              bf16* oxs, const SnakeW& next, cudaStream_t st) {
   int sh[7];
   for (int k = 0; k < 7; ++k) sh[k] = (k - 3) * dil;
-  EpiConv e1{nullptr, hs, nullptr, r.c1.bias, r.s2.a, r.s2.ib, nullptr, (long)C, 0, L * C, C};
+  EpiConv e1{nullptr, hs, nullptr, r.c1.bias, r.s2.a, r.s2.ib, (long)C, 0, L * C, C};
   ACE_PROPAGATE(conv_gemm(xs, L, C, C, r.c1, C, L, 7, sh, e1, st));
-  EpiConv e2{ox, oxs, x, r.c2.bias, next.a, next.ib, nullptr, (long)C, 0, L * C, C};
+  EpiConv e2{ox, oxs, x, r.c2.bias, next.a, next.ib, (long)C, 0, L * C, C};
   const int z = 0;
   return conv_gemm(hs, L, C, C, r.c2, C, L, 1, &z, e2, st);
 }
@@ -403,7 +403,7 @@ int ace_vae_decode(AceVae* v, const uint16_t* d_z, int frames, float* d_wav, voi
     const StageW& s0 = v->dec[0];
     int sh[7];
     for (int k = 0; k < 7; ++k) sh[k] = k - 3;
-    EpiConv e{nullptr, xs, nullptr, v->dec_conv1.bias, s0.snake.a, s0.snake.ib, nullptr, (long)s0.cin, 0,
+    EpiConv e{nullptr, xs, nullptr, v->dec_conv1.bias, s0.snake.a, s0.snake.ib, (long)s0.cin, 0,
               L * s0.cin, s0.cin};
     ACE_PROPAGATE(conv_gemm((const bf16*)d_z, L, Cz, Cz, v->dec_conv1, s0.cin, L, 7, sh, e, st));
   }
@@ -413,7 +413,7 @@ int ace_vae_decode(AceVae* v, const uint16_t* d_z, int frames, float* d_wav, voi
     // transposed conv: rows q = 0..L (L+1 of them), taps x[q], x[q-1]; output frames q*s - pad + p
     const long Lout = L * s.stride;
     const int sh2[2] = {0, -1};
-    EpiConv et{x, xs2, nullptr, s.conv.bias, s.ru[0].s1.a, s.ru[0].s1.ib, nullptr, (long)s.stride * s.cout,
+    EpiConv et{x, xs2, nullptr, s.conv.bias, s.ru[0].s1.a, s.ru[0].s1.ib, (long)s.stride * s.cout,
                -(long)s.pad * s.cout, Lout * s.cout, s.cout};
     ACE_PROPAGATE(conv_gemm(xs, L, s.cin, s.cin, s.conv, s.stride * s.cout, L + 1, 2, sh2, et, st));
     L = Lout;
@@ -475,7 +475,7 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
     ACE_CUDA_CHECK(cudaMemsetAsync(xs2 - (size_t)s.pad * s.cin, 0, (size_t)s.pad * s.cin * 2, st));
     ACE_CUDA_CHECK(cudaMemsetAsync(xs2 + (size_t)L * s.cin, 0, (size_t)(s.pad + s.stride) * s.cin * 2, st));
     const SnakeW& next = (i + 1 < n) ? v->enc[i + 1].ru[0].s1 : v->enc_snake;
-    EpiConv e{x, xs, nullptr, s.conv.bias, next.a, next.ib, nullptr, (long)s.cout, 0, Lout * s.cout, s.cout};
+    EpiConv e{x, xs, nullptr, s.conv.bias, next.a, next.ib, (long)s.cout, 0, Lout * s.cout, s.cout};
     const int sh2[2] = {0, 1};
     ACE_PROPAGATE(conv_gemm(xs2 - (size_t)s.pad * s.cin, Lout + 1, s.stride * s.cin, (long)s.stride * s.cin, s.conv,
                             s.cout, Lout, 2, sh2, e, st));
@@ -485,7 +485,7 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
   {
     const int Cin = v->enc[n - 1].cout;
     const int sh3[3] = {-1, 0, 1};
-    EpiConv e{hs, nullptr, nullptr, v->enc_conv2.bias, nullptr, nullptr, nullptr, (long)H, 0, L * H, H};
+    EpiConv e{hs, nullptr, nullptr, v->enc_conv2.bias, nullptr, nullptr, (long)H, 0, L * H, H};
     ACE_PROPAGATE(conv_gemm(xs, L, Cin, Cin, v->enc_conv2, H, L, 3, sh3, e, st));
     const int Cz = v->cfg.latent_channels;
     const long tot = L * Cz;

@@ -151,6 +151,9 @@ uint64_t ace_launch_count(void);
  * FLOPs, algorithmic HBM bytes and launch counts. */
 void ace_profile_start(void);
 int ace_profile_stop(float* ms, double* flops, double* bytes, int* launches);
+/* After ace_profile_stop: the GEMM problem shapes of the window, sorted by total time (returns the
+ * number written, at most max_out): per shape (M, N, K) the launch count and summed milliseconds. */
+int ace_profile_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Test / bring-up hooks (never used by the product path)                                       */

@@ -1,0 +1,58 @@
+// gemm_timing.cu — probe build (-DACE_GEMM_TIMING): per-phase globaltimer stamps of the CTA-pair
+// GEMM for the four DiT problem shapes at the C2 bench size (M = 1500).  Dev tool, not shipped.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../ace-step-1.5-for-windows_b200/csrc/epilogues.cuh"
+#include "../ace-step-1.5-for-windows_b200/csrc/gemm.cuh"
+using namespace ace;
+
+int main() {
+  const int M = 1500, S = 750;
+  const int shapes[4][2] = {{2048, 2048}, {4096, 2048}, {12288, 2048}, {2048, 6144}};
+  char* flush;
+  cudaMalloc(&flush, 256u << 20);
+  for (auto& sh : shapes) {
+    const int N = sh[0], K = sh[1];
+    bf16 *A, *B, *H, *G;
+    cudaMalloc(&A, (size_t)M * K * 2);
+    cudaMalloc(&B, (size_t)N * K * 2);
+    cudaMalloc(&H, (size_t)M * N * 2);
+    cudaMalloc(&G, (size_t)2 * N * 2);
+    cudaMemset(A, 0, (size_t)M * K * 2);
+    cudaMemset(B, 0, (size_t)N * K * 2);
+    cudaMemset(H, 0, (size_t)M * N * 2);
+    cudaMemset(G, 0, (size_t)2 * N * 2);
+    GemmPlan p;
+    if (make_gemm_plan(&p, A, M, K, K, B, N, K, M, 1, nullptr, 256) != ACE_OK) {
+      printf("plan: %s\n", get_error());
+      return 1;
+    }
+    EpiGatedResid epi{H, (long)N, G, (long)N, S};
+    for (int rep = 0; rep < 3; ++rep) {
+      if (rep < 2) cudaMemset(flush, rep, 256u << 20);  // reps 0,1: cold L2; rep 2: warm
+      cudaDeviceSynchronize();
+      launch_gemm(p, epi, 0);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("kernel: %s\n", cudaGetErrorString(e));
+        return 1;
+      }
+      unsigned long long st[16];
+      cudaMemcpyFromSymbol(st, g_gemm_stamps, sizeof(st));
+      printf(
+          "N=%5d K=%5d rep%d: setup %6.2f | first-issue %6.2f | first-data %6.2f | mainloop %6.2f | "
+          "mma->epi %6.2f | epilogue %6.2f | teardown %6.2f | total %6.2f us\n",
+          N, K, rep, (st[1] - st[0]) * 1e-3, (st[2] - st[1]) * 1e-3, (st[3] - st[2]) * 1e-3,
+          (st[4] - st[3]) * 1e-3, (st[5] - st[4]) * 1e-3, (st[6] - st[5]) * 1e-3, (st[7] - st[6]) * 1e-3,
+          (st[7] - st[0]) * 1e-3);
+    }
+    cudaFree(A);
+    cudaFree(B);
+    cudaFree(H);
+    cudaFree(G);
+  }
+  return 0;
+}
