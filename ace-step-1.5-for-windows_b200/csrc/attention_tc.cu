@@ -145,65 +145,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
   const int nblk = (j_hi - j_lo + BKV - 1) / BKV;
 
+  // Both issue loops run warp-uniformly and predicate only the asynchronous instructions on one
+  // elected lane, so descriptors and barrier addresses stay in uniform registers (see elect_one).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
+    // ---------------- TMA producer ----------------
+    const bool elected = elect_one();
+    if (elected) {
       mbar_arrive_expect_tx(&bar[Q_FULL], 2 * Q_HALF);
       tma_load_3d(sQ, &tm_q, &bar[Q_FULL], h * HD, q0, b);
       tma_load_3d(sQ + Q_HALF, &tm_q, &bar[Q_FULL], h * HD + 64, q0, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int row = j_lo + j * BKV;
-        mbar_wait(&bar[K_EMPTY + s], ph ^ 1);
+    }
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int row = j_lo + j * BKV;
+      mbar_wait(&bar[K_EMPTY + s], ph ^ 1);
+      if (elected) {
         mbar_arrive_expect_tx(&bar[K_FULL + s], KV_TILE);
         tma_load_3d(sK + s * KV_TILE, &tm_k, &bar[K_FULL + s], hk * HD, row, b);
         tma_load_3d(sK + s * KV_TILE + KV_HALF, &tm_k, &bar[K_FULL + s], hk * HD + 64, row, b);
-        mbar_wait(&bar[V_EMPTY + s], ph ^ 1);
+      }
+      mbar_wait(&bar[V_EMPTY + s], ph ^ 1);
+      if (elected) {
         mbar_arrive_expect_tx(&bar[V_FULL + s], KV_TILE);
         tma_load_3d(sV + s * KV_TILE, &tm_v, &bar[V_FULL + s], hk * HD, row, b);
         tma_load_3d(sV + s * KV_TILE + KV_HALF, &tm_v, &bar[V_FULL + s], hk * HD + 64, row, b);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_qk = make_umma_idesc_bf16(128, BKV);               // A, B K-major
-      constexpr uint32_t idesc_pv = make_umma_idesc_bf16(128, 128) | (1u << 16);  // B MN-major
-      mbar_wait(&bar[Q_FULL], 0);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bar[K_FULL + s], ph);
-        mbar_wait(&bar[S_EMPTY + s], ph ^ 1);
-        tcgen05_fence_after();
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_qk = make_umma_idesc_bf16(128, BKV);               // A, B K-major
+    constexpr uint32_t idesc_pv = make_umma_idesc_bf16(128, 128) | (1u << 16);  // B MN-major
+    const bool elected = elect_one();
+    const uint32_t q_lo = (smem_u32(sQ) >> 4) & 0x3FFFu, k_lo = (smem_u32(sK) >> 4) & 0x3FFFu;
+    const uint32_t p_lo = (smem_u32(sP) >> 4) & 0x3FFFu;
+    // MN-major V: LBO (bytes between the two 64-wide head_dim atoms) sits in bits [16,30) of the low word
+    const uint32_t v_lo = ((smem_u32(sV) >> 4) & 0x3FFFu) | ((uint32_t)(KV_HALF >> 4) << 16);
+    mbar_wait(&bar[Q_FULL], 0);
+    auto issue_s = [&](int j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&bar[K_FULL + s], ph);
+      mbar_wait(&bar[S_EMPTY + s], ph ^ 1);
+      tcgen05_fence_after();
+      if (elected) {
         const uint32_t d = tmem_base + (uint32_t)(s * BKV);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {  // head_dim halves of 64
-          const uint64_t da = make_umma_desc_k128(smem_u32(sQ + half * Q_HALF));
-          const uint64_t db = make_umma_desc_k128(smem_u32(sK + s * KV_TILE + half * KV_HALF));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk,
-                         (half | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_lo(d, q_lo + (uint32_t)(half * (Q_HALF >> 4) + 2 * k),
+                            k_lo + (uint32_t)(s * (KV_TILE >> 4) + half * (KV_HALF >> 4) + 2 * k), idesc_qk,
+                            (half | k) != 0 ? 1u : 0u);
         }
         umma_commit(&bar[K_EMPTY + s]);
         umma_commit(&bar[S_FULL + s]);
-      };
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_s(j + 1);
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bar[V_FULL + s], ph);
-        mbar_wait(&bar[P_FULL], (uint32_t)(j & 1));
-        tcgen05_fence_after();
-        const uint64_t da = make_umma_desc_k128(smem_u32(sP));
+      }
+    };
+    issue_s(0);
+    for (int j = 0; j < nblk; ++j) {
+      if (j + 1 < nblk) issue_s(j + 1);
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&bar[V_FULL + s], ph);
+      mbar_wait(&bar[P_FULL], (uint32_t)(j & 1));
+      tcgen05_fence_after();
+      if (elected) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // 16 keys per MMA: P advances 32 B inside its swizzled row, V advances 16 rows (2048 B)
-          const uint64_t db = make_umma_desc_mn128(smem_u32(sV + s * KV_TILE) + (uint32_t)(k * 2048), KV_HALF);
-          umma_bf16_ss(tmem_o, da + (uint64_t)(2 * k), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_bf16_ss_lo(tmem_o, p_lo + (uint32_t)(2 * k),
+                          v_lo + (uint32_t)(s * (KV_TILE >> 4) + k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(&bar[V_EMPTY + s]);
         umma_commit(&bar[P_EMPTY]);

@@ -181,6 +181,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 // wait is bounded (~2 s of SM clocks) and traps, so a protocol bug surfaces as a
 // launch failure instead of a wedged GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;  // fast path: no clock read on the issue threads' critical path
 #if ACE_HANG_GUARD
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -345,6 +346,49 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
           "r"(smem_u32(bar)),
       "h"(mask)
+      : "memory");
+}
+
+// One lane of a CONVERGED warp (the same one every call).  The tcgen05 / TMA issue loops run
+// warp-uniformly and predicate only the asynchronous instructions on this, so that descriptors and
+// barrier addresses live in uniform registers: an `if (lane == 0)` loop makes every operand
+// divergent and costs five R2UR broadcasts plus a vote loop per MMA (measured: the issue thread,
+// not the tensor pipe, paced the main loop at 670 cycles per 64-deep K block instead of 512).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// High word of a K-major SWIZZLE_128B descriptor (see make_umma_desc_k128): SBO = 1024 B,
+// version 1, layout 2.  The low word is (smem address >> 4) & 0x3FFF, so stepping a stage or a
+// 32-byte K slice is a 32-bit add.
+constexpr uint32_t UMMA_DESC_K128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_K128_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                     uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_K128_HI)
       : "memory");
 }
 

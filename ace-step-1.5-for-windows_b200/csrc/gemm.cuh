@@ -179,62 +179,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int total_kb = shp.ntaps * shp.kblocks_per_tap;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * GEMM_BM;
-        const int n0 = (tile / m_tiles) * BN;
-        int tap = 0, kk = 0;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+    const bool elected = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % m_tiles) * GEMM_BM;
+      const int n0 = (tile / m_tiles) * BN;
+      int tap = 0, kk = 0;
+      int a_row = m0 + shp.shift[0];  // refreshed after the loads of a tap's last block (off the issue path)
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elected) {
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK,
-                      m0 + shp.shift[tap]);
+          tma_load_2d(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK, a_row);
           tma_load_2d(sB + stage * L::B_BYTES, &tma_b, &full_bar[stage],
                       tap * shp.b_tap_stride + kk * GEMM_BK, n0);
-          if (++kk == shp.kblocks_per_tap) {
-            kk = 0;
-            ++tap;
-          }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++kk == shp.kblocks_per_tap) {
+          kk = 0;
+          if (++tap < shp.ntaps) a_row = m0 + shp.shift[tap];
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer (one thread) ----------------
-      constexpr uint32_t idesc = make_umma_idesc_bf16(GEMM_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+    constexpr uint32_t idesc = make_umma_idesc_bf16(GEMM_BM, BN);
+    const bool elected = elect_one();
+    const uint32_t a_lo0 = (smem_u32(sA) >> 4) & 0x3FFFu, b_lo0 = (smem_u32(sB) >> 4) & 0x3FFFu;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t da = make_umma_desc_k128(smem_u32(sA + stage * L::A_BYTES));
-          const uint64_t db = make_umma_desc_k128(smem_u32(sB + stage * L::B_BYTES));
+        if (elected) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (L::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * (L::B_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == total_kb - 1) umma_commit(&tfull_bar[as]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -289,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #ifdef ACE_GEMM_TIMING
 // probe builds only: per-phase globaltimer stamps of cluster 0 / CTA 0 (ns)
 __device__ unsigned long long g_gemm_stamps[16];
+__device__ long long g_gemm_cycles[4];  // cluster 0 MMA issuer: clock64 at first data / loop exit, k-blocks issued
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -363,44 +366,50 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer (both CTAs) ----------------
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-        const int n0 = (tile / m_tiles) * BN + (int)rank * HALF;
-        int tap = 0, kk = 0;
-        for (int kb = 0; kb < total_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ---------------- TMA producer (both CTAs; warp-uniform loop, one elected lane issues) --------
+    const bool elected = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
+      const int n0 = (tile / m_tiles) * BN + (int)rank * HALF;
+      int tap = 0, kk = 0;
+      int a_row = m0 + shp.shift[0];  // refreshed after the loads of a tap's last block (off the issue path)
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elected) {
           if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
           } else {
             mbar_arrive_remote(&full_bar[stage], 0);
           }
           if (kb == 0 && tile == cluster_id) ACE_STAMP(2);
-          tma_load_2d_pair(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK,
-                           m0 + shp.shift[tap]);
+          tma_load_2d_pair(sA + stage * L::A_BYTES, &tma_a, &full_bar[stage], kk * GEMM_BK, a_row);
           tma_load_2d_pair(sB + stage * L::B_BYTES, &tma_b, &full_bar[stage],
                            tap * shp.b_tap_stride + kk * GEMM_BK, n0);
-          if (++kk == shp.kblocks_per_tap) {
-            kk = 0;
-            ++tap;
-          }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++kk == shp.kblocks_per_tap) {
+          kk = 0;
+          if (++tap < shp.ntaps) a_row = m0 + shp.shift[tap];
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (one thread of the leader CTA) ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) -------
       constexpr uint32_t idesc = make_umma_idesc_bf16(256, BN);
+      const bool elected = elect_one();
+      const uint32_t a_lo0 = (smem_u32(sA) >> 4) & 0x3FFFu, b_lo0 = (smem_u32(sB) >> 4) & 0x3FFFu;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+#ifdef ACE_GEMM_TIMING
+      long long c_first = 0, n_kb = 0;
+#endif
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -410,18 +419,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           if (kb == 0 && it == 0) ACE_STAMP(3);
+#ifdef ACE_GEMM_TIMING
+          if (kb == 0 && it == 0) c_first = clock64();
+          ++n_kb;
+#endif
           tcgen05_fence_after();
-          const uint64_t da = make_umma_desc_k128(smem_u32(sA + stage * L::A_BYTES));
-          const uint64_t db = make_umma_desc_k128(smem_u32(sB + stage * L::B_BYTES));
+          if (elected) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * (L::A_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)stage * (L::B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_ss_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_pair(&empty_bar[stage], 3);
-          if (kb == total_kb - 1) {
-            umma_commit_pair(&tfull_bar[as], 3);
-            ACE_STAMP(4);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+              umma_bf16_ss_pair_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (kb == total_kb - 1) {
+              umma_commit_pair(&tfull_bar[as], 3);
+              ACE_STAMP(4);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -429,6 +444,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
         }
       }
+#ifdef ACE_GEMM_TIMING
+      if (blockIdx.x == 0 && elected) {
+        g_gemm_cycles[0] = c_first;
+        g_gemm_cycles[1] = clock64();
+        g_gemm_cycles[2] = n_kb;
+      }
+#endif
     }
   } else if (warp >= 4) {
     // ---------------- epilogue (both CTAs, each on its own 128 accumulator rows) ----------------
@@ -544,7 +566,10 @@ int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles = ceil_div(p.shp.M, 256) * ceil_div(p.shp.N, BN);
-  const int max_clusters = num_sms() / 2;
+  int max_clusters = num_sms() / 2;
+#ifdef ACE_GEMM_TIMING
+  if (const char* e = getenv("ACE_GEMM_MAX_CLUSTERS")) max_clusters = atoi(e);  // probe builds only
+#endif
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
   const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
   prof_tag_gemm(p.shp.M, p.shp.N, (int)ktot);
