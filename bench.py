@@ -87,7 +87,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Median SM clock of the samples taken in [t0, t1] (perf_counter seconds)."""
+        v = []
+        for ts, ln in self.lines:
+            if t0 <= ts <= t1:
+                try:
+                    v.append(float(ln.split(",")[0]))
+                except ValueError:
+                    pass
+        return statistics.median(v) if v else None
 
     def stop(self):
         if not self.proc:
@@ -99,7 +110,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for _ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -261,31 +272,48 @@ def run_b200(args, wl):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = lib.ace_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = song_device()
-    drain()  # all gathers complete inside the timed region
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = lib.ace_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
-    finite = bool(torch.isfinite(out["audio"]).all())
+    win = {}
 
-    # end-to-end through the public API with host buffers
-    song_host()
-    barrier()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oh = song_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    def measure_value():
+        """EXACTLY K songs, device-resident inputs, CUDA events, barrier + synchronize on both sides."""
+        l0 = lib.ace_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            out = song_device()
+        drain()  # all gathers complete inside the timed region
+        e1.record()
+        barrier()
+        win["value"] = (w0, time.perf_counter())
+        return e0.elapsed_time(e1), lib.ace_launch_count() - l0, bool(torch.isfinite(out["audio"]).all())
+
+    def measure_e2e():
+        """K songs through the public API with pinned HOST inputs and a HOST waveform (wall clock)."""
+        song_host()
+        barrier()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oh = song_host()
+        barrier()
+        t1 = time.perf_counter()
+        win["e2e"] = (t0, t1)
+        return t1 - t0, oh["audio"].numel() * 4
+
+    # Both regions run under the same power cap; the order is fixed (device-resident first) and the
+    # SM clock of each region is reported so a throttling difference between them is visible.
+    if os.environ.get("ACE_BENCH_ORDER", "value_first") == "e2e_first":
+        (e2e_s, d2h), (ms, launches, finite) = measure_e2e(), measure_value()
+    else:
+        (ms, launches, finite), (e2e_s, d2h) = measure_value(), measure_e2e()
+    clk = None
+    if rank == 0:
+        clk = clocks.stop()
+        clk["sm_mhz"] = clocks.window(*win["value"]) or clk["sm_mhz"]
+        clk["sm_mhz_e2e_region"] = clocks.window(*win["e2e"])
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "ctx", "src")) + noise_h.numel() * 2
-    d2h = oh["audio"].numel() * 4
 
     if world > 1:
         tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
