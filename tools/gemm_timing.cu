@@ -31,10 +31,15 @@ int main() {
       return 1;
     }
     EpiGatedResid epi{H, (long)N, G, (long)N, S};
-    for (int rep = 0; rep < 3; ++rep) {
+    EpiGatedResid epi_nogate{H, (long)N, nullptr, 0, S};
+    EpiBias epi_bias{H, (long)N, nullptr};
+    for (int rep = 0; rep < 5; ++rep) {
       if (rep < 2) cudaMemset(flush, rep, 256u << 20);  // reps 0,1: cold L2; rep 2: warm
       cudaDeviceSynchronize();
-      launch_gemm(p, epi, 0);
+      // rep 2: gated residual (warm); rep 3: residual without gate; rep 4: plain store (EpiBias)
+      if (rep <= 2) launch_gemm(p, epi, 0);
+      else if (rep == 3) launch_gemm(p, epi_nogate, 0);
+      else launch_gemm(p, epi_bias, 0);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("kernel: %s\n", cudaGetErrorString(e));
