@@ -272,11 +272,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if ((unsigned)i - lo >= span) v[c][i] = -INFINITY;  // key outside [k_lo, k_hi)
         }
       }
-      float mx = -INFINITY;
+      // row maximum: four independent chains (a single fmaxf chain over 64 values is 64 dependent ops)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < HPT; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[c][i]);
+        for (int i = 0; i < 32; i += 4) {
+          mx4[0] = fmaxf(mx4[0], v[c][i]);
+          mx4[1] = fmaxf(mx4[1], v[c][i + 1]);
+          mx4[2] = fmaxf(mx4[2], v[c][i + 2]);
+          mx4[3] = fmaxf(mx4[3], v[c][i + 3]);
+        }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (NSW == 8) {  // combine the two half-row maxima (raw score domain; scale > 0 commutes with max)
         xch[(s * 2 + hsel) * 128 + r] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -297,6 +304,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       const float neg_ref = (m_used == -INFINITY) ? 0.f : -m_used;
 
+      // P_j is computed into registers BEFORE waiting for the P buffer, so the exponentials of this
+      // block overlap the PV MMA of the previous one (which still reads the buffer)
+      uint32_t w[HPT][16];
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < HPT; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(fmaf(v[c][i], p.scale_log2, neg_ref));
+          const float p1 = exp2f(fmaf(v[c][i + 1], p.scale_log2, neg_ref));
+          rs[i & 2] += p0;
+          rs[(i & 2) + 1] += p1;
+          w[c][i >> 1] = pack_bf16x2(p0, p1);
+        }
+      }
+      l_run += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+
       // P buffer (and O) are free once PV_{j-1} has retired
       mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
       if (warp_grow && j > 0) {
@@ -310,26 +334,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_st_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
         }
       }
-      float rs0 = 0.f, rs1 = 0.f;
       uint8_t* rowp = sP + r * 128;
 #pragma unroll
       for (int c = 0; c < HPT; ++c) {
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(fmaf(v[c][i], p.scale_log2, neg_ref));
-          const float p1 = exp2f(fmaf(v[c][i + 1], p.scale_log2, neg_ref));
-          rs0 += p0;
-          rs1 += p1;
-          w[i >> 1] = pack_bf16x2(p0, p1);
-        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = ((hsel * HPT + c) * 4 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+              make_uint4(w[c][4 * q], w[c][4 * q + 1], w[c][4 * q + 2], w[c][4 * q + 3]);
         }
       }
-      l_run += rs0 + rs1;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
       tcgen05_fence_before();
       __syncwarp();

@@ -51,51 +51,77 @@ namespace {
 
 constexpr int HALO = 16;  // zero rows kept before/after every activation buffer
 
-// decoder conv2: Snake'd [L,128] bf16 -> planar fp32 [2, L]; k=7, pad 3, no bias.
+// decoder conv2: Snake'd [L,C] bf16 -> planar fp32 [2, L]; k=7, pad 3, no bias.
+// HBM-bound by construction (reads L*C*2 bytes, 10 GFLOP at C2): the work is SIMT FMA, blocked so
+// that shared-memory traffic stays far below the FMA rate.  A block covers FC_POS output positions;
+// a thread owns 4 consecutive positions x both output channels x 1/8 of the input channels (two
+// 8-channel groups per 128 channels, interleaved so a warp's 16-byte reads are contiguous), i.e.
+// 10 input rows and 14 weight vectors feed 4*2*7 = 56 dot products; the 8 channel lanes are then
+// reduced with shuffles.
+constexpr int FC_POS = 128;  // output positions per block (256 threads = 32 position groups x 8 channel lanes)
 __global__ void __launch_bounds__(256)
 final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[2][7][C]*/, float* __restrict__ out,
                   long L, int C) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) uint8_t fc_smem[];
   pdl_trigger();
-  pdl_wait();
-  float* sw = sm;                 // 2*7*C
-  float* sx = sm + 2 * 7 * C;     // (256+6) * (C+1)
+  float* sw = reinterpret_cast<float*>(fc_smem);                       // [2][7][C] fp32
+  uint4* sx = reinterpret_cast<uint4*>(fc_smem + (size_t)14 * C * 4);  // [(FC_POS + 6)][C] bf16
   const int tid = threadIdx.x;
-  const long l0 = (long)blockIdx.x * 256;
-  for (int i = tid; i < 14 * C; i += 256) sw[i] = w[i];
-  const int rows = 256 + 6;
-  for (int i = tid; i < rows * (C / 8); i += 256) {
-    const int r = i / (C / 8), c8 = i % (C / 8);
+  const long l0 = (long)blockIdx.x * FC_POS;
+  for (int i = tid; i < 14 * C; i += 256) sw[i] = w[i];  // weights: not produced by the previous kernel
+  pdl_wait();
+  const int row_u4 = C / 8;  // uint4 per row
+  for (int i = tid; i < (FC_POS + 6) * row_u4; i += 256) {
+    const int r = i / row_u4;
     const long l = l0 - 3 + r;
-    float v[8];
-    if (l >= 0 && l < L) {
-      uint4 q = *reinterpret_cast<const uint4*>(x + l * C + c8 * 8);
-      unpack_bf16x2(q.x, v[0], v[1]);
-      unpack_bf16x2(q.y, v[2], v[3]);
-      unpack_bf16x2(q.z, v[4], v[5]);
-      unpack_bf16x2(q.w, v[6], v[7]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sx[r * (C + 1) + c8 * 8 + k] = v[k];
+    sx[i] = (l >= 0 && l < L) ? reinterpret_cast<const uint4*>(x + l * C)[i - r * row_u4] : make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  const long l = l0 + tid;
-  if (l >= L) return;
-  float a0 = 0.f, a1 = 0.f;
-  for (int k = 0; k < 7; ++k) {
-    const float* xr = sx + (tid + k) * (C + 1);
-    const float* w0 = sw + k * C;
-    const float* w1 = sw + (7 + k) * C;
-    for (int c = 0; c < C; ++c) {
-      a0 = fmaf(xr[c], w0[c], a0);
-      a1 = fmaf(xr[c], w1[c], a1);
+  const int cl = tid & 7, pg = tid >> 3;  // channel lane, position group
+  float acc[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.f;
+  for (int cg = cl; cg < row_u4; cg += 8) {  // this lane's 8-channel groups
+    float xv[10][8];
+#pragma unroll
+    for (int rr = 0; rr < 10; ++rr) {
+      const uint4 q = sx[(4 * pg + rr) * row_u4 + cg];
+      unpack_bf16x2(q.x, xv[rr][0], xv[rr][1]);
+      unpack_bf16x2(q.y, xv[rr][2], xv[rr][3]);
+      unpack_bf16x2(q.z, xv[rr][4], xv[rr][5]);
+      unpack_bf16x2(q.w, xv[rr][6], xv[rr][7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+      for (int co = 0; co < 2; ++co) {
+        const float4 wa = *reinterpret_cast<const float4*>(sw + (co * 7 + k) * C + cg * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(sw + (co * 7 + k) * C + cg * 8 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* xr = xv[j + k];
+          float a = acc[j][co];
+          a = fmaf(xr[0], wa.x, a); a = fmaf(xr[1], wa.y, a); a = fmaf(xr[2], wa.z, a); a = fmaf(xr[3], wa.w, a);
+          a = fmaf(xr[4], wb.x, a); a = fmaf(xr[5], wb.y, a); a = fmaf(xr[6], wb.z, a); a = fmaf(xr[7], wb.w, a);
+          acc[j][co] = a;
+        }
+      }
     }
   }
-  out[l] = bf16_round(a0);
-  out[L + l] = bf16_round(a1);
+  // reduce over the 8 channel lanes (adjacent lanes of the warp); lane cl then stores value cl of the 8
+  float mine = 0.f;
+#pragma unroll
+  for (int co = 0; co < 2; ++co)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[j][co];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (cl == co * 4 + j) mine = v;
+    }
+  const long l = l0 + 4 * pg + (cl & 3);
+  if (l < L) out[(long)(cl >> 2) * L + l] = bf16_round(mine);
 }
 
 // encoder conv1: planar fp32 [2, N] -> [N, C] bf16 (+ Snake'd copy); k=7, pad 3, with bias.
@@ -425,14 +451,14 @@ int ace_vae_decode(AceVae* v, const uint16_t* d_z, int frames, float* d_wav, voi
     // block output: x2 (unused further) and xs = Snake_next(x2): the next ConvT's / final conv's input
   }
   const int C = v->cfg.decoder_channels;
-  const int smem = (14 * C + 262 * (C + 1)) * 4;
+  const int smem = 14 * C * 4 + (FC_POS + 6) * C * 2;
   static bool attr = false;
   if (!attr) {
     ACE_CUDA_CHECK(cudaFuncSetAttribute(final_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
   prof_begin(PROF_CONV_SIMT, 2.0 * L * 14 * C, (double)L * (C * 2 + 8), st);
-  final_conv_kernel<<<(unsigned)((L + 255) / 256), 256, smem, st>>>(xs, v->dec_conv2, d_wav, L, C);
+  final_conv_kernel<<<(unsigned)((L + FC_POS - 1) / FC_POS), 256, smem, st>>>(xs, v->dec_conv2, d_wav, L, C);
   prof_end(st);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
