@@ -306,6 +306,25 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       : "r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// TMA load multicast to every CTA of `mask` in this cluster: the box lands at the same smem offset in
+// each destination CTA and credits the mbarrier at the same offset there.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
+                                                  int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// single-CTA MMAs, but the arrival goes to the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 // TMA load issued by either CTA of a pair; the bytes land in the issuing CTA's smem but the
 // transaction count is credited to the LEADER CTA's mbarrier (peer bit 24 of the address cleared).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,

@@ -25,6 +25,7 @@
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
+#include "resunit.cuh"
 
 namespace ace {
 
@@ -304,8 +305,24 @@ int conv_gemm(const bf16* a, long a_rows, int kc, long a_ld, const ConvW& w, int
 // Residual unit on x [L, C] (and its Snake'd copy xs): returns new x / xs in the `o*` buffers.
 //   h  = conv7_d(snake1(x))            A = xs           epilogue: snake2 -> hs
 //   x' = x + conv1(snake2(h))          A = hs           epilogue: + x, also snake_next(x') -> oxs
+int g_fused_override = -1;  // ace_debug_set_vae_fused: -1 = environment default, 0 / 1 = forced
+bool fused_res_unit_enabled() {
+  if (g_fused_override >= 0) return g_fused_override != 0;
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ACE_VAE_FUSED");  // ACE_VAE_FUSED=0: two-launch path (A/B measurements)
+    on = !(e && e[0] == '0');
+  }
+  return on != 0;
+}
+
 int res_unit(const ResUnitW& r, int dil, long L, int C, const bf16* x, const bf16* xs, bf16* hs, bf16* ox,
              bf16* oxs, const SnakeW& next, cudaStream_t st) {
+  if (C == RU_C && fused_res_unit_enabled() && !gemm_debug_reference()) {
+    // 128-channel stages (2/3 of the codec's HBM traffic): the whole unit in one kernel, hs stays on chip
+    RuParams p{(int)L, dil, r.c1.bias, r.s2.a, r.s2.ib, r.c2.bias, next.a, next.ib, ox, oxs};
+    return launch_res_unit_fused(xs, x, r.c1.w, r.c2.w, p, st);
+  }
   int sh[7];
   for (int k = 0; k < 7; ++k) sh[k] = (k - 3) * dil;
   EpiConv e1{nullptr, hs, nullptr, r.c1.bias, r.s2.a, r.s2.ib, (long)C, 0, L * C, C};
@@ -344,6 +361,8 @@ size_t enc_max_elems(const AceVae* v, long samples) {
 }  // namespace
 
 extern "C" {
+
+void ace_debug_set_vae_fused(int on) { g_fused_override = on < 0 ? -1 : (on != 0); }
 
 size_t ace_vae_packed_bytes(const AceVaeConfig* cfg) {
   if (!cfg || cfg->num_stages < 1 || cfg->num_stages > 8) return 0;

@@ -160,6 +160,10 @@ int ace_profile_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, 
 /* ------------------------------------------------------------------------------------------ */
 /* 1: route every GEMM through the scalar reference kernels (validates epilogues independently). */
 void ace_debug_set_gemm_reference(int on);
+/* Codec residual units of the 128-channel stages: 1 = single fused kernel (csrc/resunit.cuh),
+ * 0 = two launches of the tap-shifted GEMM, -1 = default (fused unless ACE_VAE_FUSED=0).  Both paths
+ * round at the same points, so their outputs are bit-identical (the test that uses this hook). */
+void ace_debug_set_vae_fused(int on);
 /* D = A[m,k] * B[n,k]^T + bias, bf16 in/out, through the tcgen05 path (tests/bench). */
 int ace_debug_linear(const uint16_t* d_a, const uint16_t* d_b, const uint16_t* d_bias, uint16_t* d_out,
                      int m, int n, int k, void* stream);

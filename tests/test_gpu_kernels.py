@@ -210,3 +210,28 @@ def test_vae_encode_tiny(lib, ref):
     tol = max(1.1 * floor, 2e-2)
     assert rel_l2(got_mean.cpu().float(), want_mean) <= tol, floor
     assert rel_l2(got.cpu().float(), want) <= tol, floor
+
+
+@pytest.mark.parametrize("frames", [5, 75, 301, 13000])
+def test_fused_res_unit_matches_two_launch_path(lib, frames):
+    """csrc/resunit.cuh (one kernel per residual unit at the 128-channel stages) rounds at the same
+    points as the two-launch tap-shifted GEMM path, so decode and encode must agree bit for bit."""
+    cfg, sd, shape = _tiny_vae()
+    g = torch.Generator().manual_seed(50 + frames)
+    z = torch.randn(1, 64, frames, generator=g).to(torch.bfloat16)
+    audio = torch.rand(2, cfg.hop * frames, generator=g) - 0.5
+    eps = torch.randn(frames, 64, generator=g).to(torch.bfloat16)
+    vae = B200Vae(sd, shape, DEV)
+    out = {}
+    try:
+        for mode in (0, 1):
+            lib.ace_debug_set_vae_fused(mode)
+            dec = vae.decode(z.to(DEV))
+            enc = vae.encode_samples(audio.to(DEV), eps.to(DEV))
+            torch.cuda.synchronize()
+            out[mode] = (dec.cpu(), enc.cpu())
+    finally:
+        lib.ace_debug_set_vae_fused(-1)
+    assert torch.isfinite(out[1][0]).all()
+    assert torch.equal(out[0][0], out[1][0]), max_abs(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1]), max_abs(out[0][1].float(), out[1][1].float())
