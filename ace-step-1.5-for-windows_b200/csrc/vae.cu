@@ -126,45 +126,54 @@ final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[2][
 }
 
 // encoder conv1: planar fp32 [2, N] -> [N, C] bf16 (+ Snake'd copy); k=7, pad 3, with bias.
+// HBM-bound on its two [N, C] outputs (3 GB for 120 s of audio).  A thread owns 2 adjacent channels
+// x FC1_S consecutive samples: its 28 weights and 2 x (FC1_S + 6) inputs live in registers, the input
+// loads are warp-wide broadcasts, and each store instruction of a warp writes 128 contiguous bytes
+// (32 lanes x one bf16 pair of the same sample).
+constexpr int FC1_S = 8;
 __global__ void __launch_bounds__(256)
 first_conv_kernel(const float* __restrict__ wav, const float* __restrict__ w /*[C][2][7]*/,
                   const float* __restrict__ bias, const float* __restrict__ sn_a, const float* __restrict__ sn_ib,
                   bf16* __restrict__ out, bf16* __restrict__ out_snake, long N, int C) {
-  // one thread per (sample, 8-channel group)
   pdl_trigger();
+  const int pairs = C / 2;                       // channel pairs per sample
+  const int groups_per_block = 256 / pairs;      // sample groups handled by one block (pairs divides 256)
+  const int cp = threadIdx.x % pairs, sg = threadIdx.x / pairs;
+  const long n0 = ((long)blockIdx.x * groups_per_block + sg) * FC1_S;
+  const int c = 2 * cp;
+  float wr[2][14];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int k = 0; k < 14; ++k) wr[j][k] = w[(c + j) * 14 + k];
+  const float b0 = bias[c], b1 = bias[c + 1];
+  const float a0 = sn_a[c], a1 = sn_a[c + 1], i0 = sn_ib[c], i1 = sn_ib[c + 1];
   pdl_wait();
-  const long idx = (long)blockIdx.x * 256 + threadIdx.x;
-  const int groups = C / 8;
-  if (idx >= N * groups) return;
-  const long n = idx / groups;
-  const int c0 = (int)(idx % groups) * 8;
-  float xin[2][7];
+  if (n0 >= N) return;
+  float xin[2][FC1_S + 6];
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const long m = n - 3 + k;
+    for (int k = 0; k < FC1_S + 6; ++k) {
+      const long m = n0 - 3 + k;
       xin[ch][k] = (m >= 0 && m < N) ? bf16_round(wav[ch * N + m]) : 0.f;
     }
-  float v[8], s[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    float acc = bias[c];
+  for (int s = 0; s < FC1_S; ++s) {
+    if (n0 + s >= N) break;
+    float acc0 = b0, acc1 = b1;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-      for (int k = 0; k < 7; ++k) acc = fmaf(xin[ch][k], w[(c * 2 + ch) * 7 + k], acc);
-    v[j] = bf16_round(acc);
-    s[j] = snake_f(v[j], sn_a[c], sn_ib[c]);
+      for (int k = 0; k < 7; ++k) {
+        acc0 = fmaf(xin[ch][s + k], wr[0][ch * 7 + k], acc0);
+        acc1 = fmaf(xin[ch][s + k], wr[1][ch * 7 + k], acc1);
+      }
+    const float v0 = bf16_round(acc0), v1 = bf16_round(acc1);
+    const long o = (n0 + s) * C + c;
+    *reinterpret_cast<uint32_t*>(out + o) = pack_bf16x2(v0, v1);
+    *reinterpret_cast<uint32_t*>(out_snake + o) = pack_bf16x2(snake_f(v0, a0, i0), snake_f(v1, a1, i1));
   }
-  uint4 q;
-  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(out + n * C + c0) = q;
-  q.x = pack_bf16x2(s[0], s[1]); q.y = pack_bf16x2(s[2], s[3]);
-  q.z = pack_bf16x2(s[4], s[5]); q.w = pack_bf16x2(s[6], s[7]);
-  *reinterpret_cast<uint4*>(out_snake + n * C + c0) = q;
 }
 
 // posterior: moments [L, 128] bf16 (mean | scale) -> z = mean + (softplus(scale) + 1e-4) * eps
@@ -501,10 +510,11 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
   const int n = v->cfg.num_stages;
   {
     const SnakeW& s1 = v->enc[0].ru[0].s1;
-    const long total = L * (H / 8);
+    ACE_REQUIRE(H % 2 == 0 && 256 % (H / 2) == 0, "encoder_hidden %d unsupported by the first conv kernel", H);
+    const long samples_per_block = (long)(256 / (H / 2)) * FC1_S;
     prof_begin(PROF_CONV_SIMT, 2.0 * L * 14 * H, (double)L * (8 + 4.0 * H), st);
-    first_conv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_wav, v->enc_conv1_w, v->enc_conv1_b,
-                                                                      s1.a, s1.ib, x, xs, L, H);
+    first_conv_kernel<<<(unsigned)((L + samples_per_block - 1) / samples_per_block), 256, 0, st>>>(
+        d_wav, v->enc_conv1_w, v->enc_conv1_b, s1.a, s1.ib, x, xs, L, H);
     prof_end(st);
     ACE_CUDA_CHECK(cudaGetLastError());
   }

@@ -77,3 +77,46 @@ class B200Pipeline:
             res["time_costs"]["vae_decode_time_cost"] = time.time() - t1
         res["time_costs"]["total_time_cost"] = time.time() - t0
         return res
+
+    # ------------------------------------------------------------------
+    def repaint(self, encoder_hidden_states, src_audio, repaint_start_frame: int, repaint_end_frame: int,
+                silence_latent, seed=None, *, posterior_eps=None, noise=None, to_host: bool = True,
+                **sampler_kwargs) -> Dict[str, Any]:
+        """Repaint / edit (BASELINE config 5): reference audio -> VAE encode -> DiT loop -> VAE decode.
+
+        Mirrors the slice of the reference between `_encode_audio_to_latents` (handler/batch_prep.py:63-76)
+        and the decode: the source latents keep the encoded audio outside [start, end) and the silence
+        latent inside, the chunk mask is 1 inside (handler/conditioning_masks.py:33-76), and
+        context_latents = [src_latents | chunk_mask] (modeling_acestep_v15_base.py:1651).
+
+        src_audio [B, 2, N] fp32 (host or device, N a multiple of the hop); silence_latent [1 or B, >=T, 64];
+        posterior_eps [B, T, 64] fixes the posterior sample (else torch's device RNG, like
+        latent_dist.sample()).  Returns generate()'s dict plus "src_latents"."""
+        t0 = time.time()
+        audio = src_audio.to(self.device, torch.float32, non_blocking=True)
+        if audio.dim() == 2:
+            audio = audio.unsqueeze(0)
+        B = audio.shape[0]
+        hop = self.vae.shape.hop
+        T = audio.shape[-1] // hop
+        lat = []
+        for b in range(B):
+            eps = None if posterior_eps is None else posterior_eps[b].to(self.device, torch.bfloat16)
+            if eps is None:
+                eps = torch.randn(T, 64, device=self.device, dtype=torch.bfloat16)
+            lat.append(self.vae.encode_samples(audio[b, :, : T * hop], eps))
+        target = torch.stack(lat, dim=0)  # [B, T, 64] bf16
+        t_enc = time.time() - t0
+        s0 = max(0, min(int(repaint_start_frame), T - 1))
+        s1 = max(s0 + 1, min(int(repaint_end_frame), T))
+        sil = self._dev(silence_latent)[:, :T, :].expand(B, -1, -1)
+        src = target.clone()
+        src[:, s0:s1] = sil[:, s0:s1]
+        mask = torch.zeros(B, T, 64, device=self.device, dtype=torch.bfloat16)
+        mask[:, s0:s1] = 1.0
+        ctx = torch.cat([src, mask], dim=-1)
+        out = self.generate(encoder_hidden_states, ctx, src, seed, noise=noise, to_host=to_host, **sampler_kwargs)
+        out["src_latents"] = target
+        out["time_costs"]["vae_encode_time_cost"] = t_enc
+        out["time_costs"]["total_time_cost"] = time.time() - t0
+        return out

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the ACE-Step hot path on B200 (contract: see DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3|c5]
 
 A "step" is one pass of the hot path over one batch of synthetic input: ONE SONG per GPU —
 denoising loop (base sampler, CFG + APG) on synthetic text-conditioning embeddings + VAE decode to
@@ -41,6 +41,9 @@ WORKLOADS = {
                desc="text2music 60 s, base sampler 27 steps, CFG 7.0 + APG, batch 1 (effective 2)"),
     "c3": dict(seconds=240, T=6000, steps=60, guidance=7.0, shift=3.0, E=512, turbo=False,
                desc="text2music 240 s, base sampler 60 steps, CFG 7.0 + APG, batch 1 (effective 2)"),
+    "c5": dict(seconds=120, T=3000, steps=27, guidance=7.0, shift=3.0, E=512, turbo=False, repaint=(750, 2250),
+               desc="repaint 120 s: VAE encode of the source audio -> base sampler 27 steps, CFG 7.0 + APG, frames "
+                    "[750, 2250) repainted -> VAE decode, batch 1 per GPU (effective 2)"),
 }
 
 
@@ -181,7 +184,9 @@ def run_reference(args, wl):
         fw.append(a)
         dec.append(b)
     t_fwd, t_win = statistics.mean(fw), statistics.mean(dec)
-    song = wl["steps"] * t_fwd + (wl["T"] / 64.0) * t_win
+    # repaint also encodes the source audio: the encoder mirrors the decoder (same FLOPs per frame), so it is
+    # charged as a second pass of the timed decode window
+    song = wl["steps"] * t_fwd + (wl["T"] / 64.0) * t_win * (2 if wl.get("repaint") else 1)
     value = wl["seconds"] / song
     sample = (f"per step: 1 DiT forward at effective batch {2 if wl['guidance'] > 1 else 1}, T={wl['T']}, "
               f"E={wl['E']} (cross-KV cached) + one 64-frame VAE decode window; extrapolated to "
@@ -238,7 +243,18 @@ def run_b200(args, wl):
     n_samples = T * vshape.hop
     gathered = [torch.empty(1, 2, n_samples, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
+    rp = wl.get("repaint")
+    if rp:  # config 5: the source audio is encoded inside the timed region
+        ga = torch.Generator().manual_seed(99 + rank)
+        audio_h = (torch.rand(1, 2, n_samples, generator=ga) - 0.5).pin_memory()
+        eps_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
+        sil_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
+        audio_d, eps_d, sil_d = audio_h.to(dev), eps_h.to(dev), sil_h.to(dev)
+
     def song_local():
+        if rp:
+            return pipe.repaint(dev_in["enc"], audio_d, rp[0], rp[1], sil_d, None, posterior_eps=eps_d, noise=noise_d,
+                                to_host=False, **skw)
         return pipe.generate(dev_in["enc"], dev_in["ctx"], dev_in["src"], None, noise=noise_d, to_host=False, **skw)
 
     pending = []
@@ -257,8 +273,10 @@ def run_b200(args, wl):
         pending.clear()
 
     def song_host():
-        out = pipe.generate(host["enc"], host["ctx"], host["src"], None, noise=noise_h, to_host=True, **skw)
-        return out
+        if rp:
+            return pipe.repaint(host["enc"], audio_h, rp[0], rp[1], sil_h, None, posterior_eps=eps_h, noise=noise_h,
+                                to_host=True, **skw)
+        return pipe.generate(host["enc"], host["ctx"], host["src"], None, noise=noise_h, to_host=True, **skw)
 
     def barrier():
         if world > 1:
@@ -313,7 +331,10 @@ def run_b200(args, wl):
         clk = clocks.stop()
         clk["sm_mhz"] = clocks.window(*win["value"]) or clk["sm_mhz"]
         clk["sm_mhz_e2e_region"] = clocks.window(*win["e2e"])
-    h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "ctx", "src")) + noise_h.numel() * 2
+    if rp:
+        h2d = (host["enc"].numel() + noise_h.numel() + eps_h.numel() + sil_h.numel()) * 2 + audio_h.numel() * 4
+    else:
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "ctx", "src")) + noise_h.numel() * 2
 
     if world > 1:
         tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
@@ -348,7 +369,7 @@ def run_b200(args, wl):
                 traffic = json.load(f).get(f"{dom['m']}x{dom['n']}x{dom['k']}")
         Bc = 2 if wl["guidance"] > 1.0 else 1
         S = (T + 1) // 2
-        song_flops = wl["steps"] * dit_flops(Bc, S, E) + vae_flops_per_frame() * T
+        song_flops = wl["steps"] * dit_flops(Bc, S, E) + vae_flops_per_frame() * T * (2 if rp else 1)
         audio_s = wl["seconds"] * world * args.steps
         value = audio_s / (ms * 1e-3)
         line = {
@@ -389,7 +410,7 @@ def run_b200(args, wl):
             one_sample, threads = cpu_sample(wl)
             one_sample()
             a, b = one_sample()
-            song = wl["steps"] * a + (T / 64.0) * b
+            song = wl["steps"] * a + (T / 64.0) * b * (2 if rp else 1)
             line["cpu_baseline"] = {
                 "value": wl["seconds"] / song, "unit": "audio-s/s", "cores": threads, "kind": "port",
                 "sample": (f"1 DiT forward (effective batch {2 if wl['guidance'] > 1 else 1}, T={T}, E={E}) = {a:.2f} s and one "
