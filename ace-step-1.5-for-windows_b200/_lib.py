@@ -34,6 +34,15 @@ class AceVaeConfig(C.Structure):
     ]
 
 
+class AceEncConfig(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int), ("intermediate_size", C.c_int), ("num_layers", C.c_int),
+        ("num_heads", C.c_int), ("num_kv_heads", C.c_int), ("head_dim", C.c_int),
+        ("sliding_window", C.c_int), ("layer_is_sliding", C.c_int * 64), ("in_dim", C.c_int),
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); must list every symbol of include/acestep_b200.h
 SIGNATURES = {
@@ -59,6 +68,12 @@ SIGNATURES = {
     "ace_vae_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "ace_vae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "ace_dit_io_slots": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "ace_enc_packed_elems": (C.c_size_t, [C.POINTER(AceEncConfig)]),
+    "ace_enc_create": (C.c_int, [C.POINTER(_P), C.POINTER(AceEncConfig), _P, C.c_size_t]),
+    "ace_enc_destroy": (None, [_P]),
+    "ace_enc_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "ace_enc_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "ace_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ace_launch_count": (C.c_uint64, []),
     "ace_profile_start": (None, []),
     "ace_profile_stop": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -21,6 +21,7 @@ from typing import Any, Dict, Optional, Tuple
 
 import torch
 
+from .cond import B200ConditionEncoder, CondShape
 from .dit import B200DiT, DiTShape
 from .sampler import B200Sampler
 from .vae import B200Vae, VaeShape
@@ -31,12 +32,14 @@ class B200BackendMixin:
 
     use_b200_dit: bool = False
     use_b200_vae: bool = False
+    use_b200_cond: bool = False
+    b200_cond: Optional[B200ConditionEncoder] = None
     b200_dit: Optional[B200DiT] = None
     b200_sampler: Optional[B200Sampler] = None
     b200_vae: Optional[B200Vae] = None
 
     # ------------------------------------------------------------------ init
-    def _init_b200_backends(self, dit: bool = True, vae: bool = True) -> Tuple[str, str]:
+    def _init_b200_backends(self, dit: bool = True, vae: bool = True, cond: bool = True) -> Tuple[str, str]:
         """Build the engines from the already-loaded PyTorch modules' state_dict()s — the weight
         source the MLX converters use too (models/mlx/dit_convert.py:33-66).  Call again after a
         LoRA load/unload/scale change (lora/lifecycle.py:212-252 mutates model.decoder) to repack."""
@@ -51,6 +54,14 @@ class B200BackendMixin:
             self.b200_sampler = B200Sampler(self.b200_dit, getattr(self.model, "null_condition_emb", None))
             self.use_b200_dit = True
             dit_status = "Active (B200 tcgen05)"
+            if cond and getattr(self.model, "encoder", None) is not None:
+                # condition encoder: same layer kernels, weights from model.encoder
+                if self.b200_cond is not None:
+                    self.b200_cond.close()
+                self.b200_cond = B200ConditionEncoder(self.model.encoder.state_dict(),
+                                                      CondShape.from_config(self.model.config), device)
+                self.use_b200_cond = True
+                dit_status = "Active (B200 tcgen05, condition encoder included)"
         if vae:
             if self.b200_vae is not None:
                 self.b200_vae.close()
@@ -117,6 +128,35 @@ class B200BackendMixin:
         out["target_latents"] = out["target_latents"].to(device=self.device, dtype=self.dtype)
         return out
 
+    # ------------------------------------------------------------------ conditioning
+    def _b200_prepare_condition(self, *, text_hidden_states, text_attention_mask, lyric_hidden_states,
+                                lyric_attention_mask, refer_audio_acoustic_hidden_states_packed,
+                                refer_audio_order_mask, hidden_states, attention_mask, silence_latent, src_latents,
+                                chunk_masks, is_covers, precomputed_lm_hints_25Hz=None, audio_codes=None):
+        """`model.prepare_condition` (modeling_acestep_v15_turbo.py:1604-1649) with the condition encoder
+        (`self.encoder(...)`, :1621-1628) on the B200 kernels; same keywords, same 3-tuple.  The LM-hint
+        branch (tokenizer / FSQ / detokenizer, only consumed where is_covers > 0) stays on the stock
+        modules and is skipped entirely for plain text2music / repaint batches, whose hints the
+        reference computes and then discards (:1649)."""
+        dtype = hidden_states.dtype
+        enc, enc_mask = self.b200_cond(
+            text_hidden_states=text_hidden_states, text_attention_mask=text_attention_mask,
+            lyric_hidden_states=lyric_hidden_states, lyric_attention_mask=lyric_attention_mask,
+            refer_audio_acoustic_hidden_states_packed=refer_audio_acoustic_hidden_states_packed,
+            refer_audio_order_mask=refer_audio_order_mask)
+        if bool((is_covers > 0).any()):
+            if precomputed_lm_hints_25Hz is not None:
+                hints = precomputed_lm_hints_25Hz[:, : src_latents.shape[1], :]
+            else:
+                if audio_codes is not None:
+                    hints5 = self.model.tokenizer.quantizer.get_output_from_indices(audio_codes)
+                else:
+                    hints5, _, _ = self.model.tokenize(hidden_states, silence_latent, attention_mask)
+                hints = self.model.detokenize(hints5)[:, : src_latents.shape[1], :]
+            src_latents = torch.where(is_covers.unsqueeze(-1).unsqueeze(-1) > 0, hints, src_latents)
+        context_latents = torch.cat([src_latents, chunk_masks.to(dtype)], dim=-1)
+        return enc.to(dtype), enc_mask, context_latents
+
     # ------------------------------------------------------------------ codec
     def _b200_vae_decode(self, latents_torch: torch.Tensor) -> torch.Tensor:
         """latents [B, 64, T] -> audio [B, 2, T*1920] (fp32, on the device); cf. _mlx_vae_decode
@@ -150,14 +190,16 @@ def _execute_service_generate_diffusion(self, payload, generate_kwargs, seed_par
                 refer_audio_acoustic_hidden_states_packed=payload["refer_audio_acoustic_hidden_states_packed"],
                 refer_audio_order_mask=payload["refer_audio_order_mask"], silence_latent=self.silence_latent,
                 chunk_masks=payload["chunk_mask"])
-            enc, enc_mask, ctx = self.model.prepare_condition(
+            use_cond = getattr(self, "use_b200_cond", False) and self.b200_cond is not None
+            prepare = self._b200_prepare_condition if use_cond else self.model.prepare_condition
+            enc, enc_mask, ctx = prepare(
                 text_hidden_states=payload["text_hidden_states"], text_attention_mask=payload["text_attention_mask"],
                 hidden_states=src, attention_mask=ones(src), src_latents=src, is_covers=payload["is_covers"],
                 precomputed_lm_hints_25Hz=payload["precomputed_lm_hints_25Hz"], **cond)
             enc_nc = mask_nc = ctx_nc = None
             if audio_cover_strength < 1.0 and payload["non_cover_text_hidden_states"] is not None:
                 sil = self.silence_latent[:, : src.shape[1], :].expand(src.shape[0], -1, -1)
-                enc_nc, mask_nc, ctx_nc = self.model.prepare_condition(
+                enc_nc, mask_nc, ctx_nc = prepare(
                     text_hidden_states=payload["non_cover_text_hidden_states"],
                     text_attention_mask=payload["non_cover_text_attention_masks"], hidden_states=sil,
                     attention_mask=ones(sil), src_latents=sil, is_covers=torch.zeros_like(payload["is_covers"]), **cond)
@@ -199,8 +241,8 @@ _WRAPPED = {
     "tiled_decode": tiled_decode,
     "tiled_encode": tiled_encode,
 }
-_MIXIN_ATTRS = ("_init_b200_backends", "_b200_is_turbo", "_b200_run_diffusion", "_b200_vae_decode",
-                "_b200_vae_encode_sample")
+_MIXIN_ATTRS = ("_init_b200_backends", "_b200_is_turbo", "_b200_run_diffusion", "_b200_prepare_condition",
+                "_b200_vae_decode", "_b200_vae_encode_sample")
 
 
 def install(target):
@@ -222,8 +264,8 @@ def install(target):
             raise AttributeError(f"{cls.__name__} has no method '{name}' to wrap")
         setattr(target, "_ref_" + name.lstrip("_"), bind(original))
         setattr(target, name, bind(fn))
-    for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("b200_dit", None),
-                      ("b200_sampler", None), ("b200_vae", None)):
+    for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("use_b200_cond", False), ("b200_dit", None),
+                      ("b200_sampler", None), ("b200_vae", None), ("b200_cond", None)):
         if not hasattr(target, flag):
             setattr(target, flag, val)
     setattr(target, "_b200_installed", True)

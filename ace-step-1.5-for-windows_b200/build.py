@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 
-SOURCES = ["runtime.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dit.cu", "vae.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dit.cu", "vae.cu", "cond.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -135,13 +135,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tmem_o = tmem_base + 128u;
   pdl_wait();
 
-  // keys visited by this query tile
-  int j_lo = 0, j_hi = p.Skv;
+  // keys visited by this query tile; `skv` = this sample's valid (non-padding) keys
+  int skv = p.Skv;
+  if (p.kv_len != nullptr) {
+    skv = p.kv_len[b];
+    skv = skv < 1 ? 1 : (skv > p.Skv ? p.Skv : skv);
+  }
+  int j_lo = 0, j_hi = skv;
   if (p.window >= 0) {
     j_lo = q0 - p.window;
     if (j_lo < 0) j_lo = 0;
     j_hi = q0 + BQ - 1 + p.window + 1;
-    if (j_hi > p.Skv) j_hi = p.Skv;
+    if (j_hi > skv) j_hi = skv;
+    if (j_lo >= j_hi) j_lo = j_hi - 1;  // query tile entirely past the valid keys: one (fully masked-in-band) block
   }
   const int nblk = (j_hi - j_lo + BKV - 1) / BKV;
 
@@ -237,10 +243,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem + OFF_XCH);  // [2 parity + 1][2 halves][128 rows] (NSW == 8)
     // keys this row may attend to: [k_lo, k_hi)
-    int k_lo = 0, k_hi = p.Skv;
+    int k_lo = 0, k_hi = skv;
     if (p.window >= 0) {
       k_lo = qi - p.window > 0 ? qi - p.window : 0;
-      k_hi = qi + p.window + 1 < p.Skv ? qi + p.window + 1 : p.Skv;
+      k_hi = qi + p.window + 1 < skv ? qi + p.window + 1 : skv;
     }
     const unsigned span = k_hi > k_lo ? (unsigned)(k_hi - k_lo) : 0u;
     float m_used = -INFINITY, l_run = 0.f;
@@ -261,7 +267,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // this warp's slice of S_j is in registers
 
       // boundary blocks only: tail of the key range and the +-window band (tile-uniform test)
-      const bool interior = (jb0 + BKV <= p.Skv) &&
+      const bool interior = (jb0 + BKV <= skv) &&
                             (p.window < 0 || ((q0 + BQ - 1) - jb0 <= p.window && (jb0 + BKV - 1) - q0 <= p.window));
       if (!interior) {
 #pragma unroll

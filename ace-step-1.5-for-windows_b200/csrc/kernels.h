@@ -15,6 +15,8 @@ struct AttnParams {
   int window;               // < 0: full attention, else |i - j| <= window
   int group;                // query heads per KV head
   float scale_log2;         // head_dim^-0.5 * log2(e)
+  const int* kv_len;        // device [batch] or null: keys >= kv_len[b] are padding and masked (the
+                            // padding-aware create_4d_mask of the condition encoders, turbo :53-132)
 };
 // legacy mma.sync kernel (attention.cu) — kept for A/B measurements (ACE_ATTN=legacy)
 int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t stream);

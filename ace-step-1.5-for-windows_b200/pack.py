@@ -58,6 +58,31 @@ def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> 
 
 
 # --------------------------------------------------------------------------------------------
+# Condition encoders
+# --------------------------------------------------------------------------------------------
+def pack_encoder(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str) -> torch.Tensor:
+    """One encoder stack (`prefix` = "lyric_encoder." / "timbre_encoder." inside
+    AceStepConditionEncoder.state_dict(), modeling_acestep_v15_turbo.py:574-598, 994-1018) as the 1-D
+    bf16 blob ace_enc_create walks: embed_tokens, final norm, then per layer the two norms, fused qkv,
+    q/k norms, o_proj, gate/up interleaved in 64-row blocks (like pack_dit), down_proj."""
+    g = lambda k: _get(sd, prefix + k)
+    parts: List[torch.Tensor] = [g("embed_tokens.weight"), g("embed_tokens.bias"), g("norm.weight")]
+    for l in range(num_layers):
+        p = f"layers.{l}."
+        gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
+        inter, d = gate.shape
+        gate_up = torch.stack([gate.view(inter // 64, 64, d), up.view(inter // 64, 64, d)], dim=1).reshape(2 * inter, d)
+        parts += [
+            g(p + "input_layernorm.weight"), g(p + "post_attention_layernorm.weight"),
+            torch.cat([g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"),
+                       g(p + "self_attn.v_proj.weight")], dim=0),
+            g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight"), g(p + "self_attn.o_proj.weight"),
+            gate_up, g(p + "mlp.down_proj.weight"),
+        ]
+    return torch.cat([t.reshape(-1).to(torch.bfloat16) for t in parts]).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
 # VAE
 # --------------------------------------------------------------------------------------------
 def fold_weight_norm(sd: Dict[str, torch.Tensor], name: str) -> torch.Tensor:

@@ -141,6 +141,43 @@ int ace_vae_encode(AceVae* vae, const float* d_wav, int samples, const uint16_t*
 int ace_dit_io_slots(AceDit* dit, uint16_t** d_xt, uint16_t** d_ctx, uint16_t** d_vt);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Condition encoders: the lyric / timbre transformer stacks of                */
+/* AceStepConditionEncoder.forward, turbo modeling :1506-1552 (AceStepLyricEncoder :574-728,      */
+/* AceStepTimbreEncoder :994-1175, AceStepEncoderLayer :371-437).  One handle = one stack:        */
+/* embed_tokens Linear(in_dim -> hidden, bias) -> num_layers encoder layers -> final RMSNorm.      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct AceEncConfig {
+  int hidden_size;          /* 2048; multiple of 256 */
+  int intermediate_size;    /* 6144; multiple of 64 */
+  int num_layers;           /* 8 (lyric) / 4 (timbre) */
+  int num_heads;            /* 16 */
+  int num_kv_heads;         /* 8 */
+  int head_dim;             /* must be 128 */
+  int sliding_window;       /* 128 */
+  int layer_is_sliding[64]; /* per layer: 1 = +-window band, 0 = full attention */
+  int in_dim;               /* embed_tokens input width: 1024 (lyric) / 64 (timbre); multiple of 64 */
+  float rope_theta;         /* 1e6 */
+  float rms_eps;            /* 1e-6 */
+} AceEncConfig;
+typedef struct AceEnc AceEnc;
+
+/* Element count of the packed bf16 blob (acestep_b200/pack.py:pack_encoder is the one producer). */
+size_t ace_enc_packed_elems(const AceEncConfig* cfg);
+int ace_enc_create(AceEnc** out, const AceEncConfig* cfg, const uint16_t* weights, size_t n_elems);
+void ace_enc_destroy(AceEnc* enc);
+size_t ace_enc_workspace_bytes(const AceEnc* enc, int batch, int seq);
+/* d_in [batch, seq, in_dim] bf16 -> d_out [batch, seq, hidden] bf16.  d_kv_len: DEVICE int[batch] of
+ * valid (non-padding, left-aligned) tokens per sample, or NULL for no key-padding mask; semantics =
+ * the reference's additive create_4d_mask (:53-132), including the uniform softmax of rows whose
+ * whole band is padding. */
+int ace_enc_forward(AceEnc* enc, const uint16_t* d_in, const int* d_kv_len, uint16_t* d_out, int batch, int seq,
+                    void* ws, size_t ws_bytes, void* stream);
+/* out[m, n] = bf16(a[m, k] . w[n, k]^T + bias[n]) on the tcgen05 GEMM; bias may be NULL
+ * (text_projector, :1518).  k must be a multiple of 64. */
+int ace_linear(const uint16_t* d_a, const uint16_t* d_w, const uint16_t* d_bias, uint16_t* d_out, int m, int n,
+               int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Measurement hooks (bench.py): launch counter and per-launch CUDA-event profiling              */
 /* ------------------------------------------------------------------------------------------ */
 /* Number of kernels this library has launched in the calling process (graph replays included). */

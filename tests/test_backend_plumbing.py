@@ -132,6 +132,35 @@ def test_dit_seam_forwards_reference_arguments():
     assert {"diffusion_time_cost", "diffusion_per_step_time_cost", "total_time_cost"} <= set(out["time_costs"])
 
 
+def test_condition_seam_replaces_model_encoder_only():
+    """use_b200_cond: the encoder call of prepare_condition (:1621-1628) goes to b200_cond with the
+    reference's keywords; context_latents = [src | chunk_mask] (:1651); the stock prepare_condition is
+    not called; with is_covers > 0 the precomputed LM hints replace the source latents (:1649)."""
+    h = install(FakeHandler())
+    h.b200_sampler, h.use_b200_dit = StubSampler(), True
+    seen = []
+
+    def fake_cond(**kw):
+        seen.append(kw)
+        b = kw["text_hidden_states"].shape[0]
+        return torch.full((b, 6, 8), 7.0, dtype=torch.bfloat16), torch.ones(b, 6, dtype=torch.bool)
+
+    h.b200_cond, h.use_b200_cond = fake_cond, True
+    p = _payload()
+    p["text_hidden_states"] = torch.zeros(2, 3, 4)
+    p["src_latents"] = torch.full((2, 20, 64), 0.25)
+    p["chunk_mask"] = torch.ones(2, 20, 64, dtype=torch.bool)
+    p["is_covers"] = torch.tensor([0.0, 1.0])
+    p["precomputed_lm_hints_25Hz"] = torch.full((2, 24, 64), 0.5)
+    out, enc, mask, ctx = h._execute_service_generate_diffusion(p, {}, 1, "ode", 3.0, 1.0)
+    assert h.model.calls == [] and len(seen) == 1
+    assert set(seen[0]) == {"text_hidden_states", "text_attention_mask", "lyric_hidden_states", "lyric_attention_mask",
+                            "refer_audio_acoustic_hidden_states_packed", "refer_audio_order_mask"}
+    assert enc.dtype == torch.float32 and float(enc[0, 0, 0]) == 7.0 and mask.shape == (2, 6)
+    assert ctx.shape == (2, 20, 128) and float(ctx[0, 0, 0]) == 0.25 and float(ctx[1, 0, 0]) == 0.5
+    assert float(ctx[0, 0, 64]) == 1.0
+
+
 def test_turbo_models_use_the_turbo_sampler():
     h = install(FakeHandler())
     h.config.is_turbo = True

@@ -235,3 +235,59 @@ def test_fused_res_unit_matches_two_launch_path(lib, frames):
     assert torch.isfinite(out[1][0]).all()
     assert torch.equal(out[0][0], out[1][0]), max_abs(out[0][0], out[1][0])
     assert torch.equal(out[0][1], out[1][1]), max_abs(out[0][1].float(), out[1][1].float())
+
+
+def _cond_inputs(cfg, B, Ll, Lt, Lr, lyric_lens, text_lens, order, seed):
+    g = torch.Generator().manual_seed(seed)
+    lyric = torch.randn(B, Ll, cfg.text_hidden_dim, generator=g)
+    text = torch.randn(B, Lt, cfg.text_hidden_dim, generator=g)
+    refer = torch.randn(len(order), Lr, cfg.timbre_hidden_dim, generator=g)
+    lm = (torch.arange(Ll)[None] < torch.tensor(lyric_lens)[:, None]).long()
+    tm = (torch.arange(Lt)[None] < torch.tensor(text_lens)[:, None]).long()
+    return text, tm, lyric, lm, refer, torch.tensor(order, dtype=torch.long)
+
+
+@pytest.mark.parametrize("case", ["golden", "long"])
+def test_condition_encoder_vs_oracle(lib, case):
+    """csrc/cond.cu (lyric / timbre stacks with the key-padding mask) + acestep_b200.cond packing against
+    oracle.cond on bf16-rounded weights and inputs; bound = measured spread of an all-bf16 torch run of the
+    oracle (floor 2e-2), over EVERY row, padded ones included (the DiT cross-attends to them)."""
+    from acestep_b200.cond import B200ConditionEncoder, CondShape
+    from oracle.cond import CondConfig, condition_encoder, make_cond_weights
+
+    cfg = CondConfig.tiny()
+    w = bf16_round_(make_cond_weights(cfg, seed=5))
+    if case == "golden":
+        g = golden("cond_encoder")
+        args = [g[k] for k in ("text", "text_mask", "lyric", "lyric_mask", "refer", "order")]
+    else:  # several query tiles, padded tails longer than the window, ragged timbre packing
+        args = list(_cond_inputs(cfg, 3, 300, 40, 150, [300, 131, 17], [40, 9, 1], [0, 1, 1, 2, 2, 2], seed=77))
+    args = [a.to(torch.bfloat16).float() if a.is_floating_point() else a for a in args]
+    want, want_mask = condition_encoder(w, cfg, *args)
+    wb = {k: v.to(torch.bfloat16) for k, v in w.items()}
+    a16 = [a.to(torch.bfloat16) if a.is_floating_point() else a for a in args]
+    floor = rel_l2(condition_encoder(wb, cfg, *a16)[0].float(), want)
+    enc = B200ConditionEncoder(w, CondShape.from_config(cfg), DEV)
+    got, got_mask = enc(text_hidden_states=args[0], text_attention_mask=args[1], lyric_hidden_states=args[2],
+                        lyric_attention_mask=args[3], refer_audio_acoustic_hidden_states_packed=args[4],
+                        refer_audio_order_mask=args[5])
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert torch.equal(got_mask.cpu(), want_mask)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got.cpu().float(), want) <= max(1.5 * floor, 2e-2), floor
+    enc.close()
+
+
+def test_condition_encoder_rejects_unrepresentable_mask(lib):
+    from acestep_b200.cond import B200ConditionEncoder, CondShape
+    from oracle.cond import CondConfig, make_cond_weights
+
+    cfg = CondConfig.tiny()
+    enc = B200ConditionEncoder(make_cond_weights(cfg, seed=5), CondShape.from_config(cfg), DEV)
+    text, tm, lyric, lm, refer, order = _cond_inputs(cfg, 1, 16, 4, 8, [16], [4], [0], seed=1)
+    lm[0, 3] = 0  # a hole: not a right-padded mask
+    with pytest.raises(ValueError):
+        enc(text_hidden_states=text, text_attention_mask=tm, lyric_hidden_states=lyric, lyric_attention_mask=lm,
+            refer_audio_acoustic_hidden_states_packed=refer, refer_audio_order_mask=order)
+    enc.close()

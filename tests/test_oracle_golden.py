@@ -150,3 +150,34 @@ def test_vae_shapes_and_halo():
     audio = torch.rand(1, 2, 60 * cfg.hop) - 0.5
     m, s = ovae.encode_moments(w, cfg, audio)
     assert m.shape == (1, 64, 60) and s.shape == (1, 64, 60)
+
+
+def test_condition_encoder_matches_reference():
+    """oracle.cond vs the REAL AceStepConditionEncoder (tools/make_golden_cond.py): padded lyrics / text,
+    packed timbre references, and rows whose whole sliding band is padding (uniform softmax quirk)."""
+    from oracle.cond import CondConfig, condition_encoder, make_cond_weights
+
+    g = golden("cond_encoder")
+    cfg = CondConfig.tiny()
+    w = make_cond_weights(cfg, seed=5)
+    hs, m = condition_encoder(w, cfg, g["text"], g["text_mask"], g["lyric"], g["lyric_mask"], g["refer"], g["order"])
+    assert torch.equal(m.long(), g["out_mask"])
+    assert rel_l2(hs, g["out_hidden"]) <= 2e-5  # every row, padded ones included: the DiT attends to them
+
+
+def test_condition_sequence_plumbing_matches_oracle():
+    """acestep_b200.cond's device-side pack_sequences / unpack_timbre_embeddings (PyTorch host code,
+    runs on CPU tensors too) against the oracle restatement of :135-166 / :1020-1071."""
+    from acestep_b200.cond import pack_sequences, unpack_timbre_embeddings
+    from oracle import cond as ocond
+
+    gen = torch.Generator().manual_seed(3)
+    h1, h2 = torch.randn(3, 7, 16, generator=gen), torch.randn(3, 4, 16, generator=gen)
+    m1 = torch.tensor([[1] * 7, [1] * 3 + [0] * 4, [0] * 7])
+    m2 = torch.tensor([[1, 1, 0, 0], [1, 0, 0, 0], [1, 1, 1, 1]])
+    got, want = pack_sequences(h1, h2, m1, m2), ocond.pack_sequences(h1, h2, m1, m2)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    embs = torch.randn(6, 8, generator=gen)
+    order = torch.tensor([2, 0, 2, 1, 2, 0])
+    got, want = unpack_timbre_embeddings(embs, order), ocond.unpack_timbre(embs, order)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
