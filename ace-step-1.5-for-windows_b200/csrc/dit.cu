@@ -55,6 +55,7 @@ struct AceDit {
   bf16 *xcat, *h, *hn, *qkv, *attn, *qc, *act, *enc_e, *ckv, *temb, *tproj, *mods, *outmod, *te_scratch;
   bf16 *rope_cos, *rope_sin;
   float* t_dev;
+  uint8_t* splitk = nullptr;  // split-K scratch (partial tiles + counters), shared by all GEMMs of the step
   GemmPlan plan_in, plan_out;
   std::vector<LayerPlans> lp;
   cudaGraphExec_t graph = nullptr;
@@ -103,6 +104,7 @@ size_t carve_workspace(AceDit* d, uint8_t* base, int Bc, int T, int E) {
   d->rope_cos = c.take<bf16>((size_t)S * 64);
   d->rope_sin = c.take<bf16>((size_t)S * 64);
   d->t_dev = c.take<float>(16);
+  d->splitk = c.take<uint8_t>(gemm_splitk_scratch_bytes());
   return c.off + 256;
 }
 
@@ -414,6 +416,18 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
                     scale_log2};
       ACE_PROPAGATE(make_attn_plan(&p.cross_attn, cp, d->cfg.num_heads, bc));
     }
+  }
+  // small shapes (short clips, turbo without CFG): split K so that more than a handful of SMs stream the
+  // weights; the GEMMs of a step run one after another on one stream, so they share one scratch
+  {
+    const size_t sk = gemm_splitk_scratch_bytes();
+    ACE_CUDA_CHECK(cudaMemset(d->splitk + sk - GEMM_SPLITK_MAX_WORKS * 2 * sizeof(unsigned), 0,
+                              GEMM_SPLITK_MAX_WORKS * 2 * sizeof(unsigned)));
+    ACE_PROPAGATE(gemm_plan_enable_splitk(&d->plan_in, d->splitk, sk));
+    ACE_PROPAGATE(gemm_plan_enable_splitk(&d->plan_out, d->splitk, sk));
+    for (LayerPlans& p : d->lp)
+      for (GemmPlan* g : {&p.qkv, &p.self_o, &p.cross_q, &p.cross_o, &p.gate_up, &p.down, &p.cross_kv})
+        ACE_PROPAGATE(gemm_plan_enable_splitk(g, d->splitk, sk));
   }
   // chain the weight prefetches: every GEMM pulls the next GEMM's weights into L2
   if (!(getenv("ACE_NO_PREFETCH") && getenv("ACE_NO_PREFETCH")[0] == '1')) {

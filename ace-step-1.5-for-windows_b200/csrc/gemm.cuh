@@ -46,6 +46,12 @@ struct GemmShape {
   // B-operand TMA load pays DRAM latency and the 6-stage ring cannot cover it (profiles/r1_notes.md).
   const uint8_t* pf_ptr;
   unsigned long long pf_bytes;
+  // Split-K (single-CTA kernel, BLOCK_N 128 only; see gemm_tc_kernel): `splits` CTAs share one output
+  // tile, each accumulating a K slice; partial fp32 tiles go through `part` ([work][128][128]) and the
+  // per-tile {arrive, done} counters in `sync`.  splits <= 1: off.
+  int splits;
+  float* part;
+  unsigned* sync;
 };
 
 #ifdef __CUDACC__
@@ -88,6 +94,17 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
 int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
                    int n, long b_ld, int m, int ntaps, const int* shifts, int bn);
 
+// Split-K for problems with few output tiles (M <= a few hundred rows).  `scratch_bytes(works)` of
+// device memory hold the partial tiles followed by the per-tile counters (zero-initialised once by the
+// caller; the kernel re-arms them).  gemm_plan_enable_splitk decides from the shape (cost model in
+// runtime.cu), may switch a pair-tile plan to single-CTA 128-wide tiles, and leaves the plan untouched
+// when splitting would not pay or the scratch is too small.
+constexpr int GEMM_SPLITK_MAX_WORKS = 160;
+inline size_t gemm_splitk_scratch_bytes() {
+  return (size_t)GEMM_SPLITK_MAX_WORKS * GEMM_BM * 128 * sizeof(float) + (size_t)GEMM_SPLITK_MAX_WORKS * 2 * sizeof(unsigned);
+}
+int gemm_plan_enable_splitk(GemmPlan* plan, void* scratch, size_t scratch_bytes);
+
 // Debug switch (tests only): route launches through the scalar reference kernels below so the
 // epilogues and the surrounding pipeline can be validated independently of the tcgen05 main loop.
 void set_gemm_debug_reference(bool on);
@@ -102,6 +119,16 @@ struct AccTmem {
   uint32_t taddr;  // lane-quarter base | first column of this tile's accumulator
   __device__ __forceinline__ void load32(int col, float (&v)[32]) const {
     tmem_ld_32x32(taddr + (uint32_t)col, v);
+  }
+};
+struct AccSmem {
+  const float* p;  // &reduced[row_in_slice * BN + first column of this warp]
+  __device__ __forceinline__ void load32(int col, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = *reinterpret_cast<const float4*>(p + col + 4 * i);
+      v[4 * i + 0] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
   }
 };
 struct AccGlobal {
@@ -175,20 +202,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (shp.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int total_kb = shp.ntaps * shp.kblocks_per_tap;
+  // Split-K: work item w = tile * S + s covers K blocks [s * total_kb / S, (s + 1) * total_kb / S).
+  // Small-M problems (a 10 s clip is M = 125) have too few output tiles to pull the weights through
+  // more than a handful of SMs (16 tiles at N = 2048: 1.7 TB/s of the 6.5 TB/s HBM can reach them);
+  // S CTAs per tile stream disjoint K slices instead.  The launcher guarantees works <= #SMs, i.e.
+  // every CTA of the grid is resident, which the inter-CTA wait below relies on.
+  const int S = shp.splits > 1 ? shp.splits : 1;
+  const int num_works = m_tiles * n_tiles * S;
 
   if (warp == 0) {
     // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
     const bool elected = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_works; work += gridDim.x) {
+      const int tile = work / S, sp = work - tile * S;
       const int m0 = (tile % m_tiles) * GEMM_BM;
       const int n0 = (tile / m_tiles) * BN;
-      int tap = 0, kk = 0;
-      int a_row = m0 + shp.shift[0];  // refreshed after the loads of a tap's last block (off the issue path)
-      for (int kb = 0; kb < total_kb; ++kb) {
+      const int kb0 = (int)((long)sp * total_kb / S), kb1 = (int)((long)(sp + 1) * total_kb / S);
+      int tap = kb0 / shp.kblocks_per_tap, kk = kb0 - tap * shp.kblocks_per_tap;
+      int a_row = m0 + shp.shift[tap];  // refreshed after the loads of a tap's last block (off the issue path)
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elected) {
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -214,13 +249,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_works; work += gridDim.x, ++it) {
+      const int sp = work % S;
+      const int kb0 = (int)((long)sp * total_kb / S), kb1 = (int)((long)(sp + 1) * total_kb / S);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-      for (int kb = 0; kb < total_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elected) {
@@ -229,10 +266,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            umma_bf16_ss_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == total_kb - 1) umma_commit(&tfull_bar[as]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -246,26 +283,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // eight warps (4-7: columns [0,BN/2), 8-11: [BN/2,BN)); head-structured ones use warps 4-7.
     const int quarter = (warp - 4) & 3;
     constexpr int EBN = Epi::kHalfTile ? BN / 2 : BN;
+    constexpr int EPI_THREADS = Epi::kHalfTile ? 256 : 128;
     const int sub = Epi::kHalfTile ? ((warp - 4) >> 2) * EBN : 0;
+    const int epi_tid = threadIdx.x - 128;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < num_works; work += gridDim.x, ++it) {
+      const int tile = work / S, sp = work - tile * S;
       const int m0 = (tile % m_tiles) * GEMM_BM;
       const int n0 = (tile / m_tiles) * BN + sub;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
       const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
-      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+      if (S == 1 && live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
       __syncwarp();
-      if (live) {
-        AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
-        epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+      AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
+      if (S == 1) {
+        if (live) epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
+      // ---- split-K tail (grid == num_works: exactly one work item per CTA) ----
+      // (1) this CTA's partial accumulator -> global scratch
+      float* mine = shp.part + (size_t)work * (GEMM_BM * BN) + (size_t)(quarter * 32 + lane) * BN + sub;
+#pragma unroll 1
+      for (int c = 0; c < EBN; c += 32) {
+        float v[32];
+        acc.load32(c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          __stcg(reinterpret_cast<float4*>(mine + c) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      // (2) wait until all S partials of this tile are in L2.  The CTA barrier orders every warp's stores
+      //     before thread 0's gpu-scope fence + arrive (fences are cumulative), and thread 0's acquire
+      //     before the other warps' loads on the way back.
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+      if (epi_tid == 0) {
+        unsigned* arrive = shp.sync + 2 * tile;
+        __threadfence();
+        atomicAdd(arrive, 1u);
+        unsigned seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+        } while (seen < (unsigned)S);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+      // (3) rows [sp * R, sp * R + R) of the tile are reduced by this CTA, in split order (deterministic),
+      //     into shared memory (the operand stages are idle by now).  All S loads of an element are in
+      //     flight together: one L2 round trip per pass.
+      const int R = GEMM_BM / S;
+      float* red = reinterpret_cast<float*>(smem);
+      const float4* tile_part =
+          reinterpret_cast<const float4*>(shp.part + (size_t)tile * S * (GEMM_BM * BN) + (size_t)sp * R * BN);
+      for (int idx = epi_tid; idx < R * (BN / 4); idx += EPI_THREADS) {
+        float4 b[8];
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss)
+          if (ss < S) b[ss] = __ldcg(tile_part + (size_t)ss * (GEMM_BM * BN / 4) + idx);
+        float4 a = b[0];
+#pragma unroll
+        for (int ss = 1; ss < 8; ++ss)
+          if (ss < S) {
+            a.x += b[ss].x; a.y += b[ss].y; a.z += b[ss].z; a.w += b[ss].w;
+          }
+        reinterpret_cast<float4*>(red)[idx] = a;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+      if (epi_tid == 0) {  // last reader of the tile re-arms its counters for the next launch
+        unsigned* sy = shp.sync + 2 * tile;
+        if (atomicAdd(sy + 1, 1u) == (unsigned)(S - 1)) {
+          sy[1] = 0u;
+          __threadfence();
+          sy[0] = 0u;
+        }
+      }
+      // (4) fused epilogue on the slice: slice row lr of this warp -> global row m0 + sp * R + lr
+      if (live && quarter * 32 < R) {
+        const int lr = quarter * 32 + lane;
+        const int row = m0 + sp * R + lr;
+        int m_end = m0 + sp * R + R;
+        if (m_end > shp.M) m_end = shp.M;
+        const AccSmem racc{red + (size_t)(lr < R ? lr : R - 1) * BN + sub};
+        epi.prefetch(row, n0, m_end, shp.N, stg);
+        epi.template run<EBN>(racc, row, n0, m_end, shp.N, stg);
+      }
     }
   }
 
@@ -542,7 +650,14 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles = ceil_div(p.shp.M, GEMM_BM) * ceil_div(p.shp.N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (p.shp.splits > 1) {
+    if (BN != 128 || tiles * p.shp.splits > num_sms() || p.shp.part == nullptr || p.shp.sync == nullptr) {
+      set_error("launch_gemm: invalid split-K plan (bn %d, %d tiles x %d splits)", BN, tiles, p.shp.splits);
+      return ACE_ERR_INVALID;
+    }
+    grid = tiles * p.shp.splits;  // one work item per CTA, all co-resident
+  }
   const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
   prof_tag_gemm(p.shp.M, p.shp.N, (int)ktot);
   prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,

@@ -266,6 +266,46 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
   return ACE_OK;
 }
 
+int gemm_plan_enable_splitk(GemmPlan* plan, void* scratch, size_t scratch_bytes) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("ACE_NO_SPLITK");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  const GemmShape& sh = plan->shp;
+  if (disabled || scratch == nullptr || scratch_bytes < gemm_splitk_scratch_bytes() || sh.M <= 0 || sh.N <= 0 ||
+      sh.N % 128 != 0)
+    return ACE_OK;
+  const int total_kb = sh.ntaps * sh.kblocks_per_tap, sms = num_sms();
+  const int tiles = ceil_div(sh.M, GEMM_BM) * (sh.N / 128);
+  int best = 1;
+  for (int s = 2; s <= 8; s *= 2)
+    if (tiles * s <= sms && tiles * s <= GEMM_SPLITK_MAX_WORKS && total_kb / s >= 2) best = s;
+  if (best == 1) return ACE_OK;
+  // Cost = operand KB one CTA has to ingest on the critical path (the main loops are TMA-ingest bound,
+  // ~57 B/clk/SM); the split-K tail (partial store, inter-CTA wait, reduce) is charged as 24 K blocks
+  // (~7 us): measured on B200, a 2-way split of M = 375 x N = 2048 x K = 2048 loses (16.8 vs 15.3 us)
+  // while 8-way splits at M = 125 win once the weights come from HBM rather than L2.
+  const long cost_split = (long)ceil_div(total_kb, best) * 32 + 24 * 32;
+  long cost_now;
+  if (plan->bn == 128) {
+    cost_now = (long)ceil_div(tiles, sms) * total_kb * 32;
+  } else {
+    const int pair_tiles = ceil_div(sh.M, 256) * ceil_div(sh.N, plan->bn);
+    cost_now = (long)ceil_div(pair_tiles, sms / 2) * total_kb * (plan->bn == 192 ? 28 : 32);
+  }
+  if (cost_split >= cost_now) return ACE_OK;
+  if (plan->bn == 192)  // the single-CTA kernel stages B in 128-row boxes
+    ACE_PROPAGATE(encode_tmap_2d(&plan->tma_b, plan->b_ptr, (uint64_t)sh.ntaps * sh.b_tap_stride, (uint64_t)sh.N,
+                                 (uint64_t)plan->b_ld * sizeof(bf16), 128u));
+  plan->bn = 128;
+  plan->shp.splits = best;
+  plan->shp.part = reinterpret_cast<float*>(scratch);
+  plan->shp.sync = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(scratch) +
+                                               (size_t)GEMM_SPLITK_MAX_WORKS * GEMM_BM * 128 * sizeof(float));
+  return ACE_OK;
+}
+
 static bool g_debug_ref = false;
 void set_gemm_debug_reference(bool on) { g_debug_ref = on; }
 bool gemm_debug_reference() { return g_debug_ref; }

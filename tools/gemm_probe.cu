@@ -36,7 +36,7 @@ static float bf2f(uint16_t b) {
 }
 
 static int run_case(const char* name, int M, int N, int kc, int ntaps, const int* shifts,
-                    int a_rows, bool ref_path, int check_stride, int timing_iters, int bn = 128) {
+                    int a_rows, bool ref_path, int check_stride, int timing_iters, int bn = 128, bool splitk = false) {
   const long Ktot = (long)ntaps * kc;
   std::vector<uint16_t> hA((size_t)a_rows * kc), hB((size_t)N * Ktot), hbias(N);
   for (auto& x : hA) x = f2bf(frand());
@@ -55,6 +55,17 @@ static int run_case(const char* name, int M, int N, int kc, int ntaps, const int
   if (make_gemm_plan(&plan, dA, a_rows, kc, kc, dB, N, Ktot, M, ntaps, shifts, bn) != ACE_OK) {
     printf("[%s] plan failed: %s\n", name, get_error());
     return 1;
+  }
+  void* scratch = nullptr;
+  if (splitk) {  // let the cost model decide; report what it chose
+    CK(cudaMalloc(&scratch, gemm_splitk_scratch_bytes()));
+    CK(cudaMemset(scratch, 0, gemm_splitk_scratch_bytes()));
+    if (gemm_plan_enable_splitk(&plan, scratch, gemm_splitk_scratch_bytes()) != ACE_OK) {
+      printf("[%s] split-K plan failed: %s\n", name, get_error());
+      return 1;
+    }
+    printf("[%s] split-K: bn=%d splits=%d\n", name, plan.bn, plan.shp.splits);
+    bn = plan.bn;
   }
   EpiBias epi{dO, (long)N, dbias};
   set_gemm_debug_reference(ref_path);
@@ -108,6 +119,7 @@ static int run_case(const char* name, int M, int N, int kc, int ntaps, const int
   cudaFree(dB);
   cudaFree(dbias);
   cudaFree(dO);
+  if (scratch) cudaFree(scratch);
   return pass ? 0 : 1;
 }
 
@@ -137,6 +149,16 @@ int main() {
   fails += run_case("pair-down", 1500, 2048, 6144, 1, one, 1500, false, 997, 20, 256);
   fails += run_case("pair-conv7", 5000, 512, 512, 7, conv7, 5000, false, 1013, 10, 256);
   fails += run_case("pair-conv7-n128", 96000, 128, 128, 7, conv7, 96000, false, 9973, 10, 256);
+  // split-K (few output tiles): every element checked on the small ones, launched repeatedly (counter re-arm)
+  fails += run_case("splitk-m125", 125, 2048, 2048, 1, one, 125, false, 1, 20, 0, true);
+  fails += run_case("nosplit-m125", 125, 2048, 2048, 1, one, 125, false, 97, 20, 0, false);
+  fails += run_case("splitk-qkv-m125", 125, 4096, 2048, 1, one, 125, false, 3, 20, 0, true);
+  fails += run_case("splitk-gateup-m125", 125, 12288, 2048, 1, one, 125, false, 997, 20, 0, true);
+  fails += run_case("splitk-down-m125", 125, 2048, 6144, 1, one, 125, false, 3, 20, 0, true);
+  fails += run_case("splitk-m375", 375, 2048, 2048, 1, one, 375, false, 7, 20, 0, true);
+  fails += run_case("nosplit-m375", 375, 2048, 2048, 1, one, 375, false, 97, 20, 0, false);
+  fails += run_case("splitk-m40-n128", 40, 128, 2048, 1, one, 40, false, 1, 20, 0, true);
+  fails += run_case("splitk-conv7", 200, 256, 128, 7, conv7, 200, false, 1, 0, 0, true);
   printf("gemm_probe: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }
