@@ -23,6 +23,7 @@ import torch
 
 from .cond import B200ConditionEncoder, CondShape
 from .dit import B200DiT, DiTShape
+from .pack import UnsupportedAdapterError, effective_decoder_state
 from .sampler import B200Sampler
 from .vae import B200Vae, VaeShape
 
@@ -50,7 +51,8 @@ class B200BackendMixin:
             shape = DiTShape.from_config(self.model.config)
             if self.b200_dit is not None:
                 self.b200_dit.close()
-            self.b200_dit = B200DiT(decoder.state_dict(), shape, device)
+            # adapter-aware: active PEFT LoRA deltas are folded into the packed weights
+            self.b200_dit = B200DiT(effective_decoder_state(decoder), shape, device)
             self.b200_sampler = B200Sampler(self.b200_dit, getattr(self.model, "null_condition_emb", None))
             self.use_b200_dit = True
             dit_status = "Active (B200 tcgen05)"
@@ -236,6 +238,33 @@ def tiled_encode(self, audio, chunk_size=None, overlap=None, offload_latent_to_c
     return self._ref_tiled_encode(audio, chunk_size, overlap, offload_latent_to_cpu)
 
 
+# Weight-mutation hooks.  Every LoRA lifecycle / control entry point of the handler
+# (handler/lora/lifecycle.py:164-440 add_lora / load_lora / add_voice_lora / remove_lora / unload_lora,
+# handler/lora/controls.py:35-150 set_use_lora / set_lora_scale) changes what model.decoder computes; a
+# backend that owns PACKED weights must repack or it silently keeps generating with the old ones.
+_LORA_MUTATORS = ("add_lora", "load_lora", "add_voice_lora", "remove_lora", "unload_lora", "set_use_lora",
+                  "set_lora_scale")
+
+
+def _make_repacking(name):
+    def wrapper(self, *args, **kwargs):
+        status = getattr(self, "_ref_" + name)(*args, **kwargs)
+        if getattr(self, "use_b200_dit", False) and getattr(self, "model", None) is not None:
+            try:
+                self._init_b200_backends(dit=True, vae=False, cond=False)
+            except UnsupportedAdapterError as exc:
+                # not silent: the B200 DiT is switched off, the stock path takes over, and the status
+                # string the UI shows says so
+                self.use_b200_dit = False
+                note = f" | ⚠️ B200 DiT disabled ({exc}); using the PyTorch decoder"
+                status = status + note if isinstance(status, str) else status
+        return status
+
+    wrapper.__name__ = name
+    wrapper.__doc__ = f"{name} of the reference handler, followed by a repack of the B200 DiT weights."
+    return wrapper
+
+
 _WRAPPED = {
     "_execute_service_generate_diffusion": _execute_service_generate_diffusion,
     "tiled_decode": tiled_decode,
@@ -264,6 +293,12 @@ def install(target):
             raise AttributeError(f"{cls.__name__} has no method '{name}' to wrap")
         setattr(target, "_ref_" + name.lstrip("_"), bind(original))
         setattr(target, name, bind(fn))
+    for name in _LORA_MUTATORS:  # present on the real handler; optional on minimal hosts
+        original = getattr(cls, name, None)
+        if original is None:
+            continue
+        setattr(target, "_ref_" + name, bind(original))
+        setattr(target, name, bind(_make_repacking(name)))
     for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("use_b200_cond", False), ("b200_dit", None),
                       ("b200_sampler", None), ("b200_vae", None), ("b200_cond", None)):
         if not hasattr(target, flag):

@@ -19,6 +19,68 @@ def _get(sd: Dict[str, torch.Tensor], key: str) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
+# Adapter-aware weight source (LoRA load / unload / scale mutates model.decoder)
+# --------------------------------------------------------------------------------------------
+class UnsupportedAdapterError(RuntimeError):
+    """model.decoder carries a parametrisation this packer cannot fold into plain Linear weights."""
+
+
+def effective_decoder_state(decoder) -> Dict[str, torch.Tensor]:
+    """`state_dict()` of the PLAIN decoder that computes what `decoder` computes right now.
+
+    The reference wraps `model.decoder` in a PEFT `PeftModel` when a LoRA is loaded
+    (handler/lora/lifecycle.py:164-287): Linear layers become LoRA layers with `base_layer`,
+    `lora_A[name]`, `lora_B[name]`, `scaling[name]`, `active_adapters`, `disable_adapters`, and the state
+    dict keys gain a `base_model.model.` prefix and `.base_layer` infixes.  This folds every ACTIVE
+    adapter into its base weight, W + sum_a scaling[a] * B_a @ A_a (what PEFT's `get_delta_weight` adds
+    on merge), and restores the reference key names so pack_dit can walk it.  A decoder without
+    adapters is returned as its own state dict.  LoKr / LyCORIS nets (`_lycoris_net`,
+    lifecycle.py:101-156) are not Linear-foldable here: UnsupportedAdapterError."""
+    if getattr(decoder, "_lycoris_net", None) is not None:
+        raise UnsupportedAdapterError("decoder carries a LyCORIS (LoKr) net; the B200 packer folds PEFT LoRA only")
+    deltas: Dict[str, torch.Tensor] = {}
+    for name, mod in decoder.named_modules():
+        if not (hasattr(mod, "base_layer") and hasattr(mod, "lora_A") and hasattr(mod, "lora_B")):
+            continue
+        if getattr(mod, "merged", False):
+            continue  # already folded into base_layer.weight by PEFT
+        if getattr(mod, "disable_adapters", False):
+            continue
+        active = getattr(mod, "active_adapters", None)
+        if active is None:
+            active = list(mod.lora_A.keys())
+        if isinstance(active, str):
+            active = [active]
+        delta = None
+        for a in active:
+            if a not in mod.lora_A or a not in mod.lora_B:
+                continue
+            wa, wb = mod.lora_A[a].weight.detach().float(), mod.lora_B[a].weight.detach().float()
+            d = float(mod.scaling[a]) * (wb @ wa)
+            delta = d if delta is None else delta + d
+        if delta is not None:
+            deltas[name] = delta
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in decoder.state_dict().items():
+        if ".lora_A." in k or ".lora_B." in k or ".lora_embedding_" in k or ".lora_magnitude_vector" in k:
+            continue
+        key = k
+        owner = None
+        if ".base_layer." in key:
+            owner = key.split(".base_layer.")[0]
+            key = key.replace(".base_layer.", ".")
+        t = v.detach()
+        if owner is not None and key.endswith(".weight") and owner in deltas:
+            t = (t.float() + deltas[owner].to(t.device)).to(t.dtype)
+        for pre in ("base_model.model.", "base_model."):
+            if key.startswith(pre):
+                key = key[len(pre):]
+                break
+        out[key] = t
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # DiT
 # --------------------------------------------------------------------------------------------
 def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> torch.Tensor:

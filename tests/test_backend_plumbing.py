@@ -161,6 +161,80 @@ def test_condition_seam_replaces_model_encoder_only():
     assert float(ctx[0, 0, 64]) == 1.0
 
 
+def test_effective_decoder_state_folds_active_lora():
+    """PEFT-shaped LoRA layers (duck-typed: base_layer / lora_A / lora_B / scaling / active_adapters) are
+    folded into plain Linear weights under the reference's key names; disabled adapters are ignored."""
+    from acestep_b200.pack import UnsupportedAdapterError, effective_decoder_state
+
+    class LoraLinear(torch.nn.Module):
+        def __init__(self, i, o, r=2):
+            super().__init__()
+            self.base_layer = torch.nn.Linear(i, o, bias=False)
+            self.lora_A = torch.nn.ModuleDict({"a": torch.nn.Linear(i, r, bias=False), "b": torch.nn.Linear(i, r, bias=False)})
+            self.lora_B = torch.nn.ModuleDict({"a": torch.nn.Linear(r, o, bias=False), "b": torch.nn.Linear(r, o, bias=False)})
+            self.scaling = {"a": 0.5, "b": 2.0}
+            self.active_adapters = ["a"]
+            self.disable_adapters = False
+
+    class Inner(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = LoraLinear(4, 3)
+            self.norm = torch.nn.LayerNorm(3)
+
+    class Peft(torch.nn.Module):  # PeftModel.base_model.model.<decoder>
+        def __init__(self):
+            super().__init__()
+            self.base_model = torch.nn.Module()
+            self.base_model.model = Inner()
+
+    torch.manual_seed(0)
+    m = Peft()
+    lin = m.base_model.model.q_proj
+    sd = effective_decoder_state(m)
+    assert set(sd) == {"q_proj.weight", "norm.weight", "norm.bias"}
+    want = lin.base_layer.weight + 0.5 * lin.lora_B["a"].weight @ lin.lora_A["a"].weight
+    assert torch.allclose(sd["q_proj.weight"], want.detach())
+    lin.active_adapters = ["a", "b"]
+    want2 = want + 2.0 * lin.lora_B["b"].weight @ lin.lora_A["b"].weight
+    assert torch.allclose(effective_decoder_state(m)["q_proj.weight"], want2.detach())
+    lin.disable_adapters = True
+    assert torch.equal(effective_decoder_state(m)["q_proj.weight"], lin.base_layer.weight.detach())
+    plain = torch.nn.Linear(4, 3)
+    assert set(effective_decoder_state(plain)) == {"weight", "bias"}
+    plain._lycoris_net = object()
+    with pytest.raises(UnsupportedAdapterError):
+        effective_decoder_state(plain)
+
+
+def test_lora_mutators_trigger_a_repack():
+    class LoraHost(FakeHandler):
+        def load_lora(self, path):
+            self.ref_calls.append(("load_lora", path))
+            return "✅ loaded"
+
+        def set_lora_scale(self, a, b=None):
+            self.ref_calls.append(("scale", a, b))
+            return "✅ scale"
+
+    h = install(LoraHost())
+    repacks = []
+    h._init_b200_backends = lambda dit=True, vae=True, cond=True: repacks.append((dit, vae, cond))
+    assert h.load_lora("x") == "✅ loaded" and repacks == []  # inactive backend: nothing to repack
+    h.use_b200_dit = True
+    assert h.load_lora("y") == "✅ loaded" and h.set_lora_scale("a", 0.5) == "✅ scale"
+    assert repacks == [(True, False, False)] * 2
+    assert h.ref_calls == [("load_lora", "x"), ("load_lora", "y"), ("scale", "a", 0.5)]
+
+    def boom(dit=True, vae=True, cond=True):
+        from acestep_b200.pack import UnsupportedAdapterError
+        raise UnsupportedAdapterError("LoKr")
+
+    h._init_b200_backends = boom
+    msg = h.load_lora("z")
+    assert "B200 DiT disabled" in msg and h.use_b200_dit is False  # loud, not silent
+
+
 def test_turbo_models_use_the_turbo_sampler():
     h = install(FakeHandler())
     h.config.is_turbo = True
