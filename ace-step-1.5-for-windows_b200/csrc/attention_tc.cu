@@ -259,9 +259,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tcgen05_fence_after();
       __syncwarp();
       float v[HPT][32];
+      {  // both 32-column loads in flight, one wait
+        uint32_t raw[HPT][32];
 #pragma unroll
-      for (int c = 0; c < HPT; ++c)
-        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)(s * BKV + (hsel * HPT + c) * 32), v[c]);
+        for (int c = 0; c < HPT; ++c)
+          tmem_ld_32x32_nowait(tmem_base + lane_base + (uint32_t)(s * BKV + (hsel * HPT + c) * 32), raw[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < HPT; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c][i] = __uint_as_float(raw[c][i]);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // this warp's slice of S_j is in registers
@@ -318,8 +326,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int c = 0; c < HPT; ++c) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(fmaf(v[c][i], p.scale_log2, neg_ref));
-          const float p1 = exp2f(fmaf(v[c][i + 1], p.scale_log2, neg_ref));
+          const float p0 = ex2_approx(fmaf(v[c][i], p.scale_log2, neg_ref));
+          const float p1 = ex2_approx(fmaf(v[c][i + 1], p.scale_log2, neg_ref));
           rs[i & 2] += p0;
           rs[(i & 2) + 1] += p1;
           w[c][i >> 1] = pack_bf16x2(p0, p1);
