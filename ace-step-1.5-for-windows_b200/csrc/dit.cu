@@ -529,6 +529,9 @@ int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const f
 int ace_euler_step(uint16_t* xt, const uint16_t* vt, float dt, size_t n, void* stream) {
   return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream);
 }
+int ace_euler_step_dup(uint16_t* xt, const uint16_t* vt, float dt, size_t n, uint16_t* dup, void* stream) {
+  return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream, (bf16*)dup);
+}
 int ace_sde_step(uint16_t* xt, const uint16_t* vt, const uint16_t* eps, float t_cur, float t_next, size_t n,
                  void* stream) {
   return launch_sde((bf16*)xt, (const bf16*)vt, (const bf16*)eps, t_cur, t_next, (long)n, (cudaStream_t)stream);

@@ -269,7 +269,9 @@ __global__ void rope_tables_kernel(bf16* __restrict__ cos_tab, bf16* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void euler_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt, float dt, long n8) {
+// `dup` (optional): second copy of the updated state — the unconditional half of the next step's CFG batch
+__global__ void euler_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt, float dt, long n8,
+                             bf16* __restrict__ dup) {
   pdl_trigger();
   pdl_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +282,7 @@ __global__ void euler_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt,
 #pragma unroll
   for (int k = 0; k < 8; ++k) x[k] = x[k] - bf16_round(v[k] * dt);
   st8(xt + i * 8, x);
+  if (dup != nullptr) st8(dup + i * 8, x);
 }
 
 __global__ void sde_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt,
@@ -300,74 +303,87 @@ __global__ void sde_kernel(bf16* __restrict__ xt, const bf16* __restrict__ vt,
   st8(xt + i * 8, x);
 }
 
-// APG: one 1024-thread block per batch item; thread (c = tid % 64, lane-in-time = tid / 64).
-__global__ void __launch_bounds__(1024)
+// APG: the reductions run along TIME per (batch item, channel), so channels are independent: one block per
+// (8-channel group, batch item), thread = (channel c = tid % 8 of the group, time lane tid / 8).  A warp reads
+// 4 time rows x 16 contiguous bytes.  (The first version used one block per batch item: a single SM looping
+// over T x 64 elements in fp64, 50-100 us per step at T = 1500.)
+constexpr int APG_CG = 8;     // channels per block
+constexpr int APG_TL = 128;   // time lanes per block
+__global__ void __launch_bounds__(APG_CG * APG_TL)
 apg_kernel(const bf16* __restrict__ cond, const bf16* __restrict__ uncond, bf16* __restrict__ mom,
            int first_update, float momentum_coef, float norm_threshold, float guidance_scale,
            bf16* __restrict__ vt_out, int T) {
   pdl_trigger();
   pdl_wait();
-  __shared__ double red[16][64][2];
-  __shared__ float sf_s[64];
-  __shared__ double dot_s[64], cn_s[64];
-  const int c = threadIdx.x & 63, tl = threadIdx.x >> 6;
-  const long base = (long)blockIdx.x * T * 64;
+  __shared__ double red[APG_TL][APG_CG][2];
+  __shared__ float sf_s[APG_CG];
+  __shared__ double coef_s[APG_CG], rn_s[APG_CG];
+  const int cl = threadIdx.x % APG_CG, tl = threadIdx.x / APG_CG;
+  const int c = blockIdx.x * APG_CG + cl;
+  const long base = (long)blockIdx.y * T * 64;
+  auto reduce2 = [&](double a, double b, double& ra, double& rb) {  // sum over the time lanes of channel cl
+    red[tl][cl][0] = a;
+    red[tl][cl][1] = b;
+    __syncthreads();
+    for (int s = APG_TL / 2; s > 0; s >>= 1) {
+      if (tl < s) {
+        red[tl][cl][0] += red[tl + s][cl][0];
+        red[tl][cl][1] += red[tl + s][cl][1];
+      }
+      __syncthreads();
+    }
+    ra = red[0][cl][0];
+    rb = red[0][cl][1];
+    __syncthreads();
+  };
 
   // phase A: momentum update, sum of squares of the running average along time
   double ss = 0.0;
-  for (int t = tl; t < T; t += 16) {
+  for (int t = tl; t < T; t += APG_TL) {
     const long i = base + (long)t * 64 + c;
     float d = bf16_round(__bfloat162float(cond[i]) - __bfloat162float(uncond[i]));
     if (!first_update) d = bf16_round(d + bf16_round(momentum_coef * __bfloat162float(mom[i])));
     mom[i] = __float2bfloat16_rn(d);
     ss += (double)d * d;
   }
-  red[tl][c][0] = ss;
-  __syncthreads();
+  double s_tot, unused;
+  reduce2(ss, 0.0, s_tot, unused);
   if (tl == 0) {
-    double s = 0.0;
-    for (int k = 0; k < 16; ++k) s += red[k][c][0];
     float sf = 1.0f;
     if (norm_threshold > 0.f) {
-      const float nrm = bf16_round((float)sqrt(s));
+      const float nrm = bf16_round((float)sqrt(s_tot));
       sf = fminf(1.0f, bf16_round(norm_threshold / nrm));
     }
-    sf_s[c] = sf;
+    sf_s[cl] = sf;
   }
   __syncthreads();
-  const float sf = sf_s[c];
+  const float sf = sf_s[cl];
 
   // phase B: <diff, cond> and <cond, cond> along time (fp64 like project())
   double dot = 0.0, cn = 0.0;
-  for (int t = tl; t < T; t += 16) {
+  for (int t = tl; t < T; t += APG_TL) {
     const long i = base + (long)t * 64 + c;
     const double d = (double)bf16_round(__bfloat162float(mom[i]) * sf);
     const double pc = (double)__bfloat162float(cond[i]);
     dot += d * pc;
     cn += pc * pc;
   }
-  red[tl][c][0] = dot;
-  red[tl][c][1] = cn;
-  __syncthreads();
+  double dot_t, cn_t;
+  reduce2(dot, cn, dot_t, cn_t);
   if (tl == 0) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < 16; ++k) {
-      s0 += red[k][c][0];
-      s1 += red[k][c][1];
-    }
-    dot_s[c] = s0;
-    cn_s[c] = s1;
-  }
+    const double nrm = fmax(sqrt(cn_t), 1e-12);  // F.normalize eps
+    coef_s[cl] = dot_t / nrm;                     // <v0, v1/|v1|>
+    rn_s[cl] = 1.0 / nrm;                         // v1/|v1| = v1 * (1/|v1|): one fp64 ulp from the division,
+  }                                               // far below the bf16 rounding of the result
   __syncthreads();
-  const double nrm = fmax(sqrt(cn_s[c]), 1e-12);  // F.normalize eps
-  const double coef = dot_s[c] / nrm;             // <v0, v1/|v1|>
+  const double coef = coef_s[cl], rn = rn_s[cl];
 
   // phase C: orthogonal component, guided prediction
-  for (int t = tl; t < T; t += 16) {
+  for (int t = tl; t < T; t += APG_TL) {
     const long i = base + (long)t * 64 + c;
     const double d = (double)bf16_round(__bfloat162float(mom[i]) * sf);
     const float pc = __bfloat162float(cond[i]);
-    const double par = coef * ((double)pc / nrm);
+    const double par = coef * ((double)pc * rn);
     const float orth = bf16_round((float)(d - par));
     vt_out[i] = __float2bfloat16_rn(pc + bf16_round((guidance_scale - 1.0f) * orth));
   }
@@ -508,10 +524,10 @@ int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStr
   return ACE_OK;
 }
 
-int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream) {
+int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream, bf16* dup) {
   ACE_REQUIRE(n % 8 == 0, "euler: n must be a multiple of 8");
   if (n == 0) return ACE_OK;
-  ELEM(n * 6, euler_kernel, (unsigned)((n / 8 + 255) / 256), 256, xt, vt, dt, n / 8);
+  ELEM(n * (dup ? 8 : 6), euler_kernel, (unsigned)((n / 8 + 255) / 256), 256, xt, vt, dt, n / 8, dup);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }
@@ -529,9 +545,8 @@ int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum, int first_u
                float momentum_coef, float norm_threshold, float guidance_scale, bf16* vt_out, int B,
                int T, cudaStream_t stream) {
   if (B == 0 || T == 0) return ACE_OK;
-  ELEM((double)B * T * 64 * 10, apg_kernel, B, 1024, cond, uncond, momentum, first_update,
-                                                               momentum_coef, norm_threshold, guidance_scale,
-                                                               vt_out, T);
+  ELEM((double)B * T * 64 * 10, apg_kernel, dim3(64 / APG_CG, B), APG_CG * APG_TL, cond, uncond, momentum,
+       first_update, momentum_coef, norm_threshold, guidance_scale, vt_out, T);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

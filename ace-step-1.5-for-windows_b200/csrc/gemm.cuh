@@ -330,8 +330,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         __threadfence();
         atomicAdd(arrive, 1u);
         unsigned seen;
+#if ACE_HANG_GUARD
+        const long long t0 = clock64();
+#endif
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+#if ACE_HANG_GUARD
+          if (seen < (unsigned)S && clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug must not wedge the GPU
+            printf("ace: split-K wait timeout (block %d tile %d: %u of %d arrived)\n", blockIdx.x, tile, seen, S);
+            __trap();
+          }
+#endif
         } while (seen < (unsigned)S);
       }
       asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");

@@ -59,7 +59,7 @@ int launch_rope_tables(bf16* cos_tab, bf16* sin_tab, int S, float theta, cudaStr
 
 // ---- sampler-side elementwise ------------------------------------------------------------------
 // xt <- bf16(xt - bf16(vt * dt))       (Euler, base :1977-1979 / turbo :1985-1991, :1975-1977)
-int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream);
+int launch_euler(bf16* xt, const bf16* vt, float dt, long n, cudaStream_t stream, bf16* dup = nullptr);
 // xt <- bf16(t_next * eps + (1 - t_next) * bf16(xt - bf16(vt * t_cur)))   (SDE re-noise)
 int launch_sde(bf16* xt, const bf16* vt, const bf16* eps, float t_cur, float t_next, long n,
                cudaStream_t stream);

@@ -101,6 +101,26 @@ class B200DiT:
             _lib.check(self.lib.ace_dit_bind(self.handle, bc, T, E, self._ws.data_ptr(), need), "ace_dit_bind")
         self.bound = (bc, T, E)
 
+    def io_views(self):
+        """(xt [bc,T,64], ctx [bc,T,128], vt [bc,T,64]) bf16 views of the handle's static I/O slots inside the
+        bound workspace (ace_dit_io_slots).  A sampler that keeps its state in them passes exactly these to
+        step(), which then skips the three device-to-device copies per step."""
+        if self.bound is None:
+            raise _lib.B200Error("io_views: handle not bound")
+        bc, T, _ = self.bound
+        px, pc, pv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self.lib.ace_dit_io_slots(self.handle, C.byref(px), C.byref(pc), C.byref(pv)), "ace_dit_io_slots")
+        base = self._ws.data_ptr()
+
+        def view(ptr, ch):
+            off = ptr.value - base
+            n = bc * T * ch * 2
+            if off < 0 or off + n > self._ws.numel():
+                raise _lib.B200Error("io slot outside the bound workspace")
+            return self._ws[off: off + n].view(torch.bfloat16).view(bc, T, ch)
+
+        return view(px, 64), view(pc, 128), view(pv, 64)
+
     def set_condition(self, enc: torch.Tensor) -> None:
         """enc [bc, E, hidden]: condition_embedder + all layers' cross K/V (cached until next call)."""
         bc, E, D = enc.shape

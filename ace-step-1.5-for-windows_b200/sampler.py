@@ -85,8 +85,13 @@ class B200Sampler:
     def _stream(self):
         return _lib.stream_handle(self.device)
 
-    def _euler(self, xt, vt, dt: float):
-        _lib.check(self.lib.ace_euler_step(xt.data_ptr(), vt.data_ptr(), dt, xt.numel(), self._stream()), "ace_euler_step")
+    def _euler(self, xt, vt, dt: float, dup=None):
+        if dup is None:
+            _lib.check(self.lib.ace_euler_step(xt.data_ptr(), vt.data_ptr(), dt, xt.numel(), self._stream()),
+                       "ace_euler_step")
+        else:  # the new state also lands in `dup` (unconditional half of the next step's CFG batch)
+            _lib.check(self.lib.ace_euler_step_dup(xt.data_ptr(), vt.data_ptr(), dt, xt.numel(), dup.data_ptr(),
+                                                   self._stream()), "ace_euler_step_dup")
 
     def _sde(self, xt, vt, eps, t_cur: float, t_next: float):
         _lib.check(self.lib.ace_sde_step(xt.data_ptr(), vt.data_ptr(), eps.data_ptr(), t_cur, t_next, xt.numel(),
@@ -139,7 +144,11 @@ class B200Sampler:
         cover_steps = int(n * audio_cover_strength)
         self.dit.bind(B, T, enc.shape[1])
         self.dit.set_condition(enc)
-        vt = torch.empty_like(xt)
+        # loop state in the handle's static I/O slots: no per-step copies (see generate_base)
+        xin, ctxin, vt = self.dit.io_views()
+        ctxin.copy_(ctx)
+        xin.copy_(xt)
+        xt = xin
         switched = False
         for i in range(n):
             t_cur = t_sched[i]
@@ -148,9 +157,14 @@ class B200Sampler:
                 if enc_nc is None or ctx_nc is None:
                     raise ValueError("audio_cover_strength < 1 needs non-cover conditioning")
                 enc, ctx = enc_nc, ctx_nc
+                keep = xt.clone()  # a different condition length re-carves the workspace
                 self.dit.bind(B, T, enc.shape[1])
                 self.dit.set_condition(enc)  # re-creates the cross-KV cache (turbo :1956)
-            self.dit.step(xt, ctx, [t_cur] * B, out=vt)
+                xin, ctxin, vt = self.dit.io_views()
+                ctxin.copy_(ctx)
+                xin.copy_(keep)
+                xt = xin
+            self.dit.step(xt, ctxin, [t_cur] * B, out=vt)
             if i == n - 1:
                 self._euler(xt, vt, t_cur)  # x0 = xt - vt * t (:1975-1977)
                 break
@@ -160,6 +174,7 @@ class B200Sampler:
                 self._sde(xt, vt, eps, t_cur, t_next)
             else:
                 self._euler(xt, vt, _bf16(t_cur - t_next))
+        xt = xt.clone()  # the slots are reused by the next request
         torch.cuda.synchronize(self.device)
         t1 = time.time()
         return {"target_latents": xt,
@@ -216,8 +231,15 @@ class B200Sampler:
         Bc = enc.shape[0]
         self.dit.bind(Bc, T, enc.shape[1])
         self.dit.set_condition(enc)
-        x2 = torch.empty(Bc, T, 64, device=dev, dtype=bf)
-        vt = torch.empty_like(x2)
+        # The loop state lives in the DiT handle's static I/O slots (xin = [xt | xt copy for the unconditional
+        # half], ctx, vt), so a step is: set t -> CUDA graph -> guidance -> Euler, with no copies in between.
+        xin, ctxin, vt = self.dit.io_views()
+        ctxin.copy_(ctx)
+        xin[:B].copy_(xt)
+        if do_cfg:
+            xin[B:].copy_(xt)
+        xt = xin[:B]
+        dup = xin[B:] if do_cfg else None
         vg = torch.empty_like(xt)
         momentum = torch.zeros_like(xt)
         first_apg = True
@@ -232,12 +254,17 @@ class B200Sampler:
                 if do_cfg:
                     enc = torch.cat([enc, null.expand_as(enc)], dim=0)
                     ctx = torch.cat([ctx, ctx], dim=0)
+                keep = xt.clone()  # a different condition length re-carves the workspace
                 self.dit.bind(Bc, T, enc.shape[1])
                 self.dit.set_condition(enc)  # new cross-KV cache (base :1927)
-            x2[:B].copy_(xt)
-            if do_cfg:
-                x2[B:].copy_(xt)
-            self.dit.step(x2, ctx, [t_cur] * Bc, out=vt)
+                xin, ctxin, vt = self.dit.io_views()
+                ctxin.copy_(ctx)
+                xin[:B].copy_(keep)
+                if do_cfg:
+                    xin[B:].copy_(keep)
+                xt = xin[:B]
+                dup = xin[B:] if do_cfg else None
+            self.dit.step(xin, ctxin, [t_cur] * Bc, out=vt)
             v = vt[:B]
             if do_cfg and in_interval[i]:
                 if use_adg:
@@ -254,8 +281,11 @@ class B200Sampler:
                 nxt = 1.0 - float(i + 1) / n  # ignores `shift`, like the reference (:1972)
                 eps = self._to(sde_noise[i]) if sde_noise is not None else torch.randn_like(xt)
                 self._sde(xt, v, eps, t_cur, nxt)
+                if do_cfg:
+                    dup.copy_(xt)
             else:
-                self._euler(xt, v, dts[i])
+                self._euler(xt, v, dts[i], dup)
+        xt = xt.clone()  # the slots are reused by the next request
         torch.cuda.synchronize(dev)
         t1 = time.time()
         return {"target_latents": xt,

@@ -92,6 +92,9 @@ int ace_dit_step(AceDit* dit, const uint16_t* d_xt, const uint16_t* d_ctx, const
 /* ------------------------------------------------------------------------------------------ */
 /* xt <- xt - vt * dt over n bf16 elements (n % 8 == 0) */
 int ace_euler_step(uint16_t* d_xt, const uint16_t* d_vt, float dt, size_t n, void* stream);
+/* Same update, and the new state is also written to `d_dup` (n elements): the unconditional half of the
+ * next step's CFG batch, so the sampler needs no separate copy kernel between steps. */
+int ace_euler_step_dup(uint16_t* d_xt, const uint16_t* d_vt, float dt, size_t n, uint16_t* d_dup, void* stream);
 /* xt <- t_next * eps + (1 - t_next) * (xt - vt * t_cur) */
 int ace_sde_step(uint16_t* d_xt, const uint16_t* d_vt, const uint16_t* d_eps, float t_cur,
                  float t_next, size_t n, void* stream);
