@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200.so")
+# ACE_B200_LIB: alternative build of the same ABI (A/B timing of two kernel versions on one box)
+LIB_PATH = os.environ.get("ACE_B200_LIB") or os.path.join(PKG_DIR, "libacestep_b200.so")
 
 
 class B200Error(RuntimeError):

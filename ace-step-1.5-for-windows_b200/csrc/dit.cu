@@ -429,8 +429,12 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
       for (GemmPlan* g : {&p.qkv, &p.self_o, &p.cross_q, &p.cross_o, &p.gate_up, &p.down, &p.cross_kv})
         ACE_PROPAGATE(gemm_plan_enable_splitk(g, d->splitk, sk));
   }
-  // chain the weight prefetches: every GEMM pulls the next GEMM's weights into L2
-  if (!(getenv("ACE_NO_PREFETCH") && getenv("ACE_NO_PREFETCH")[0] == '1')) {
+  // Optional chain of weight prefetches (every GEMM pulls the next GEMM's weights into L2 with
+  // cp.async.bulk.prefetch.L2).  OFF by default: it paid off with the first, issue-bound main loops, but
+  // A/B runs of the current kernels on one B200 have the step FASTER without it at every shape
+  // (T=1500: 5.19 -> 4.98 ms, T=6000: 18.5 -> 18.2, T=250: 3.34 -> 3.27) — the prefetch traffic competes
+  // with the running GEMM's own operand stream.  ACE_PREFETCH=1 re-enables it for experiments.
+  if (getenv("ACE_PREFETCH") && getenv("ACE_PREFETCH")[0] == '1') {
     auto chain = [](GemmPlan& cur, const GemmPlan& next) {
       cur.shp.pf_ptr = reinterpret_cast<const uint8_t*>(next.b_ptr);
       cur.shp.pf_bytes = (unsigned long long)next.shp.N * next.b_ld * sizeof(bf16);

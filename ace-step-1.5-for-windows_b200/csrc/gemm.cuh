@@ -42,8 +42,7 @@ struct GemmShape {
   int shift[GEMM_MAX_TAPS];
   // Optional L2 prefetch of the NEXT kernel's weights (read-only, so it may start before the
   // programmatic-dependency wait): each CTA's idle warp 3 issues cp.async.bulk.prefetch.L2 for its
-  // slice.  The DiT streams 3.2 GB of weights per step through a 126 MB L2, so without this every
-  // B-operand TMA load pays DRAM latency and the 6-stage ring cannot cover it (profiles/r1_notes.md).
+  // slice.  Null unless the owner chains plans (dit.cu: off by default, see the A/B note there).
   const uint8_t* pf_ptr;
   unsigned long long pf_bytes;
   // Split-K (single-CTA kernel, BLOCK_N 128 only; see gemm_tc_kernel): `splits` CTAs share one output
