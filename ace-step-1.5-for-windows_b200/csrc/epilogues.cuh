@@ -468,19 +468,23 @@ struct EpiConv {
             v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
+        // every rounding two elements at a time (F2FP.PACK_AB): the bf16 conversions share the XU pipe
+        // with the Snake cosine and paced the memory-bound codec stages; badd2 is an exactly rounded bf16 add
+        uint32_t xp[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+        for (int i = 0; i < 16; ++i) xp[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         if (resid) {
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rq);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float r[8];
-            unpack_bf16x2(rq[i].x, r[0], r[1]); unpack_bf16x2(rq[i].y, r[2], r[3]);
-            unpack_bf16x2(rq[i].z, r[4], r[5]); unpack_bf16x2(rq[i].w, r[6], r[7]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[8 * i + k] = bf16_round(v[8 * i + k] + r[k]);
-          }
+          for (int i = 0; i < 16; ++i) xp[i] = badd2(xp[i], rw[i]);
         }
-        if (out_main) store_bf16x32(out_main + idx, v);
+        if (out_main) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(out_main + idx)[i] = make_uint4(xp[4 * i], xp[4 * i + 1], xp[4 * i + 2], xp[4 * i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) unpack_bf16x2(xp[i], v[2 * i], v[2 * i + 1]);
         if (out_snake) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {

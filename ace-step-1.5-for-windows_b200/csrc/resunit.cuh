@@ -250,15 +250,20 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
       for (int c = c_lo; c < c_lo + 64; c += 32) {
         float v[32];
         tmem_ld_32x32(taddr + (uint32_t)c, v);
+        // bf16 conversions run on the XU pipe (16 per clock per SM, shared with the Snake cosine) and were
+        // what paced this kernel: every rounding is therefore done two elements at a time (F2FP.PACK_AB)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias1 + c) + i);
           const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.a2 + c) + i);
           const float4 i4 = __ldg(reinterpret_cast<const float4*>(p.ib2 + c) + i);
-          v[4 * i + 0] = snake_f(bf16_round(v[4 * i + 0] + b4.x), a4.x, i4.x);
-          v[4 * i + 1] = snake_f(bf16_round(v[4 * i + 1] + b4.y), a4.y, i4.y);
-          v[4 * i + 2] = snake_f(bf16_round(v[4 * i + 2] + b4.z), a4.z, i4.z);
-          v[4 * i + 3] = snake_f(bf16_round(v[4 * i + 3] + b4.w), a4.w, i4.w);
+          float h0, h1, h2, h3;
+          unpack_bf16x2(pack_bf16x2(v[4 * i + 0] + b4.x, v[4 * i + 1] + b4.y), h0, h1);
+          unpack_bf16x2(pack_bf16x2(v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w), h2, h3);
+          v[4 * i + 0] = snake_f(h0, a4.x, i4.x);
+          v[4 * i + 1] = snake_f(h1, a4.y, i4.y);
+          v[4 * i + 2] = snake_f(h2, a4.z, i4.z);
+          v[4 * i + 3] = snake_f(h3, a4.w, i4.w);
         }
         uint8_t* half = rowp + (c >> 6) * S::A_BYTES;
 #pragma unroll
@@ -302,14 +307,16 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
           const uint4 xq = *reinterpret_cast<const uint4*>(half + chunk * 16);
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c) + 2 * q);
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c) + 2 * q + 1);
-          float xr[8];
-          unpack_bf16x2(xq.x, xr[0], xr[1]); unpack_bf16x2(xq.y, xr[2], xr[3]);
-          unpack_bf16x2(xq.z, xr[4], xr[5]); unpack_bf16x2(xq.w, xr[6], xr[7]);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[8 * q + k] = bf16_round(bf16_round(v[8 * q + k] + bb[k]) + xr[k]);
+          // x' = bf16(bf16(acc + b2) + x): one pair-wise rounding, then a packed bf16 add (exactly rounded)
+          uint4 xn;
+          xn.x = badd2(pack_bf16x2(v[8 * q + 0] + b0.x, v[8 * q + 1] + b0.y), xq.x);
+          xn.y = badd2(pack_bf16x2(v[8 * q + 2] + b0.z, v[8 * q + 3] + b0.w), xq.y);
+          xn.z = badd2(pack_bf16x2(v[8 * q + 4] + b1.x, v[8 * q + 5] + b1.y), xq.z);
+          xn.w = badd2(pack_bf16x2(v[8 * q + 6] + b1.z, v[8 * q + 7] + b1.w), xq.w);
+          if (ok) reinterpret_cast<uint4*>(p.ox + row * RU_C + c)[q] = xn;
+          unpack_bf16x2(xn.x, v[8 * q + 0], v[8 * q + 1]); unpack_bf16x2(xn.y, v[8 * q + 2], v[8 * q + 3]);
+          unpack_bf16x2(xn.z, v[8 * q + 4], v[8 * q + 5]); unpack_bf16x2(xn.w, v[8 * q + 6], v[8 * q + 7]);
         }
-        if (ok) store_bf16x32(p.ox + row * RU_C + c, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.an + c) + i);
