@@ -416,7 +416,12 @@ struct EpiProjOut {
 // before the MUFU cosine.  (acestep/models/mlx/vae_model.py:24-56)
 __device__ __forceinline__ float snake_f(float x, float a, float ib) {
   float y = 2.0f * a * x;
-  y = fmaf(-6.283185307179586f, rintf(y * 0.15915494309189535f), y);
+  // round(y / 2pi) by the add-and-subtract-1.5*2^23 trick (exact round-to-nearest-even for |y / 2pi| < 2^22;
+  // larger arguments lose all phase information in fp32 anyway): FRND would be a second XU-pipe
+  // instruction per element next to the cosine, and the XU pipe is what paces the codec epilogues
+  float k = y * 0.15915494309189535f;
+  k = (k + 12582912.0f) - 12582912.0f;
+  y = fmaf(-6.283185307179586f, k, y);
   return fmaf(ib, 0.5f - 0.5f * __cosf(y), x);
 }
 
