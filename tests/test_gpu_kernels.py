@@ -291,3 +291,74 @@ def test_condition_encoder_rejects_unrepresentable_mask(lib):
         enc(text_hidden_states=text, text_attention_mask=tm, lyric_hidden_states=lyric, lyric_attention_mask=lm,
             refer_audio_acoustic_hidden_states_packed=refer, refer_audio_order_mask=order)
     enc.close()
+
+
+@pytest.mark.parametrize("B,T,E", [(1, 1, 1), (3, 7, 2), (16, 5, 3)])
+def test_dit_forward_edge_shapes(lib, B, T, E):
+    """Smallest and most ragged shapes: one latent frame (one half-empty patch), one condition token, the
+    maximum effective batch the handle accepts; every GEMM is a single partial tile (split-K path)."""
+    cfg, w = _tiny_dit()
+    g = torch.Generator().manual_seed(100 + B + T + E)
+    xt = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    ctx = torch.randn(B, T, 128, generator=g).to(torch.bfloat16)
+    enc = torch.randn(B, E, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    t = torch.rand(B, generator=g).to(torch.bfloat16)
+    want = dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True)
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    dit.bind(B, T, E)
+    dit.set_condition(enc.to(DEV))
+    vt = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())
+    torch.cuda.synchronize()
+    assert vt.shape == (B, T, 64) and torch.isfinite(vt.float()).all()
+    assert rel_l2(vt.cpu().float(), want) <= 2e-2
+
+
+def test_dit_forward_full_size_short_clip(lib):
+    """The shipped architecture (2048 wide, 24 layers, 16/8 heads) at the 10 s shape of BASELINE config 0
+    (T = 250 -> 125 tokens, no CFG): every GEMM runs its production tile / split-K plan.  Tolerance: the
+    reference's own bf16-vs-fp32 spread at this size is 1.67e-2, bound 2e-2."""
+    cfg = DiTConfig()
+    w = bf16_round_(make_dit_weights(cfg, seed=0))
+    g = torch.Generator().manual_seed(9)
+    B, T, E = 1, 250, 64
+    xt = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    ctx = torch.cat([torch.randn(B, T, 64, generator=g), torch.ones(B, T, 64)], -1).to(torch.bfloat16)
+    enc = torch.randn(B, E, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    t = torch.tensor([0.625]).to(torch.bfloat16)
+    with torch.no_grad():
+        want = dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True)
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    dit.bind(B, T, E)
+    dit.set_condition(enc.to(DEV))
+    vt = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())
+    vt2 = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())
+    torch.cuda.synchronize()
+    assert torch.isfinite(vt.float()).all()
+    assert max_abs(vt2, vt) == 0.0  # split-K reduces in a fixed order: replays are bit-identical
+    assert rel_l2(vt.cpu().float(), want) <= 2e-2
+    dit.close()
+
+
+def test_c_abi_rejects_bad_arguments(lib):
+    """Errors are int status codes + ace_last_error(), never exceptions or aborts (include/acestep_b200.h)."""
+    cfg, w = _tiny_dit()
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    for bc, t, e in ((0, 8, 4), (17, 8, 4), (1, 0, 4), (1, 8, 0)):
+        assert lib.ace_dit_bind(dit.handle, bc, t, e, ws.data_ptr(), ws.numel()) != 0
+        assert lib.ace_last_error()
+    assert lib.ace_dit_bind(dit.handle, 1, 64, 16, ws.data_ptr(), 1024) != 0  # workspace too small
+    assert b"workspace" in lib.ace_last_error()
+    with pytest.raises(_lib.B200Error):
+        dit.step(torch.zeros(1, 8, 64, device=DEV, dtype=torch.bfloat16),
+                 torch.zeros(1, 8, 128, device=DEV, dtype=torch.bfloat16), [0.5])  # not bound
+    cfgv, sd, shape = _tiny_vae()
+    vae = B200Vae(sd, shape, DEV)
+    with pytest.raises(_lib.B200Error):
+        vae.encode_samples(torch.zeros(2, cfgv.hop * 3 + 1, device=DEV), None)  # not a multiple of the hop
+    with pytest.raises(ValueError):
+        vae.encode(torch.zeros(1, 2, cfgv.hop - 1, device=DEV))  # shorter than one hop
+    with pytest.raises(ValueError):
+        vae.decode(torch.zeros(64, 4, device=DEV))  # wrong rank
+    with pytest.raises(_lib.B200Error):
+        B200DiT(w, DiTShape.from_config(cfg), "cpu")  # no CPU path
