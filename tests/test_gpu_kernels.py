@@ -362,3 +362,32 @@ def test_c_abi_rejects_bad_arguments(lib):
         vae.decode(torch.zeros(64, 4, device=DEV))  # wrong rank
     with pytest.raises(_lib.B200Error):
         B200DiT(w, DiTShape.from_config(cfg), "cpu")  # no CPU path
+
+
+def test_vae_full_size_short_clip(lib):
+    """The shipped Oobleck config (strides 2,4,4,6,10, channels 128..2048) on a 1 s clip: every stage's
+    kernel variant runs (pair-tile convs, transposed / strided convs, fused residual units at 128 channels,
+    SIMT end convs).  Bound like the tiny test: the spread of an all-bf16 torch run of the oracle."""
+    cfg = ovae.VaeConfig()
+    sd = make_vae_weights(cfg, seed=4)
+    wf = folded_vae_state(sd)
+    shape = VaeShape()
+    g = torch.Generator().manual_seed(60)
+    frames = 25
+    z = torch.randn(1, 64, frames, generator=g).to(torch.bfloat16)
+    audio = torch.rand(1, 2, frames * cfg.hop, generator=g) - 0.5
+    vae = B200Vae(sd, shape, DEV)
+    wb = {k: v.to(torch.bfloat16) for k, v in wf.items()}
+    with torch.no_grad():
+        want = ovae.decode(wf, cfg, z.float())
+        floor = _bf16_floor(lambda: want, lambda: ovae.decode(wb, cfg, z))
+        mean, _ = ovae.encode_moments(wf, cfg, audio.to(torch.bfloat16).float())
+        efloor = _bf16_floor(lambda: mean, lambda: ovae.encode_moments(wb, cfg, audio.to(torch.bfloat16))[0])
+    got = vae.decode(z.to(DEV))
+    got_mean = vae.encode_samples(audio[0].to(DEV), None)
+    torch.cuda.synchronize()
+    assert got.shape == (1, 2, frames * 1920) and torch.isfinite(got).all()
+    assert rel_l2(got.cpu(), want) <= max(1.1 * floor, 2e-2), floor
+    assert got_mean.shape == (frames, 64)
+    assert rel_l2(got_mean.cpu().float(), mean[0].T) <= max(1.1 * efloor, 2e-2), efloor
+    vae.close()
