@@ -158,6 +158,18 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// L2 promotion of the tensor maps (experiments: ACE_TMAP_L2=0|64|128|256, default 256)
+static CUtensorMapL2promotion tmap_l2_promotion() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ACE_TMAP_L2");
+    v = e ? atoi(e) : 256;
+  }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                          : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows,
                    uint64_t row_pitch_bytes, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -175,7 +187,7 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  tmap_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p cols=%llu rows=%llu pitch=%llu box=%u",
               (int)r, base, (unsigned long long)cols, (unsigned long long)rows,
