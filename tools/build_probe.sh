@@ -8,3 +8,4 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-r
 nvcc $FLAGS -o tools/_bin/gemm_probe tools/gemm_probe.cu $CS/runtime.cu
 nvcc $FLAGS -DACE_GEMM_TIMING -o tools/_bin/gemm_timing tools/gemm_timing.cu $CS/runtime.cu
 nvcc $FLAGS -DACE_GEMM_TIMING -o tools/_bin/gemm_l2_probe tools/gemm_l2_probe.cu $CS/runtime.cu
+nvcc $FLAGS -o tools/_bin/mufu_probe tools/mufu_probe.cu
