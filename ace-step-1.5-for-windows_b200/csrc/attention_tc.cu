@@ -84,6 +84,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[3
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+#ifdef ACE_ATTN_TIMING
+// probe builds only (tools/attn_timing.cu): cycles CTA 0 / warp 4 / lane 0 spends per phase of the KV loop
+__device__ long long g_attn_cycles[8];
+#define ATT_T(i) do { if (stamp) { const long long now_ = clock64(); g_attn_cycles[i] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define ATT_T(i) do { } while (0)
+#endif
+
 template <int NSW>
 __global__ void __launch_bounds__(128 + 32 * NSW, NSW == 4 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -250,12 +258,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     const unsigned span = k_hi > k_lo ? (unsigned)(k_hi - k_lo) : 0u;
     float m_used = -INFINITY, l_run = 0.f;
+#ifdef ACE_ATTN_TIMING
+    const bool stamp = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    long long tprev = clock64();
+#endif
 
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const int jb0 = j_lo + j * BKV;
       mbar_wait(&bar[S_FULL + s], ph);
+      ATT_T(0);  // wait for S_j
       tcgen05_fence_after();
       __syncwarp();
       float v[HPT][32];
@@ -273,6 +286,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[S_EMPTY + s]);  // this warp's slice of S_j is in registers
+      ATT_T(1);  // TMEM load
 
       // boundary blocks only: tail of the key range and the +-window band (tile-uniform test)
       const bool interior = (jb0 + BKV <= skv) &&
@@ -317,6 +331,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         l_run *= factor;
       }
       const float neg_ref = (m_used == -INFINITY) ? 0.f : -m_used;
+      ATT_T(2);  // mask + max + rescale decision
 
       // P_j is computed into registers BEFORE waiting for the P buffer, so the exponentials of this
       // block overlap the PV MMA of the previous one (which still reads the buffer)
@@ -335,8 +350,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       l_run += (rs[0] + rs[1]) + (rs[2] + rs[3]);
 
+      ATT_T(3);  // exponentials
       // P buffer (and O) are free once PV_{j-1} has retired
       mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
+      ATT_T(4);  // wait for PV_{j-1}
       if (warp_grow && j > 0) {
         tcgen05_fence_after();
 #pragma unroll 1
@@ -362,6 +379,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[P_FULL]);
+      ATT_T(5);  // (rescale,) P store, fence, arrive
     }
 
     if (NSW == 8) {  // row sums: add the partner's partial (both are relative to the same m_used)
