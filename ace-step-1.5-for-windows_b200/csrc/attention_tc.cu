@@ -12,7 +12,10 @@
 //               maximum is combined through smem + a 64-thread named barrier — the single-warp-
 //               per-scheduler version was ALU-latency bound, profiles/r1_notes.md):
 //               tcgen05.ld S -> scale (+ band / tail mask only on boundary blocks) -> exp2 ->
-//               bf16 P into swizzled smem (A operand of the PV MMA).  O stays in TMEM across the
+//               bf16 P written back to TENSOR MEMORY over the S columns it came from (tcgen05.st) and read
+//               by the PV MMA as its A operand (tcgen05.mma with A in TMEM): no shared-memory store, no
+//               proxy fence; in-situ A/B on B200: DiT step -3 % at 60 s, -6 % at 240 s.  (The NSW = 8
+//               variant and ACE_ATTN_PTMEM=0 keep the swizzled-smem P buffer.)  O stays in TMEM across the
 //               whole KV loop; it is rescaled (tcgen05.ld/st) only when a row maximum grows by more
 //               than 2^8 (lazy rescale: P and the row sum keep using the stale maximum, which is
 //               exact because the final 1/l normalisation uses the same reference).
@@ -92,7 +95,25 @@ __device__ long long g_attn_cycles[8];
 #define ATT_T(i) do { } while (0)
 #endif
 
-template <int NSW>
+__device__ __forceinline__ void tmem_st_32x32_u32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// PT = true (NSW == 4 only): P_j is written back into tensor memory over the first 32 columns of the S buffer
+// it was computed from (64 bf16 keys = 32 packed words per row) and P.V reads its A operand from there: no
+// shared-memory store, no generic->async proxy fence, and the P.V MMAs read half as much shared memory.
+// The tensor pipe runs MMAs in issue order, so S_{j+2} (same buffer) cannot overtake PV_j.
+template <int NSW, bool PT>
 __global__ void __launch_bounds__(128 + 32 * NSW, NSW == 4 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
@@ -227,9 +248,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (elected) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          // 16 keys per MMA: P advances 32 B inside its swizzled row, V advances 16 rows (2048 B)
-          umma_bf16_ss_lo(tmem_o, p_lo + (uint32_t)(2 * k),
-                          v_lo + (uint32_t)(s * (KV_TILE >> 4) + k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          // 16 keys per MMA: P advances 32 B inside its swizzled row (8 TMEM columns), V advances 16 rows (2048 B)
+          if (PT) {
+            umma_bf16_ts_lo(tmem_o, tmem_base + (uint32_t)(s * BKV + 8 * k),
+                            v_lo + (uint32_t)(s * (KV_TILE >> 4) + k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          } else {
+            umma_bf16_ss_lo(tmem_o, p_lo + (uint32_t)(2 * k),
+                            v_lo + (uint32_t)(s * (KV_TILE >> 4) + k * (2048 >> 4)), idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&bar[V_EMPTY + s]);
         umma_commit(&bar[P_EMPTY]);
@@ -351,6 +377,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       l_run += (rs[0] + rs[1]) + (rs[2] + rs[3]);
 
       ATT_T(3);  // exponentials
+      if (PT) {
+        // O may only be touched once PV_{j-1} has retired; P_j itself goes into the S buffer just read, which
+        // nothing else uses until S_{j+2} (queued behind PV_j on the tensor pipe)
+        if (warp_grow && j > 0) {
+          mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
+          tcgen05_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < OCH; ++c) {
+            float o[32];
+            tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= factor;
+            tmem_st_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
+          }
+        }
+        ATT_T(4);
+        uint32_t pw[32];
+#pragma unroll
+        for (int c = 0; c < HPT; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pw[(c * 16 + i) & 31] = w[c][i];
+        tmem_st_32x32_u32(tmem_base + lane_base + (uint32_t)(s * BKV), pw);
+      } else {
       // P buffer (and O) are free once PV_{j-1} has retired
       mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
       ATT_T(4);  // wait for PV_{j-1}
@@ -376,6 +425,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[P_FULL]);
@@ -434,15 +484,15 @@ int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
   return ACE_OK;
 }
 
-template <int NSW>
+template <int NSW, bool PT>
 static int launch_attention_tc_n(const AttnPlan& plan, dim3 grid, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    ACE_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<NSW, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem_bytes<NSW>()));
     attr = true;
   }
-  ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel<NSW>, grid, dim3(128 + 32 * NSW), (size_t)smem_bytes<NSW>(),
+  ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel<NSW, PT>, grid, dim3(128 + 32 * NSW), (size_t)smem_bytes<NSW>(),
                                stream, plan.tm_q, plan.tm_k, plan.tm_v, plan.p));
   return ACE_OK;
 }
@@ -466,7 +516,14 @@ int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
     forced = e ? atoi(e) : 0;
   }
   const int nsw = forced == 8 ? 8 : 4;
-  const int st = nsw == 8 ? launch_attention_tc_n<8>(plan, grid, stream) : launch_attention_tc_n<4>(plan, grid, stream);
+  static int ptmem = -1;
+  if (ptmem < 0) {
+    const char* e = getenv("ACE_ATTN_PTMEM");  // default on; ACE_ATTN_PTMEM=0 keeps P in shared memory (A/B)
+    ptmem = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int st = nsw == 8 ? launch_attention_tc_n<8, false>(plan, grid, stream)
+                          : (ptmem ? launch_attention_tc_n<4, true>(plan, grid, stream)
+                                   : launch_attention_tc_n<4, false>(plan, grid, stream));
   prof_end(stream);
   return st;
 }

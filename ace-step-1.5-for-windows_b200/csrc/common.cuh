@@ -420,6 +420,20 @@ __device__ __forceinline__ void umma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, 
       : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_K128_HI)
       : "memory");
 }
+// A operand from TENSOR MEMORY (128 lanes = rows, 8 consecutive 32-bit columns = 16 bf16 along K per MMA),
+// B from shared memory: used for P.V in attention, where P is written by tcgen05.st over the S columns it
+// was computed from and never touches shared memory.
+__device__ __forceinline__ void umma_bf16_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_K128_HI)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16_ss_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
                                                      uint32_t idesc, uint32_t accumulate) {
   asm volatile(
