@@ -84,6 +84,7 @@ SIGNATURES = {
                                           C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "ace_debug_set_gemm_reference": (None, [C.c_int]),
     "ace_debug_set_vae_fused": (None, [C.c_int]),
+    "ace_debug_set_attention_p_in_tmem": (None, [C.c_int]),
     "ace_debug_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "ace_debug_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }

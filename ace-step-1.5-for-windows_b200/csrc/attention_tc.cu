@@ -51,7 +51,7 @@ constexpr float RESCALE_TAU = 8.0f;  // log2 domain
 
 enum Bar {
   Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11,
-  P_FULL = 13, P_EMPTY = 14, NBAR = 15
+  P_FULL = 13, P_EMPTY = 15, NBAR = 16  // P_FULL: one barrier (P in smem) or one per S buffer (P in TMEM)
 };
 
 // MN-major SWIZZLE_128B operand: atoms of 64 (MN) x 8 (K); SBO = 1024 B between 8-row K groups,
@@ -150,6 +150,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&bar[S_EMPTY + i], NSW);
     }
     mbar_init(&bar[P_FULL], NSW);
+    mbar_init(&bar[P_FULL + 1], NSW);
     mbar_init(&bar[P_EMPTY], 1);
     fence_barrier_init();
   }
@@ -222,6 +223,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&bar[K_FULL + s], ph);
       mbar_wait(&bar[S_EMPTY + s], ph ^ 1);
+      // P_{j-2} lives in this S buffer (PT): S_j overwrites it, so wait until PV_{j-2} has retired rather than
+      // rely on issue order alone (PV_{j-2} was issued a whole softmax earlier: the wait is almost always free).
+      if (PT && j >= 2) mbar_wait(&bar[P_EMPTY], (uint32_t)(j & 1));
       tcgen05_fence_after();
       if (elected) {
         const uint32_t d = tmem_base + (uint32_t)(s * BKV);
@@ -243,7 +247,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int s = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&bar[V_FULL + s], ph);
-      mbar_wait(&bar[P_FULL], (uint32_t)(j & 1));
+      // PT: P_j has its own barrier per S buffer.  With a single barrier a softmax warp that runs one block ahead
+      // (S_{j+1} is ready before PV_j, and nothing makes it wait for P_EMPTY unless it rescales) would put its
+      // P_{j+1} arrival into phase j, completing it while a slower warp's P_j is still unwritten.
+      if (PT) mbar_wait(&bar[P_FULL + s], ph);
+      else mbar_wait(&bar[P_FULL], (uint32_t)(j & 1));
       tcgen05_fence_after();
       if (elected) {
 #pragma unroll
@@ -378,10 +386,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
       ATT_T(3);  // exponentials
       if (PT) {
-        // O may only be touched once PV_{j-1} has retired; P_j itself goes into the S buffer just read, which
-        // nothing else uses until S_{j+2} (queued behind PV_j on the tensor pipe)
+        // P_j goes into the S buffer just read, which nothing else uses until S_{j+2}.  Every warp still waits
+        // for PV_{j-1} in every block, not only when it rescales O: the parity waits on P_EMPTY are only
+        // unambiguous while no waiter is more than one phase behind.  A warp that skipped this wait could finish
+        // its last block while PV_{nblk-2} was still pending, see the (nblk-1) parity of the final wait as
+        // already complete, and read O two P.V products short (12 % of launches in tools/attn_stress.py).
+        // PV_{j-1} was issued a whole softmax block earlier, so the wait is almost always free.
+        if (j > 0) mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
         if (warp_grow && j > 0) {
-          mbar_wait(&bar[P_EMPTY], (uint32_t)((j & 1) ^ 1));
           tcgen05_fence_after();
 #pragma unroll 1
           for (int c = 0; c < OCH; ++c) {
@@ -428,7 +440,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[P_FULL]);
+      if (lane == 0) mbar_arrive(&bar[P_FULL + (PT ? s : 0)]);
       ATT_T(5);  // (rescale,) P store, fence, arrive
     }
 
@@ -469,6 +481,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 }
 
 }  // namespace
+
+static int g_attn_ptmem_override = -1;
+void set_attention_p_in_tmem(int mode) { g_attn_ptmem_override = mode < 0 ? -1 : (mode != 0); }
 
 int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
   plan->p = p;
@@ -516,11 +531,12 @@ int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
     forced = e ? atoi(e) : 0;
   }
   const int nsw = forced == 8 ? 8 : 4;
-  static int ptmem = -1;
-  if (ptmem < 0) {
+  static int ptmem_env = -1;
+  if (ptmem_env < 0) {
     const char* e = getenv("ACE_ATTN_PTMEM");  // default on; ACE_ATTN_PTMEM=0 keeps P in shared memory (A/B)
-    ptmem = (e && e[0] == '0') ? 0 : 1;
+    ptmem_env = (e && e[0] == '0') ? 0 : 1;
   }
+  const int ptmem = g_attn_ptmem_override >= 0 ? g_attn_ptmem_override : ptmem_env;
   const int st = nsw == 8 ? launch_attention_tc_n<8, false>(plan, grid, stream)
                           : (ptmem ? launch_attention_tc_n<4, true>(plan, grid, stream)
                                    : launch_attention_tc_n<4, false>(plan, grid, stream));

@@ -212,6 +212,7 @@ int ace_init(int device) {
 }
 
 void ace_debug_set_gemm_reference(int on) { set_gemm_debug_reference(on != 0); }
+void ace_debug_set_attention_p_in_tmem(int mode) { set_attention_p_in_tmem(mode); }
 
 uint64_t ace_launch_count(void) { return launch_count(); }
 void ace_profile_start(void) { prof_start(); }

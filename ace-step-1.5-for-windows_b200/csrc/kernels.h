@@ -30,6 +30,8 @@ struct AttnPlan {
 int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch);
 int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream);
 bool attention_use_legacy();
+// tests: 1 = P through tensor memory (default), 0 = P through shared memory, -1 = environment default
+void set_attention_p_in_tmem(int mode);
 
 // x[b, t, :] = [ctx[b, t, 0:128] | xt[b, t, 0:64]] for t < T, zeros for T <= t < Tpad
 int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,

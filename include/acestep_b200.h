@@ -204,6 +204,9 @@ void ace_debug_set_gemm_reference(int on);
  * 0 = two launches of the tap-shifted GEMM, -1 = default (fused unless ACE_VAE_FUSED=0).  Both paths
  * round at the same points, so their outputs are bit-identical (the test that uses this hook). */
 void ace_debug_set_vae_fused(int on);
+/* Attention: 1 = P goes back to tensor memory and P.V reads its A operand from there (default), 0 = P through
+ * shared memory, -1 = default.  The stress test compares the two on long KV loops. */
+void ace_debug_set_attention_p_in_tmem(int mode);
 /* D = A[m,k] * B[n,k]^T + bias, bf16 in/out, through the tcgen05 path (tests/bench). */
 int ace_debug_linear(const uint16_t* d_a, const uint16_t* d_b, const uint16_t* d_bias, uint16_t* d_out,
                      int m, int n, int k, void* stream);

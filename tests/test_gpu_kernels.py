@@ -391,3 +391,36 @@ def test_vae_full_size_short_clip(lib):
     assert got_mean.shape == (frames, 64)
     assert rel_l2(got_mean.cpu().float(), mean[0].T) <= max(1.1 * efloor, 2e-2), efloor
     vae.close()
+
+
+def test_attention_p_in_tmem_stress(lib):
+    """P through tensor memory (default) against P through shared memory on long KV loops, many launches, both
+    co-resident CTAs busy: the two paths round identically, so outputs must be bit-identical and finite.  (A
+    missing PV_{j-2} -> S_j ordering passed every small test and produced NaNs only after ~10^3 launches.)"""
+    g = torch.Generator().manual_seed(123)
+    B, H, HK, S = 2, 16, 8, 1500
+    q = (torch.randn(B, S, H * 128, generator=g) * 2).to(torch.bfloat16).to(DEV)
+    k = (torch.randn(B, S, HK * 128, generator=g) * 2).to(torch.bfloat16).to(DEV)
+    v = torch.randn(B, S, HK * 128, generator=g).to(torch.bfloat16).to(DEV)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.ace_debug_set_attention_p_in_tmem(mode)
+            o = torch.empty(B, S, H * 128, dtype=torch.bfloat16, device=DEV)
+            ref = None
+            for it in range(150 if mode == 1 else 2):
+                for win in (-1, 128):
+                    _lib.check(lib.ace_debug_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK,
+                                                       S, S, win, _stream()))
+                    if win == -1:
+                        cur = o.clone()
+                        if ref is None:
+                            ref = cur
+                        else:
+                            assert torch.equal(cur, ref), f"launch {it}: result changed between launches"
+            torch.cuda.synchronize()
+            outs[mode] = ref
+    finally:
+        lib.ace_debug_set_attention_p_in_tmem(-1)
+    assert torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[0], outs[1]), max_abs(outs[0].float(), outs[1].float())

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Attention stress probe: launch-to-launch determinism of both P paths (tensor memory / shared memory), their
+difference, and each against an fp32 torch reference, on long KV loops with both co-resident CTAs busy."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from acestep_b200 import _lib
+
+lib = _lib.load()
+dev = torch.device("cuda:0")
+_lib.check(lib.ace_init(0))
+st = torch.cuda.current_stream().cuda_stream
+g = torch.Generator().manual_seed(123)
+B, H, HK, S = 2, 16, 8, 1500
+q = (torch.randn(B, S, H * 128, generator=g) * 2).to(torch.bfloat16).to(dev)
+k = (torch.randn(B, S, HK * 128, generator=g) * 2).to(torch.bfloat16).to(dev)
+v = torch.randn(B, S, HK * 128, generator=g).to(torch.bfloat16).to(dev)
+qf = q.float().view(B, S, H, 128).transpose(1, 2)
+kf = k.float().view(B, S, HK, 128).transpose(1, 2).repeat_interleave(H // HK, 1)
+vf = v.float().view(B, S, HK, 128).transpose(1, 2).repeat_interleave(H // HK, 1)
+want = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, S, H * 128)
+outs = {}
+for mode in (0, 1):
+    lib.ace_debug_set_attention_p_in_tmem(mode)
+    o = torch.empty(B, S, H * 128, dtype=torch.bfloat16, device=dev)
+    ref, changed = None, 0
+    for it in range(300):
+        for win in (-1, 128):
+            _lib.check(lib.ace_debug_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK, S, S, win, st))
+            if win == -1:
+                cur = o.clone()
+                if ref is None:
+                    ref = cur
+                elif not torch.equal(cur, ref):
+                    changed += 1
+                    if changed <= 3:
+                        d = (cur.float() - ref.float()).abs()
+                        print(f"mode {mode} launch {it}: {int((d > 0).sum())} elements differ, max {float(d.max()):.3e}, "
+                              f"finite {bool(torch.isfinite(cur.float()).all())}")
+    torch.cuda.synchronize()
+    outs[mode] = ref
+    err = (ref.float() - want).abs().max()
+    print(f"mode {mode}: {changed} of 299 launches differ from the first; max abs err vs fp32 sdpa {float(err):.3e}, "
+          f"finite {bool(torch.isfinite(ref.float()).all())}")
+d = (outs[0].float() - outs[1].float()).abs()
+print(f"mode 0 vs mode 1: {int((d > 0).sum())} of {d.numel()} elements differ, max abs {float(d.max()):.3e}")
