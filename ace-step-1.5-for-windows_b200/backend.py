@@ -165,7 +165,10 @@ class B200BackendMixin:
         (handler/mlx_vae_decode_native.py:31-76).  One pass per sample, no overlap-discard waste."""
         if self.b200_vae is None:
             raise RuntimeError("B200 VAE decode requested but b200_vae is not initialized.")
-        return self.b200_vae.decode(latents_torch)
+        # tiled_decode's only caller peak-normalises next (generate_music_decode.py:191-195: |x| temporary,
+        # amax, host sync on `any`, divide).  Doing it here in one read pass makes that step an identity —
+        # every peak it then sees is <= 1 — without touching the caller.
+        return self.b200_vae.decode_normalized(latents_torch)
 
     def _b200_vae_encode_sample(self, audio_torch: torch.Tensor) -> torch.Tensor:
         """audio [B, 2, N] -> sampled latents [B, 64, N // 1920]; cf. _mlx_vae_encode_sample."""

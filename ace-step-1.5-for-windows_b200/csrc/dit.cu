@@ -537,6 +537,12 @@ int ace_euler_step(uint16_t* xt, const uint16_t* vt, float dt, size_t n, void* s
 int ace_euler_step_dup(uint16_t* xt, const uint16_t* vt, float dt, size_t n, uint16_t* dup, void* stream) {
   return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream, (bf16*)dup);
 }
+int ace_peak_normalize(float* wav, int batch, size_t n, float* peak, void* stream) {
+  return launch_peak_normalize(wav, batch, n, peak, (cudaStream_t)stream);
+}
+int ace_latent_guard(const uint16_t* lat, size_t n, int* flags, void* stream) {
+  return launch_latent_guard(lat, n, flags, (cudaStream_t)stream);
+}
 int ace_sde_step(uint16_t* xt, const uint16_t* vt, const uint16_t* eps, float t_cur, float t_next, size_t n,
                  void* stream) {
   return launch_sde((bf16*)xt, (const bf16*)vt, (const bf16*)eps, t_cur, t_next, (long)n, (cudaStream_t)stream);

@@ -437,6 +437,66 @@ __global__ void adg_kernel(const bf16* __restrict__ xt, const bf16* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Output path: per-sample peak normalisation of the decoded waveform,
+//   peak = wav.abs().amax(dim=[1,2]); wav = wav / peak.clamp(min=1)   (handler/generate_music_decode.py:191-195)
+// and the latent sanity guard (NaN / Inf / all-zero, generate_music_decode.py:66-77), each as ONE pass
+// over HBM with no host decision in between.  |x| is reduced on its IEEE bit pattern: for non-negative
+// floats unsigned order == numeric order, and a NaN (0x7fc00000) sorts above +Inf, so it propagates like amax.
+__global__ void __launch_bounds__(256)
+abs_peak_kernel(const float* __restrict__ wav, size_t n, unsigned* __restrict__ peak_bits) {
+  const float* x = wav + (size_t)blockIdx.y * n;
+  unsigned m = 0u;
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    m = max(max(m, q.x & 0x7fffffffu), max(q.y & 0x7fffffffu, max(q.z & 0x7fffffffu, q.w & 0x7fffffffu)));
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
+  m = __reduce_max_sync(0xffffffffu, m);
+  __shared__ unsigned sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = __reduce_max_sync(0xffu, sm[threadIdx.x]);
+    if (threadIdx.x == 0 && m != 0u) atomicMax(peak_bits + blockIdx.y, m);
+  }
+}
+
+// The whole grid leaves after one 4-byte read when the sample's peak is <= 1 (or NaN), the common case.
+__global__ void __launch_bounds__(256)
+peak_scale_kernel(float* __restrict__ wav, size_t n, const float* __restrict__ peak) {
+  const float pk = peak[blockIdx.y];
+  if (!(pk > 1.0f)) return;
+  float* x = wav + (size_t)blockIdx.y * n;
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 q = reinterpret_cast<float4*>(x)[i];
+    q.x = __fdiv_rn(q.x, pk); q.y = __fdiv_rn(q.y, pk); q.z = __fdiv_rn(q.z, pk); q.w = __fdiv_rn(q.w, pk);
+    reinterpret_cast<float4*>(x)[i] = q;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    x[i] = __fdiv_rn(x[i], pk);
+}
+
+// flags[0] |= 1 if any element is NaN or Inf; flags[1] |= 1 if any element is non-zero
+__global__ void __launch_bounds__(256)
+latent_guard_kernel(const uint16_t* __restrict__ lat, size_t n, int* __restrict__ flags) {
+  bool bad = false, nonzero = false;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const unsigned v = lat[i] & 0x7fffu;
+    bad |= v >= 0x7f80u;  // exponent all ones: Inf or NaN
+    nonzero |= v != 0u;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  nonzero = __any_sync(0xffffffffu, nonzero);
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicOr(flags, 1);
+    if (nonzero) atomicOr(flags + 1, 1);
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -558,6 +618,33 @@ int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma
   ELEM(frames * 64 * 8, adg_kernel, (unsigned)((frames + 7) / 8), 256, xt, cond, uncond, sigma,
                                                                                  guidance_scale, angle_clip,
                                                                                  vt_out, frames);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, cudaStream_t stream) {
+  ACE_REQUIRE(batch >= 0 && (batch == 0 || peak) && (batch == 0 || n == 0 || wav), "peak_normalize: null argument");
+  if (batch == 0) return ACE_OK;
+  ACE_CUDA_CHECK(cudaMemsetAsync(peak, 0, (size_t)batch * sizeof(float), stream));
+  if (n == 0) return ACE_OK;
+  // enough CTAs to keep every SM streaming (4 per SM across the batch), at least 16 KB of waveform each
+  size_t per = (n + 4095) / 4096;
+  const size_t want = (size_t)(4 * num_sms() + batch - 1) / batch;
+  const unsigned gx = (unsigned)(per < want ? per : want);
+  ELEM((double)batch * n * 4, abs_peak_kernel, dim3(gx, batch), 256, (const float*)wav, n,
+       reinterpret_cast<unsigned*>(peak));
+  ELEM((double)batch * 4, peak_scale_kernel, dim3(gx, batch), 256, wav, n, (const float*)peak);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_latent_guard(const uint16_t* lat, size_t n, int* flags, cudaStream_t stream) {
+  ACE_REQUIRE(flags && (n == 0 || lat), "latent_guard: null argument");
+  ACE_CUDA_CHECK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), stream));
+  if (n == 0) return ACE_OK;
+  const size_t blocks = (n + 2047) / 2048;
+  const unsigned gx = (unsigned)(blocks < (size_t)(2 * num_sms()) ? blocks : (size_t)(2 * num_sms()));
+  ELEM((double)n * 2, latent_guard_kernel, gx, 256, lat, n, flags);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -73,5 +73,10 @@ int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum /*[B,T,64] r
 int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma,
                float guidance_scale, float angle_clip, bf16* vt_out, int B, int T,
                cudaStream_t stream);
+// Output path: per-sample |x| peak into peak[batch] (fp32) and in-place x / max(peak, 1); latent sanity flags
+// {any NaN/Inf, any non-zero} into flags[2].
+int num_sms();  // runtime.cu
+int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, cudaStream_t stream);
+int launch_latent_guard(const uint16_t* lat, size_t n, int* flags, cudaStream_t stream);
 
 }  // namespace ace

@@ -1,0 +1,65 @@
+"""Output path of the hot path: the latent sanity guard and the per-sample
+peak normalisation the reference runs either side of the VAE decode, on the C ABI.
+
+Reference: handler/generate_music_decode.py:66-77 (NaN / Inf / all-zero guard, three torch reductions and
+three host syncs) and :191-195 (`peak = wav.abs().amax(dim=[1, 2]); if any(peak > 1): wav / peak.clamp(min=1)`,
+an |x| temporary as large as the waveform plus a host sync for the `any`).  Here: one pass over the latents
+with one 8-byte read-back, and one read pass over the waveform + a scale pass that leaves after 4 bytes when
+the peak is <= 1; no host decision in between, so the waveform's D2H copy can be queued right behind it."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+NAN_MESSAGE = "Generation produced NaN or Inf latents."
+ZERO_MESSAGE = "Generation produced zero latents."
+
+
+def peak_normalize_(wav: torch.Tensor, peak: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place on a CUDA fp32 tensor [B, C, N] (or [C, N] = one sample): every sample whose max|x| exceeds 1
+    is divided by it.  Returns the per-sample peaks [B] (fp32, on the device, measured BEFORE scaling)."""
+    if not wav.is_cuda:
+        raise _lib.B200Error("peak_normalize_: the B200 output path needs a CUDA tensor (no CPU fallback)")
+    if wav.dtype != torch.float32 or not wav.is_contiguous():
+        raise ValueError(f"peak_normalize_ expects a contiguous fp32 tensor, got {wav.dtype}, "
+                         f"contiguous={wav.is_contiguous()}")
+    if wav.dim() not in (2, 3):
+        raise ValueError(f"peak_normalize_ expects [B, C, N] or [C, N], got {tuple(wav.shape)}")
+    batch = wav.shape[0] if wav.dim() == 3 else 1
+    n = wav.numel() // batch if batch else 0
+    if peak is None:
+        peak = torch.empty(batch, dtype=torch.float32, device=wav.device)
+    elif peak.numel() != batch or peak.dtype != torch.float32 or peak.device != wav.device:
+        raise ValueError("peak buffer must be fp32 [B] on the waveform's device")
+    with torch.cuda.device(wav.device):
+        _lib.check(_lib.load().ace_peak_normalize(wav.data_ptr(), batch, n, peak.data_ptr(),
+                                                  _lib.stream_handle(wav.device)), "ace_peak_normalize")
+    return peak
+
+
+def latent_flags(lat: torch.Tensor) -> Tuple[bool, bool]:
+    """(any NaN/Inf, any non-zero) of a CUDA bf16 tensor — one kernel, one 8-byte device->host read."""
+    if not lat.is_cuda:
+        raise _lib.B200Error("latent_flags: the B200 output path needs a CUDA tensor (no CPU fallback)")
+    if lat.dtype != torch.bfloat16:
+        raise ValueError(f"latent_flags expects bf16 latents, got {lat.dtype}")
+    lat = lat.contiguous()
+    flags = torch.empty(2, dtype=torch.int32, device=lat.device)
+    with torch.cuda.device(lat.device):
+        _lib.check(_lib.load().ace_latent_guard(lat.data_ptr(), lat.numel(), flags.data_ptr(),
+                                                _lib.stream_handle(lat.device)), "ace_latent_guard")
+    bad, nonzero = flags.tolist()
+    return bool(bad), bool(nonzero)
+
+
+def check_latents(lat: torch.Tensor) -> None:
+    """The reference's guard, same order and same leading sentence of each message: RuntimeError on NaN/Inf,
+    then on all-zero latents (only when there is at least one element)."""
+    bad, nonzero = latent_flags(lat)
+    if bad:
+        raise RuntimeError(NAN_MESSAGE)
+    if lat.numel() > 0 and not nonzero:
+        raise RuntimeError(ZERO_MESSAGE)

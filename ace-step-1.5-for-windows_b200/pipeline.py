@@ -13,6 +13,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from .dit import B200DiT, DiTShape
+from .output import check_latents, peak_normalize_
 from .sampler import B200Sampler
 from .vae import B200Vae, VaeShape
 
@@ -51,20 +52,15 @@ class B200Pipeline:
         out = fn(enc, ctx, src, seed, noise=noise, **sampler_kwargs)
         lat = out["target_latents"]
         # NaN / Inf / all-zero guard of _prepare_generate_music_decode_state (generate_music_decode.py:66-77)
-        if torch.isnan(lat).any() or torch.isinf(lat).any():
-            raise RuntimeError("Generation produced NaN or Inf latents.")
-        if lat.numel() > 0 and lat.abs().sum() == 0:
-            raise RuntimeError("Generation produced zero latents.")
+        check_latents(lat)
         if latent_shift != 0.0 or latent_rescale != 1.0:
             lat = lat * latent_rescale + latent_shift
         res: Dict[str, Any] = {"target_latents": lat, "time_costs": out["time_costs"]}
         if decode:
             t1 = time.time()
             wav = torch.stack([self.vae.decode_frames(lat[b]) for b in range(lat.shape[0])], dim=0)
-            # .float() + per-sample peak normalisation (generate_music_decode.py:191-195)
-            peak = wav.abs().amax(dim=[1, 2], keepdim=True)
-            if torch.any(peak > 1.0):
-                wav = wav / peak.clamp(min=1.0)
+            # per-sample peak normalisation (generate_music_decode.py:191-195), in place, no host decision
+            res["peak"] = peak_normalize_(wav)
             if to_host:
                 if self._pinned_wav is None or self._pinned_wav.shape != wav.shape:
                     self._pinned_wav = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)

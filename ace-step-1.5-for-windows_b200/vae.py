@@ -112,6 +112,15 @@ class B200Vae:
             outs.append(self._decode_long(latents[b].transpose(0, 1)))
         return torch.stack(outs, dim=0)
 
+    def decode_normalized(self, latents: torch.Tensor) -> torch.Tensor:
+        """decode() followed by the caller's per-sample peak normalisation (generate_music_decode.py:191-195),
+        in place on the device: samples whose max|x| exceeds 1 are divided by it."""
+        from .output import peak_normalize_
+
+        wav = self.decode(latents)
+        peak_normalize_(wav)
+        return wav
+
     def _decode_long(self, z_tc: torch.Tensor) -> torch.Tensor:
         T = z_tc.shape[0]
         if T <= self.MAX_FRAMES_PER_PASS:

@@ -108,6 +108,19 @@ int ace_adg(const uint16_t* d_xt, const uint16_t* d_cond, const uint16_t* d_unco
             float guidance_scale, float angle_clip, uint16_t* d_out, int b, int t, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Output path (handler/generate_music_decode.py:66-77 and :191-195)                            */
+/* ------------------------------------------------------------------------------------------ */
+/* Per-sample peak normalisation of decoded waveforms, in place: d_wav is [batch][n] fp32 (n = channels *
+ * samples), d_peak [batch] fp32 receives max|x| of each sample, and a sample whose peak exceeds 1 is divided
+ * by it (IEEE division, identical to `wav / peak.clamp(min=1)`; dividing the other samples by 1 is the
+ * identity, so the reference's batch-wide `if torch.any(peak > 1)` needs no host decision).  A NaN in a
+ * sample makes its peak NaN and leaves the sample untouched. */
+int ace_peak_normalize(float* d_wav, int batch, size_t n, float* d_peak, void* stream);
+/* Latent sanity guard over n bf16 elements: d_flags[0] = 1 if any NaN/Inf, d_flags[1] = 1 if any non-zero
+ * (the reference raises on NaN/Inf and on all-zero latents before decoding). */
+int ace_latent_guard(const uint16_t* d_lat, size_t n, int* d_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Oobleck VAE (diffusers.AutoencoderOobleck; structure acestep/models/mlx/vae_model.py:149-230) */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct AceVaeConfig {

@@ -88,6 +88,8 @@ class StubVae:
     def decode(self, lat):
         return torch.full((lat.shape[0], 2, lat.shape[2] * 1920), 0.5)
 
+    decode_normalized = decode  # the codec seam asks for the peak-normalised waveform
+
     def encode(self, audio, sample=True):
         return torch.full((audio.shape[0], 64, audio.shape[2] // 1920), 0.25)
 
@@ -266,7 +268,7 @@ def test_no_silent_fallback_when_active():
     h = install(FakeHandler())
 
     class Boom:
-        def decode(self, lat):
+        def decode_normalized(self, lat):
             raise RuntimeError("kernel failure")
 
     h.b200_vae, h.use_b200_vae = Boom(), True
