@@ -57,12 +57,14 @@ SIGNATURES = {
     "ace_dit_bind": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     "ace_dit_set_condition": (C.c_int, [_P, _P, _P]),
     "ace_dit_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), _P, _P]),
+    "ace_dit_cross_attentions": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.c_int, _P, _P]),
     "ace_euler_step": (C.c_int, [_P, _P, C.c_float, C.c_size_t, _P]),
     "ace_euler_step_dup": (C.c_int, [_P, _P, C.c_float, C.c_size_t, _P, _P]),
     "ace_sde_step": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_size_t, _P]),
     "ace_apg": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, C.c_int, C.c_int, _P]),
     "ace_adg": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_float, _P, C.c_int, C.c_int, _P]),
     "ace_peak_normalize": (C.c_int, [_P, C.c_int, C.c_size_t, _P, _P]),
+    "ace_peak_normalize_db": (C.c_int, [_P, C.c_int, C.c_size_t, _P, C.c_float, _P]),
     "ace_latent_guard": (C.c_int, [_P, C.c_size_t, _P, _P]),
     "ace_vae_packed_bytes": (C.c_size_t, [C.POINTER(AceVaeConfig)]),
     "ace_vae_create": (C.c_int, [C.POINTER(_P), C.POINTER(AceVaeConfig), _P, C.c_size_t]),

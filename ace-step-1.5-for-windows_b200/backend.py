@@ -241,6 +241,70 @@ def tiled_encode(self, audio, chunk_size=None, overlap=None, offload_latent_to_c
     return self._ref_tiled_encode(audio, chunk_size, overlap, offload_latent_to_cpu)
 
 
+# Lyric alignment: `get_lyric_timestamp` / `get_lyric_score` call `self.model.decoder(...,
+# output_attentions=True, custom_layers_config=cfg, enable_early_exit=True)` directly and read only element [2],
+# the per-layer cross-attention probabilities (handler/lyric_timestamp.py:78-103, lyric_score.py:94-122).  While
+# the B200 DiT is active those two methods run with `model.decoder` swapped for this shim.
+class B200DecoderShim(torch.nn.Module):
+    """Callable with the reference decoder's keywords (turbo :1300-1317).  Attention-extraction calls go to
+    `B200DiT.cross_attentions`; anything else is forwarded to the real decoder."""
+
+    def __init__(self, host, real_decoder):
+        super().__init__()
+        object.__setattr__(self, "_host", host)          # plain references: neither is a child module
+        object.__setattr__(self, "_real", real_decoder)
+
+    def forward(self, hidden_states=None, timestep=None, timestep_r=None, attention_mask=None,
+                encoder_hidden_states=None, encoder_attention_mask=None, context_latents=None,
+                output_attentions=False, custom_layers_config=None, enable_early_exit=False, **kwargs):
+        wants_attn = bool(output_attentions) or (custom_layers_config is not None and enable_early_exit)
+        if not wants_attn:
+            return self._real(hidden_states=hidden_states, timestep=timestep, timestep_r=timestep_r,
+                              attention_mask=attention_mask, encoder_hidden_states=encoder_hidden_states,
+                              encoder_attention_mask=encoder_attention_mask, context_latents=context_latents,
+                              output_attentions=output_attentions, custom_layers_config=custom_layers_config,
+                              enable_early_exit=enable_early_exit, **kwargs)
+        dit = self._host.b200_dit
+        if dit is None:
+            raise RuntimeError("B200 DiT requested for attention extraction but b200_dit is not initialized.")
+        if timestep_r is not None and not torch.equal(timestep_r, timestep):
+            # the engine precomputes time_embed_r(t - r) for t == r (every inference caller); be loud otherwise
+            raise ValueError("B200 decoder shim supports timestep_r == timestep only")
+        n_total = dit.shape.num_hidden_layers
+        n_layers = n_total
+        if custom_layers_config is not None and enable_early_exit:
+            n_layers = min(n_total, max(int(k) for k in custom_layers_config.keys()) + 1)
+        bc, T, _ = hidden_states.shape
+        dit.bind(bc, T, encoder_hidden_states.shape[1])
+        dit.set_condition(encoder_hidden_states)
+        probs = dit.cross_attentions(hidden_states, context_latents, timestep.float().tolist(), n_layers)
+        probs = probs.to(hidden_states.dtype)
+        # (hidden_states, past_key_values, all_cross_attentions): the alignment callers read [2] only, and
+        # index it by absolute layer number, so layers [0, n_layers) are all present
+        return None, None, tuple(probs[i] for i in range(n_layers))
+
+
+def _make_attention_caller(name):
+    def wrapper(self, *args, **kwargs):
+        ref = getattr(self, "_ref_" + name)
+        model = getattr(self, "model", None)
+        if not (getattr(self, "use_b200_dit", False) and self.b200_dit is not None and model is not None):
+            return ref(*args, **kwargs)
+        real = model.decoder
+        model.decoder = B200DecoderShim(self, real)
+        try:
+            return ref(*args, **kwargs)
+        finally:
+            model.decoder = real
+
+    wrapper.__name__ = name
+    wrapper.__doc__ = f"{name} of the reference handler with the decoder's attention extraction on the B200 DiT."
+    return wrapper
+
+
+_ATTENTION_CALLERS = ("get_lyric_timestamp", "get_lyric_score")
+
+
 # Weight-mutation hooks (SURVEY §8f row 3).  Every LoRA lifecycle / control entry point of the handler
 # (handler/lora/lifecycle.py:164-440 add_lora / load_lora / add_voice_lora / remove_lora / unload_lora,
 # handler/lora/controls.py:35-150 set_use_lora / set_lora_scale) changes what model.decoder computes; a
@@ -302,6 +366,12 @@ def install(target):
             continue
         setattr(target, "_ref_" + name, bind(original))
         setattr(target, name, bind(_make_repacking(name)))
+    for name in _ATTENTION_CALLERS:  # present on the real handler; optional on minimal hosts
+        original = getattr(cls, name, None)
+        if original is None:
+            continue
+        setattr(target, "_ref_" + name, bind(original))
+        setattr(target, name, bind(_make_attention_caller(name)))
     for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("use_b200_cond", False), ("b200_dit", None),
                       ("b200_sampler", None), ("b200_vae", None), ("b200_cond", None)):
         if not hasattr(target, flag):

@@ -139,7 +139,9 @@ bool skip_class(const char* what) {
 #define LAUNCH_NORM(...) do { if (!skip_norm) ACE_PROPAGATE(launch_adaln_rmsnorm(__VA_ARGS__)); } while (0)
 
 // Enqueue one full forward (everything after the inputs sit in xin/ctxin/t_dev).
-int enqueue_forward(AceDit* d, cudaStream_t st) {
+// `probs` non-null: also export the cross-attention probabilities of layers [0, probs_layers) into
+// probs[l][Bc][heads][S][E] and stop right after the last of them (the alignment callers use nothing else).
+int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs_layers = 0) {
   const bool skip_gemm = skip_class("gemm"), skip_norm = skip_class("norm"), skip_attn = skip_class("attn");
   const int D = d->D, NQ = d->NQ, NKV = d->NKV, S = d->S, Bc = d->Bc, M = d->M, E = d->E;
   const float eps = d->cfg.rms_eps;
@@ -179,6 +181,12 @@ int enqueue_forward(AceDit* d, cudaStream_t st) {
     LAUNCH_GEMM(p.cross_q, EpiQKV{d->qc, (long)NQ, NQ, 0, w.cross_qn, w.cross_kn, nullptr,
                                                 nullptr, S, eps}, st);
     const bf16* kv = d->ckv + (size_t)l * Bc * E * 2 * NKV;
+    if (probs != nullptr && l < probs_layers) {
+      ACE_PROPAGATE(launch_cross_probs(d->qc, (long)NQ, kv, 2L * NKV,
+                                       probs + (size_t)l * Bc * d->cfg.num_heads * S * E, d->cfg.num_heads, Bc, S, E,
+                                       group, st));
+      if (l == probs_layers - 1) return ACE_OK;
+    }
     AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, E, -1, group,
                   scale_log2};
     if (skip_attn) {
@@ -531,6 +539,29 @@ int ace_dit_step(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const f
   return ACE_OK;
 }
 
+int ace_dit_cross_attentions(AceDit* d, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t, int n_layers,
+                             uint16_t* d_probs, void* stream) {
+  ACE_REQUIRE(d && d->ws, "ace_dit_cross_attentions: handle not bound");
+  ACE_REQUIRE(d_xt && d_ctx && h_t && d_probs, "ace_dit_cross_attentions: null argument");
+  ACE_REQUIRE(n_layers >= 1 && n_layers <= d->L, "n_layers %d out of range [1,%d]", n_layers, d->L);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nx = (size_t)d->Bc * d->T * 64;
+  if (!d->rope_ready) {
+    ACE_PROPAGATE(launch_rope_tables(d->rope_cos, d->rope_sin, d->S, d->cfg.rope_theta, st));
+    d->rope_ready = true;
+  }
+  if ((const bf16*)d_xt != d->xin)
+    ACE_CUDA_CHECK(cudaMemcpyAsync(d->xin, d_xt, nx * 2, cudaMemcpyDeviceToDevice, st));
+  if ((const bf16*)d_ctx != d->ctxin)
+    ACE_CUDA_CHECK(cudaMemcpyAsync(d->ctxin, d_ctx, nx * 4, cudaMemcpyDeviceToDevice, st));
+  TVals tv;
+  for (int i = 0; i < 16; ++i) tv.v[i] = i < d->Bc ? h_t[i] : 0.f;
+  prof_begin(PROF_ELEM, 0.0, 64.0, st);
+  set_t_kernel<<<1, 32, 0, st>>>(d->t_dev, tv, d->Bc);
+  prof_end(st);
+  return enqueue_forward(d, st, (bf16*)d_probs, n_layers);  // eager: a once-per-song call, not worth a graph
+}
+
 int ace_euler_step(uint16_t* xt, const uint16_t* vt, float dt, size_t n, void* stream) {
   return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream);
 }
@@ -538,7 +569,14 @@ int ace_euler_step_dup(uint16_t* xt, const uint16_t* vt, float dt, size_t n, uin
   return launch_euler((bf16*)xt, (const bf16*)vt, dt, (long)n, (cudaStream_t)stream, (bf16*)dup);
 }
 int ace_peak_normalize(float* wav, int batch, size_t n, float* peak, void* stream) {
-  return launch_peak_normalize(wav, batch, n, peak, (cudaStream_t)stream);
+  return launch_peak_normalize(wav, batch, n, peak, 0.0f, (cudaStream_t)stream);
+}
+int ace_peak_normalize_db(float* wav, int batch, size_t n, float* peak, float target_amp, void* stream) {
+  if (!(target_amp > 0.0f)) {
+    set_error("ace_peak_normalize_db: target_amp must be positive, got %g", (double)target_amp);
+    return ACE_ERR_INVALID;
+  }
+  return launch_peak_normalize(wav, batch, n, peak, target_amp, (cudaStream_t)stream);
 }
 int ace_latent_guard(const uint16_t* lat, size_t n, int* flags, void* stream) {
   return launch_latent_guard(lat, n, flags, (cudaStream_t)stream);

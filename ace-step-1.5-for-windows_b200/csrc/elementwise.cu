@@ -445,6 +445,7 @@ __global__ void adg_kernel(const bf16* __restrict__ xt, const bf16* __restrict__
 // floats unsigned order == numeric order, and a NaN (0x7fc00000) sorts above +Inf, so it propagates like amax.
 __global__ void __launch_bounds__(256)
 abs_peak_kernel(const float* __restrict__ wav, size_t n, unsigned* __restrict__ peak_bits) {
+  pdl_wait();  // launched with programmatic serialization: the producer of `wav` must have finished
   const float* x = wav + (size_t)blockIdx.y * n;
   unsigned m = 0u;
   const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
@@ -464,25 +465,47 @@ abs_peak_kernel(const float* __restrict__ wav, size_t n, unsigned* __restrict__ 
   }
 }
 
-// The whole grid leaves after one 4-byte read when the sample's peak is <= 1 (or NaN), the common case.
+// Stage 1 (handler): x / max(peak, 1).  Stage 2 (optional, target_amp > 0): the front-end's normalize_audio
+// (acestep/audio_utils.py:24-62, applied to every song by default at -1 dB: inference.py:674-679) on the result of
+// stage 1: peak2 = max|x1| — which equals fl(peak / d) because rounding is monotone, so no second reduction —
+// unchanged if peak2 < 1e-6, else x1 * gain with gain = fl(fl(1 / peak2) * target_amp) (torch evaluates
+// `float / tensor` as tensor.reciprocal() * float).  Same roundings in the same order as the two torch passes.
+// The whole grid leaves after one 4-byte read when neither stage applies.
 __global__ void __launch_bounds__(256)
-peak_scale_kernel(float* __restrict__ wav, size_t n, const float* __restrict__ peak) {
+peak_scale_kernel(float* __restrict__ wav, size_t n, const float* __restrict__ peak, float target_amp) {
+  pdl_wait();
   const float pk = peak[blockIdx.y];
-  if (!(pk > 1.0f)) return;
+  const bool s1 = pk > 1.0f;
+  const float d = s1 ? pk : 1.0f;
+  bool s2 = false;
+  float gain = 1.0f;
+  if (target_amp > 0.0f) {
+    const float p2 = __fdiv_rn(pk, d);
+    if (!(p2 < 1e-6f)) {
+      gain = __fmul_rn(__frcp_rn(p2), target_amp);
+      s2 = true;
+    }
+  }
+  if (!s1 && !s2) return;
   float* x = wav + (size_t)blockIdx.y * n;
+  auto f = [&](float v) {
+    if (s1) v = __fdiv_rn(v, d);
+    if (s2) v = __fmul_rn(v, gain);
+    return v;
+  };
   const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 q = reinterpret_cast<float4*>(x)[i];
-    q.x = __fdiv_rn(q.x, pk); q.y = __fdiv_rn(q.y, pk); q.z = __fdiv_rn(q.z, pk); q.w = __fdiv_rn(q.w, pk);
+    q.x = f(q.x); q.y = f(q.y); q.z = f(q.z); q.w = f(q.w);
     reinterpret_cast<float4*>(x)[i] = q;
   }
-  for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
-    x[i] = __fdiv_rn(x[i], pk);
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) x[i] = f(x[i]);
 }
 
 // flags[0] |= 1 if any element is NaN or Inf; flags[1] |= 1 if any element is non-zero
 __global__ void __launch_bounds__(256)
 latent_guard_kernel(const uint16_t* __restrict__ lat, size_t n, int* __restrict__ flags) {
+  pdl_wait();
   bool bad = false, nonzero = false;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
     const unsigned v = lat[i] & 0x7fffu;
@@ -622,7 +645,7 @@ int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma
   return ACE_OK;
 }
 
-int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, cudaStream_t stream) {
+int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, float target_amp, cudaStream_t stream) {
   ACE_REQUIRE(batch >= 0 && (batch == 0 || peak) && (batch == 0 || n == 0 || wav), "peak_normalize: null argument");
   if (batch == 0) return ACE_OK;
   ACE_CUDA_CHECK(cudaMemsetAsync(peak, 0, (size_t)batch * sizeof(float), stream));
@@ -633,7 +656,8 @@ int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, cudaStre
   const unsigned gx = (unsigned)(per < want ? per : want);
   ELEM((double)batch * n * 4, abs_peak_kernel, dim3(gx, batch), 256, (const float*)wav, n,
        reinterpret_cast<unsigned*>(peak));
-  ELEM((double)batch * 4, peak_scale_kernel, dim3(gx, batch), 256, wav, n, (const float*)peak);
+  ELEM((double)batch * (target_amp > 0.f ? 8.0 * n : 4.0), peak_scale_kernel, dim3(gx, batch), 256, wav, n,
+       (const float*)peak, target_amp);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

@@ -20,6 +20,10 @@ struct AttnParams {
 };
 // legacy mma.sync kernel (attention.cu) — kept for A/B measurements (ACE_ATTN=legacy)
 int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t stream);
+// softmax(q k^T / sqrt(128)) with the eager path's bf16 roundings -> out [batch][heads][S][E] (bf16); q rows
+// [batch*S] at pitch ldq (head h at column 128 h), k rows [batch*E] at pitch ldk (kv head h / group)
+int launch_cross_probs(const bf16* q, long ldq, const bf16* k, long ldk, bf16* out, int heads, int batch, int S,
+                       int E, int group, cudaStream_t stream);
 
 // tcgen05 / TMEM kernel (attention_tc.cu): tensor maps are encoded once per bound shape
 struct AttnPlan {
@@ -73,10 +77,11 @@ int launch_apg(const bf16* cond, const bf16* uncond, bf16* momentum /*[B,T,64] r
 int launch_adg(const bf16* xt, const bf16* cond, const bf16* uncond, float sigma,
                float guidance_scale, float angle_clip, bf16* vt_out, int B, int T,
                cudaStream_t stream);
-// Output path: per-sample |x| peak into peak[batch] (fp32) and in-place x / max(peak, 1); latent sanity flags
+// Output path: per-sample |x| peak into peak[batch] (fp32) and in-place x / max(peak, 1), then (target_amp > 0)
+// the front-end's normalisation to target_amp; latent sanity flags
 // {any NaN/Inf, any non-zero} into flags[2].
 int num_sms();  // runtime.cu
-int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, cudaStream_t stream);
+int launch_peak_normalize(float* wav, int batch, size_t n, float* peak, float target_amp, cudaStream_t stream);
 int launch_latent_guard(const uint16_t* lat, size_t n, int* flags, cudaStream_t stream);
 
 }  // namespace ace

@@ -146,3 +146,24 @@ class B200DiT:
             _lib.check(self.lib.ace_dit_step(self.handle, xt.data_ptr(), ctx.data_ptr(), tv, out.data_ptr(),
                                              _lib.stream_handle(self.device)), "ace_dit_step")
         return out
+
+    def cross_attentions(self, xt: torch.Tensor, ctx: torch.Tensor, t: Sequence[float], n_layers: int) -> torch.Tensor:
+        """Cross-attention probabilities of layers [0, n_layers): bf16 [n_layers, bc, heads, S, E] with
+        S = ceil(T / 2) tokens — element [l] is what the reference decoder returns as
+        `outputs[2][l]` with output_attentions=True (turbo :1448-1482); the forward stops after layer
+        n_layers - 1.  Call set_condition() first, like step()."""
+        bc, T, _ = xt.shape
+        if self.bound is None or self.bound[:2] != (bc, T):
+            raise _lib.B200Error(f"cross_attentions: xt {tuple(xt.shape)} does not match bound shape {self.bound}")
+        if not 1 <= n_layers <= self.shape.num_hidden_layers:
+            raise ValueError(f"n_layers {n_layers} out of range [1, {self.shape.num_hidden_layers}]")
+        xt = xt.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        ctx = ctx.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        S, E = (T + 1) // 2, self.bound[2]
+        probs = torch.empty(n_layers, bc, self.shape.num_attention_heads, S, E, dtype=torch.bfloat16, device=self.device)
+        tv = (C.c_float * bc)(*[float(x) for x in t])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ace_dit_cross_attentions(self.handle, xt.data_ptr(), ctx.data_ptr(), tv, n_layers,
+                                                         probs.data_ptr(), _lib.stream_handle(self.device)),
+                       "ace_dit_cross_attentions")
+        return probs

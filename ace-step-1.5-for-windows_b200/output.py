@@ -18,9 +18,13 @@ NAN_MESSAGE = "Generation produced NaN or Inf latents."
 ZERO_MESSAGE = "Generation produced zero latents."
 
 
-def peak_normalize_(wav: torch.Tensor, peak: Optional[torch.Tensor] = None) -> torch.Tensor:
+def peak_normalize_(wav: torch.Tensor, peak: Optional[torch.Tensor] = None,
+                    normalization_db: Optional[float] = None) -> torch.Tensor:
     """In place on a CUDA fp32 tensor [B, C, N] (or [C, N] = one sample): every sample whose max|x| exceeds 1
-    is divided by it.  Returns the per-sample peaks [B] (fp32, on the device, measured BEFORE scaling)."""
+    is divided by it.  With `normalization_db` (<= 0, the front-end's GenerationParams.normalization_db,
+    inference.py:117-118, 674-679) the same kernel then applies `normalize_audio(sample, normalization_db)`
+    (acestep/audio_utils.py:24-62) to each sample, bit-identically to the reference's host pass.
+    Returns the per-sample peaks [B] (fp32, on the device, measured BEFORE scaling)."""
     if not wav.is_cuda:
         raise _lib.B200Error("peak_normalize_: the B200 output path needs a CUDA tensor (no CPU fallback)")
     if wav.dtype != torch.float32 or not wav.is_contiguous():
@@ -34,9 +38,17 @@ def peak_normalize_(wav: torch.Tensor, peak: Optional[torch.Tensor] = None) -> t
         peak = torch.empty(batch, dtype=torch.float32, device=wav.device)
     elif peak.numel() != batch or peak.dtype != torch.float32 or peak.device != wav.device:
         raise ValueError("peak buffer must be fp32 [B] on the waveform's device")
+    lib = _lib.load()
     with torch.cuda.device(wav.device):
-        _lib.check(_lib.load().ace_peak_normalize(wav.data_ptr(), batch, n, peak.data_ptr(),
-                                                  _lib.stream_handle(wav.device)), "ace_peak_normalize")
+        if normalization_db is None:
+            _lib.check(lib.ace_peak_normalize(wav.data_ptr(), batch, n, peak.data_ptr(),
+                                              _lib.stream_handle(wav.device)), "ace_peak_normalize")
+        else:
+            if normalization_db > 0.0:  # the front-end skips normalisation for positive targets (inference.py:674)
+                raise ValueError(f"normalization_db must be <= 0 dB, got {normalization_db}")
+            target_amp = 10 ** (normalization_db / 20.0)  # audio_utils.py:54
+            _lib.check(lib.ace_peak_normalize_db(wav.data_ptr(), batch, n, peak.data_ptr(), target_amp,
+                                                 _lib.stream_handle(wav.device)), "ace_peak_normalize_db")
     return peak
 
 

@@ -41,9 +41,13 @@ class B200Pipeline:
 
     def generate(self, encoder_hidden_states, context_latents, src_latents=None, seed=None, *,
                  noise=None, to_host: bool = True, decode: bool = True, latent_shift: float = 0.0,
-                 latent_rescale: float = 1.0, **sampler_kwargs) -> Dict[str, Any]:
+                 latent_rescale: float = 1.0, normalization_db: Optional[float] = None,
+                 **sampler_kwargs) -> Dict[str, Any]:
         """Returns {"audio": fp32 [B,2,N] (peak-normalised like the reference when |x|max > 1),
-        "target_latents": bf16 [B,T,64], "time_costs": {...}}."""
+        "target_latents": bf16 [B,T,64], "peak": fp32 [B] raw peaks, "time_costs": {...}}.
+        `normalization_db` (e.g. -1.0, GenerationParams.normalization_db) also applies the front-end's
+        `normalize_audio` per song (inference.py:674-679) inside the same device pass, so the host copy that
+        comes back is the final audio and the reference's three host passes over it are not needed."""
         t0 = time.time()
         enc, ctx = self._dev(encoder_hidden_states), self._dev(context_latents)
         src = self._dev(src_latents) if src_latents is not None else ctx[..., :64].contiguous()
@@ -60,7 +64,7 @@ class B200Pipeline:
             t1 = time.time()
             wav = torch.stack([self.vae.decode_frames(lat[b]) for b in range(lat.shape[0])], dim=0)
             # per-sample peak normalisation (generate_music_decode.py:191-195), in place, no host decision
-            res["peak"] = peak_normalize_(wav)
+            res["peak"] = peak_normalize_(wav, normalization_db=normalization_db)
             if to_host:
                 if self._pinned_wav is None or self._pinned_wav.shape != wav.shape:
                     self._pinned_wav = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)

@@ -87,6 +87,14 @@ int ace_dit_set_condition(AceDit* dit, const uint16_t* d_enc, void* stream);
 int ace_dit_step(AceDit* dit, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t,
                  uint16_t* d_vt, void* stream);
 
+/* One forward through layers [0, n_layers) that exports the CROSS-ATTENTION PROBABILITIES of each of them,
+ * d_probs [n_layers][bc][heads][S][e] bf16 with S = ceil(t / 2) tokens, and stops there — what
+ * `decoder(..., output_attentions=True, custom_layers_config=cfg, enable_early_exit=True)[2]` feeds the lyric
+ * aligner (handler/lyric_timestamp.py:78-103, lyric_score.py; turbo :349-350, :1448-1482), with n_layers =
+ * max(cfg) + 1.  Same roundings as the reference's eager path in bf16.  No velocity is produced. */
+int ace_dit_cross_attentions(AceDit* dit, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t,
+                             int n_layers, uint16_t* d_probs, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Sampler update kernels (base :1945-1979, turbo :1975-1991, apg_guidance.py)                  */
 /* ------------------------------------------------------------------------------------------ */
@@ -116,6 +124,11 @@ int ace_adg(const uint16_t* d_xt, const uint16_t* d_cond, const uint16_t* d_unco
  * identity, so the reference's batch-wide `if torch.any(peak > 1)` needs no host decision).  A NaN in a
  * sample makes its peak NaN and leaves the sample untouched. */
 int ace_peak_normalize(float* d_wav, int batch, size_t n, float* d_peak, void* stream);
+/* The same pass followed, in the same kernel, by the front-end's `normalize_audio` (acestep/audio_utils.py:24-62;
+ * on by default at -1 dB, inference.py:674-679) applied to the result: target_amp = 10^(dB/20) > 0; a sample whose
+ * peak after the first stage is below 1e-6 is left as it is.  Bit-identical to the two torch passes; d_peak still
+ * receives the raw peaks. */
+int ace_peak_normalize_db(float* d_wav, int batch, size_t n, float* d_peak, float target_amp, void* stream);
 /* Latent sanity guard over n bf16 elements: d_flags[0] = 1 if any NaN/Inf, d_flags[1] = 1 if any non-zero
  * (the reference raises on NaN/Inf and on all-zero latents before decoding). */
 int ace_latent_guard(const uint16_t* d_lat, size_t n, int* d_flags, void* stream);

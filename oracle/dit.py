@@ -87,8 +87,9 @@ def band_mask(seq_len: int, window: int, dtype=torch.float32) -> torch.Tensor:
     return m.masked_fill(keep, 0.0)[None, None]
 
 
-def attention(q, k, v, mask, n_rep: int, scaling: float) -> torch.Tensor:
-    """sdpa / eager attention with grouped KV heads (repeat_kv): q [B,H,S,D], k/v [B,Hkv,E,D]."""
+def attention(q, k, v, mask, n_rep: int, scaling: float, probs_out: Optional[list] = None) -> torch.Tensor:
+    """sdpa / eager attention with grouped KV heads (repeat_kv): q [B,H,S,D], k/v [B,Hkv,E,D].
+    `probs_out` (a list) receives the probabilities, like output_attentions=True (:349-368)."""
     if n_rep > 1:
         k = k.repeat_interleave(n_rep, dim=1)
         v = v.repeat_interleave(n_rep, dim=1)
@@ -96,6 +97,8 @@ def attention(q, k, v, mask, n_rep: int, scaling: float) -> torch.Tensor:
     if mask is not None:
         s = s + mask
     p = torch.softmax(s, dim=-1, dtype=torch.float32).to(q.dtype)
+    if probs_out is not None:
+        probs_out.append(p)  # [B, heads, Sq, Skv]: eager_attention_forward's second return value
     return torch.matmul(p, v)
 
 
@@ -136,7 +139,7 @@ def cross_kv(w, cfg: DiTConfig, layer: int, enc: torch.Tensor):
     return k, v
 
 
-def dit_layer(w, cfg: DiTConfig, i: int, h, tproj, cos, sin, mask, enc_kv) -> torch.Tensor:
+def dit_layer(w, cfg: DiTConfig, i: int, h, tproj, cos, sin, mask, enc_kv, cross_probs: Optional[list] = None) -> torch.Tensor:
     """AceStepDiTLayer.forward (:472-536)."""
     p = f"layers.{i}."
     eps = cfg.rms_norm_eps
@@ -160,7 +163,7 @@ def dit_layer(w, cfg: DiTConfig, i: int, h, tproj, cos, sin, mask, enc_kv) -> to
     c = p + "cross_attn."
     q = rms_norm(_heads(F.linear(x, w[c + "q_proj.weight"]), cfg.head_dim), w[c + "q_norm.weight"], eps)
     ck, cv = enc_kv
-    o = attention(q, ck, cv, None, n_rep, scaling).transpose(1, 2).reshape(h.shape[0], h.shape[1], -1)
+    o = attention(q, ck, cv, None, n_rep, scaling, cross_probs).transpose(1, 2).reshape(h.shape[0], h.shape[1], -1)
     h = h + F.linear(o, w[c + "o_proj.weight"])
 
     # SwiGLU MLP with AdaLN
@@ -180,10 +183,11 @@ class CrossCache:
 
 def dit_forward(w: Dict[str, torch.Tensor], cfg: DiTConfig, xt: torch.Tensor, t: torch.Tensor,
                 ctx: torch.Tensor, enc: torch.Tensor, cache: Optional[CrossCache] = None,
-                bf16_time: bool = False) -> torch.Tensor:
+                bf16_time: bool = False, cross_probs: Optional[list] = None) -> torch.Tensor:
     """AceStepDiTModel.forward (:1300-1504) with timestep_r == timestep (inference).
 
-    xt [B,T,64], t [B], ctx [B,T,128], enc [B,E,hidden] -> vt [B,T,64].
+    xt [B,T,64], t [B], ctx [B,T,128], enc [B,E,hidden] -> vt [B,T,64].  `cross_probs` (a list) receives one
+    [B, heads, S, E] tensor per layer: `all_cross_attentions` of output_attentions=True (:1448-1482).
     """
     B, T, _ = xt.shape
     temb_t, proj_t = timestep_embedding(w, "time_embed.", t, bf16_time)
@@ -208,7 +212,7 @@ def dit_forward(w: Dict[str, torch.Tensor], cfg: DiTConfig, xt: torch.Tensor, t:
             kv = cross_kv(w, cfg, i, enc_e)
             if cache is not None:
                 cache.kv[i] = kv
-        h = dit_layer(w, cfg, i, h, tproj, cos, sin, masks[cfg.layer_types[i]], kv)
+        h = dit_layer(w, cfg, i, h, tproj, cos, sin, masks[cfg.layer_types[i]], kv, cross_probs)
 
     shift, scale = (w["scale_shift_table"] + temb.unsqueeze(1)).chunk(2, dim=1)
     h = rms_norm(h, w["norm_out.weight"], cfg.rms_norm_eps) * (1 + scale) + shift

@@ -299,3 +299,85 @@ def test_graft_onto_real_handler_and_run_reference_plumbing_tests():
         suite.addTests(unittest.defaultTestLoader.loadTestsFromName(f"acestep.core.generation.handler.{m}"))
     result = unittest.TextTestRunner(verbosity=0, stream=open(os.devnull, "w")).run(suite)
     assert result.testsRun >= 30 and result.wasSuccessful(), (result.failures, result.errors)
+
+
+class _StubDiT:
+    """Records the attention-extraction calls the decoder shim makes."""
+
+    shape = types.SimpleNamespace(num_hidden_layers=24, num_attention_heads=16)
+
+    def __init__(self):
+        self.calls = []
+
+    def bind(self, bc, T, E):
+        self.calls.append(("bind", bc, T, E))
+
+    def set_condition(self, enc):
+        self.calls.append(("cond", tuple(enc.shape)))
+
+    def cross_attentions(self, xt, ctx, t, n_layers):
+        self.calls.append(("attn", tuple(xt.shape), tuple(ctx.shape), list(t), n_layers))
+        bc, T, _ = xt.shape
+        return torch.full((n_layers, bc, 16, (T + 1) // 2, 5), 0.2, dtype=torch.bfloat16)
+
+
+def test_lyric_alignment_callers_use_the_b200_decoder_shim():
+    """get_lyric_timestamp / get_lyric_score call model.decoder(..., output_attentions=True,
+    custom_layers_config, enable_early_exit=True) and read [2] (handler/lyric_timestamp.py:78-103): with the
+    B200 DiT active the decoder is swapped for the shim during the call and restored afterwards — also when
+    the call raises — and an inactive backend leaves everything alone."""
+
+    class RealDecoder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.seen = 0
+
+        def forward(self, **kw):
+            self.seen += 1
+            return "vt", None, ("ref-attn",) if kw.get("output_attentions") else None
+
+    class Model(torch.nn.Module):  # a real nn.Module: assigning a non-module to .decoder would raise
+        def __init__(self):
+            super().__init__()
+            self.decoder = RealDecoder()
+
+    class Host(FakeHandler):
+        custom_layers_config = {2: [6], 6: [8]}
+
+        def get_lyric_timestamp(self, xt, enc, ctx, fail=False, plain=False):
+            t = torch.tensor([0.125] * xt.shape[0], dtype=torch.bfloat16)
+            if plain:
+                return self.model.decoder(hidden_states=xt, timestep=t, timestep_r=t, encoder_hidden_states=enc,
+                                          context_latents=ctx)
+            out = self.model.decoder(hidden_states=xt, timestep=t, timestep_r=t, attention_mask=None,
+                                     encoder_hidden_states=enc, use_cache=False, past_key_values=None,
+                                     encoder_attention_mask=None, context_latents=ctx, output_attentions=True,
+                                     custom_layers_config=self.custom_layers_config, enable_early_exit=True)
+            if fail:
+                raise RuntimeError("aligner failure")
+            return out
+
+    h = Host()
+    h.model = Model()
+    real = h.model.decoder
+    install(h)
+    xt, enc, ctx = torch.zeros(2, 9, 64), torch.zeros(2, 5, 8), torch.zeros(2, 9, 128)
+    assert h.get_lyric_timestamp(xt, enc, ctx)[2] == ("ref-attn",) and real.seen == 1  # inactive: stock decoder
+    h.b200_dit, h.use_b200_dit = _StubDiT(), True
+    out = h.get_lyric_timestamp(xt, enc, ctx)
+    assert real.seen == 1 and h.model.decoder is real  # not called; restored
+    assert out[0] is None and len(out[2]) == 7 and out[2][6].shape == (2, 16, 5, 5)  # layers 0..max(cfg)
+    assert out[2][0].dtype == xt.dtype
+    assert h.b200_dit.calls == [("bind", 2, 9, 5), ("cond", (2, 5, 8)),
+                                ("attn", (2, 9, 64), (2, 9, 128), [0.125, 0.125], 7)]
+    with pytest.raises(RuntimeError):
+        h.get_lyric_timestamp(xt, enc, ctx, fail=True)
+    assert h.model.decoder is real
+    # a call without attention extraction made while the shim is in place goes to the real decoder
+    assert h.get_lyric_timestamp(xt, enc, ctx, plain=True)[0] == "vt" and real.seen == 2
+    # timestep_r != timestep is not representable by the engine: loud, not silent
+    from acestep_b200.backend import B200DecoderShim
+    shim = B200DecoderShim(h, real)
+    with pytest.raises(ValueError):
+        shim(hidden_states=xt, timestep=torch.tensor([0.5, 0.5]), timestep_r=torch.tensor([0.0, 0.0]),
+             encoder_hidden_states=enc, context_latents=ctx, output_attentions=True)

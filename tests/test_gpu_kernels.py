@@ -424,3 +424,62 @@ def test_attention_p_in_tmem_stress(lib):
         lib.ace_debug_set_attention_p_in_tmem(-1)
     assert torch.isfinite(outs[1].float()).all()
     assert torch.equal(outs[0], outs[1]), max_abs(outs[0].float(), outs[1].float())
+
+
+def test_cross_attention_probabilities_tiny_vs_oracle_and_reference(lib):
+    """ace_dit_cross_attentions (the lyric aligner's output_attentions call, handler/lyric_timestamp.py:78-91)
+    vs the fp32 oracle with the same bf16-rounded weights, and vs the REAL reference decoder's fp32 output
+    (tests/golden/dit_cross_attn_tiny.npz).  Tolerance: probabilities are bf16 (2^-9 relative) computed from
+    scores the eager path rounds to bf16 twice (2^-8 relative on |score| <= ~6 -> a few 1e-2 relative on p):
+    rel-L2 <= 3e-2 per layer, max-abs <= 2e-2, rows sum to 1 within 1e-2."""
+    cfg, w = _tiny_dit()
+    g = golden("dit_cross_attn_tiny")
+    xt, ctx, enc = (g[k].to(torch.bfloat16) for k in ("xt", "ctx", "enc"))
+    t = g["t"].to(torch.bfloat16)
+    want = []
+    dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True, cross_probs=want)
+    L = cfg.num_hidden_layers
+    assert len(want) == L
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    dit.bind(xt.shape[0], xt.shape[1], enc.shape[1])
+    dit.set_condition(enc.to(DEV))
+    for n_layers in (L, 1, 3):
+        probs = dit.cross_attentions(xt.to(DEV), ctx.to(DEV), t.float().tolist(), n_layers)
+        torch.cuda.synchronize()
+        assert probs.shape == (n_layers, 2, cfg.num_attention_heads, 19, 21) and probs.dtype == torch.bfloat16
+        p = probs.cpu().float()
+        assert torch.isfinite(p).all() and p.min() >= 0 and p.max() <= 1
+        assert (p.sum(-1) - 1).abs().max() <= 1e-2
+        for l in range(n_layers):
+            assert rel_l2(p[l], want[l]) <= 3e-2, (n_layers, l)
+            assert max_abs(p[l], want[l]) <= 2e-2, (n_layers, l)
+            assert rel_l2(p[l], g["probs"][l]) <= 4e-2, (n_layers, l)  # real reference, fp32 weights
+    # the step after an attention extraction is unaffected (shared workspace, graph replay)
+    vt = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())
+    want_vt = dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True)
+    assert rel_l2(vt.cpu().float(), want_vt) <= 2e-2
+    with pytest.raises(ValueError):
+        dit.cross_attentions(xt.to(DEV), ctx.to(DEV), t.float().tolist(), L + 1)
+
+
+def test_cross_attention_probabilities_ragged_mid_size(lib):
+    """S and E that are not multiples of the kernel's 16-row / 64-key tiles, GQA 4:2, odd E (2-byte rows)."""
+    cfg = DiTConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                    num_key_value_heads=2, sliding_window=128)
+    w = bf16_round_(make_dit_weights(cfg, seed=5))
+    g = torch.Generator().manual_seed(8)
+    B, T, E = 2, 333, 131
+    xt = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    ctx = torch.cat([torch.randn(B, T, 64, generator=g), torch.ones(B, T, 64)], -1).to(torch.bfloat16)
+    enc = torch.randn(B, E, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    t = torch.tensor([0.125, 0.125]).to(torch.bfloat16)
+    want = []
+    dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True, cross_probs=want)
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    dit.bind(B, T, E)
+    dit.set_condition(enc.to(DEV))
+    p = dit.cross_attentions(xt.to(DEV), ctx.to(DEV), t.float().tolist(), 2).cpu().float()
+    assert p.shape == (2, B, 4, 167, E)
+    assert (p.sum(-1) - 1).abs().max() <= 1e-2
+    for l in range(2):
+        assert rel_l2(p[l], want[l]) <= 3e-2 and max_abs(p[l], want[l]) <= 2e-2, l

@@ -181,3 +181,34 @@ def test_condition_sequence_plumbing_matches_oracle():
     order = torch.tensor([2, 0, 2, 1, 2, 0])
     got, want = unpack_timbre_embeddings(embs, order), ocond.unpack_timbre(embs, order)
     assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+def test_output_path_restatements_match_reference_bit_exact():
+    """oracle.output vs the real `normalize_audio` (compiled from the reference source by
+    tools/make_golden_output.py) and the handler's peak-normalisation expressions: bit-exact."""
+    from oracle import output as oout
+
+    g = golden("output_normalize")
+    wavs, peak = oout.peak_normalize(g["wav"])
+    assert torch.equal(peak, g["peak"]) and torch.equal(wavs, g["stage1"])
+    for db in (-1.0, 0.0, -6.0, -0.1):
+        final, _ = oout.finalize(g["wav"], db)
+        assert torch.equal(final, g[f"final_db{db}"]), db
+    raw = torch.stack([oout.normalize_audio(g["raw"][i], -1.0) for i in range(g["raw"].shape[0])])
+    assert torch.equal(raw, g["raw_db-1.0"])
+    # silence and near-silence are returned unchanged (audio_utils.py:50-51)
+    assert torch.equal(g["final_db-1.0"][5], g["stage1"][5]) and torch.equal(g["final_db-1.0"][6], g["stage1"][6])
+    assert oout.latent_guard(torch.zeros(2, 3)) == (False, False)
+    assert oout.latent_guard(torch.tensor([0.0, float("inf")])) == (True, True)
+
+
+def test_cross_attention_probabilities_match_reference(dit):
+    """oracle `cross_probs` vs `decoder(..., output_attentions=True, enable_early_exit=True)[2]` of the real
+    reference (tools/make_golden_attn.py)."""
+    cfg, w, _ = dit
+    g = golden("dit_cross_attn_tiny")
+    got = []
+    vt = dit_forward(w, cfg, g["xt"], g["t"], g["ctx"], g["enc"], cross_probs=got)
+    assert len(got) == cfg.num_hidden_layers == g["probs"].shape[0]
+    assert rel_l2(torch.stack(got), g["probs"]) < TOL
+    assert rel_l2(vt, g["vt"]) < TOL  # the eager path's velocity equals the sdpa one to fp32 round-off
