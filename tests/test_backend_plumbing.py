@@ -381,3 +381,17 @@ def test_lyric_alignment_callers_use_the_b200_decoder_shim():
     with pytest.raises(ValueError):
         shim(hidden_states=xt, timestep=torch.tensor([0.5, 0.5]), timestep_r=torch.tensor([0.0, 0.0]),
              encoder_hidden_states=enc, context_latents=ctx, output_attentions=True)
+
+
+def test_output_path_has_no_cpu_fallback():
+    """The product output path refuses CPU tensors instead of quietly running torch (no CPU fallback anywhere
+    on the hot path); argument validation happens before any library call."""
+    from acestep_b200 import _lib
+    from acestep_b200.output import check_latents, latent_flags, peak_normalize_
+
+    with pytest.raises(_lib.B200Error):
+        peak_normalize_(torch.zeros(1, 2, 8))
+    with pytest.raises(_lib.B200Error):
+        latent_flags(torch.zeros(1, 4, 64, dtype=torch.bfloat16))
+    with pytest.raises(_lib.B200Error):
+        check_latents(torch.zeros(1, 4, 64, dtype=torch.bfloat16))

@@ -13,7 +13,7 @@ from acestep_b200.vae import B200Vae, VaeShape
 
 dev = torch.device("cuda:0")
 T = int(os.environ.get("PROF_T", "1500"))
-E, Bc = 512, int(os.environ.get("PROF_BC", "2"))
+E, Bc = int(os.environ.get("PROF_E", "512")), int(os.environ.get("PROF_BC", "2"))  # PROF_E: condition tokens (SURVEY §8d side table: 64 / 512 / 2305)
 dit = B200DiT(random_dit_state(DiTShape(), 0, dev), DiTShape(), dev)
 g = torch.Generator(device=dev).manual_seed(0)
 xt = torch.randn(Bc, T, 64, device=dev, generator=g).bfloat16()
@@ -33,7 +33,7 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-msg = f"skip={os.environ.get('ACE_SKIP', '-'):10s} T={T} Bc={Bc}: DiT step {ms:.3f} ms"
+msg = f"skip={os.environ.get('ACE_SKIP', '-'):10s} T={T} Bc={Bc} E={E}: DiT step {ms:.3f} ms"
 if os.environ.get("PROF_VAE", "1") == "1" and not os.environ.get("ACE_SKIP"):
     vae = B200Vae(random_vae_state(VaeShape(), 0, dev), VaeShape(), dev)
     z = xt[0]
