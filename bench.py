@@ -85,6 +85,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi's start-up (NVML attach) can stall the GPU for tens of ms: let it deliver its first
+            # sample BEFORE the timed region opens (seen once as +12 ms per song on the first region only)
+            deadline = time.perf_counter() + 5.0
+            while not self.lines and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
@@ -290,6 +295,9 @@ def run_b200(args, wl):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    song_device()  # one more untimed song after the sampler attached, so the region starts from steady state
+    drain()
+    barrier()
     win = {}
 
     def measure_value():

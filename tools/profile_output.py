@@ -53,9 +53,10 @@ us_db = timed(lambda: peak_normalize_(next(it), normalization_db=-1.0), reps=20)
 us_guard = timed(lambda: latent_flags(lat), reps=20)
 us_attn = timed(lambda: dit.cross_attentions(xt, ctx, [0.125] * Bc, 7), reps=5)
 mb = base.numel() * 4 / 1e6
-print(f"peak_normalize (2 x 60 s, one scaled): {us_plain:.1f} us  ({mb * 1.5 / us_plain * 1e-3 * 1e3:.0f} GB/s algorithmic: "
-      f"read all + rewrite the loud half)")
-print(f"peak_normalize -1 dB (both scaled):    {us_db:.1f} us  ({mb * 3 / us_db:.0f} GB/s algorithmic)")
+# mb MB at 1 us = mb TB/s = 1000 mb GB/s
+print(f"peak_normalize (2 x 60 s, one scaled): {us_plain:.1f} us  ({mb * 2.0 / us_plain * 1e3:.0f} GB/s algorithmic: "
+      f"read all, then read + write the loud half; memset + 2 launches included)")
+print(f"peak_normalize -1 dB (both scaled):    {us_db:.1f} us  ({mb * 3 / us_db * 1e3:.0f} GB/s algorithmic: read, read + write)")
 print(f"latent guard (2 x 1500 x 64 bf16, incl. the 8-byte read-back): {us_guard:.1f} us")
 print(f"cross attentions, 7 layers at C2 (incl. the partial forward):   {us_attn:.1f} us")
 
