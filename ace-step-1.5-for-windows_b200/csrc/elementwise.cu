@@ -449,10 +449,20 @@ abs_peak_kernel(const float* __restrict__ wav, size_t n, unsigned* __restrict__ 
   const float* x = wav + (size_t)blockIdx.y * n;
   unsigned m = 0u;
   const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + i);
-    m = max(max(m, q.x & 0x7fffffffu), max(q.y & 0x7fffffffu, max(q.z & 0x7fffffffu, q.w & 0x7fffffffu)));
+  // four independent 16-byte loads in flight per thread: with one, 592 CTAs keep 2.4 MB outstanding and the
+  // kernel sits at 3.6 TB/s (profiles/r1_v6_ncu_output_summary.txt), latency-bound rather than HBM-bound
+  const uint4* x4 = reinterpret_cast<const uint4*>(x);
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  auto amax4 = [](unsigned acc, const uint4& q) {
+    return max(max(acc, q.x & 0x7fffffffu), max(q.y & 0x7fffffffu, max(q.z & 0x7fffffffu, q.w & 0x7fffffffu)));
+  };
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const uint4 q0 = __ldg(x4 + i), q1 = __ldg(x4 + i + stride), q2 = __ldg(x4 + i + 2 * stride),
+                q3 = __ldg(x4 + i + 3 * stride);
+    m = amax4(amax4(amax4(amax4(m, q0), q1), q2), q3);
   }
+  for (; i < n4; i += stride) m = amax4(m, __ldg(x4 + i));
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
     m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
   m = __reduce_max_sync(0xffffffffu, m);
@@ -494,11 +504,21 @@ peak_scale_kernel(float* __restrict__ wav, size_t n, const float* __restrict__ p
     return v;
   };
   const size_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    float4 q = reinterpret_cast<float4*>(x)[i];
+  float4* x4 = reinterpret_cast<float4*>(x);
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  auto f4 = [&](float4 q) {
     q.x = f(q.x); q.y = f(q.y); q.z = f(q.z); q.w = f(q.w);
-    reinterpret_cast<float4*>(x)[i] = q;
+    return q;
+  };
+  for (; i + 3 * stride < n4; i += 4 * stride) {  // four loads in flight before the (XU-heavy) divisions
+    const float4 q0 = x4[i], q1 = x4[i + stride], q2 = x4[i + 2 * stride], q3 = x4[i + 3 * stride];
+    x4[i] = f4(q0);
+    x4[i + stride] = f4(q1);
+    x4[i + 2 * stride] = f4(q2);
+    x4[i + 3 * stride] = f4(q3);
   }
+  for (; i < n4; i += stride) x4[i] = f4(x4[i]);
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) x[i] = f(x[i]);
 }
 
