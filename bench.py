@@ -288,17 +288,23 @@ def run_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        song_device()
-    drain()
-    barrier()
+    # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop
+    # (`out = song_device()`): otherwise the timed region's second song is the first to need a second set of
+    # output buffers and pays torch's cudaMalloc (+6 ... +24 ms on that one song, seen with ACE_BENCH_PER_SONG=1).
+    # The clock sampler attaches BEFORE the warm-up, and the warm-up runs back to back into the timed region:
+    # after any idle gap a power-capped B200 runs one song fast and then over-corrects for about one song
+    # (148 / 174 / 150 / 150 ... ms per song with ACE_BENCH_PER_SONG=1), so the gap must not sit between them.
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    song_device()  # one more untimed song after the sampler attached, so the region starts from steady state
-    drain()
     barrier()
+    out = None
+    for _ in range(args.warmup):
+        out = song_device()
+    drain()
     win = {}
+
+    per_song = os.environ.get("ACE_BENCH_PER_SONG") == "1"
 
     def measure_value():
         """EXACTLY K songs, device-resident inputs, CUDA events, barrier + synchronize on both sides."""
@@ -307,12 +313,22 @@ def run_b200(args, wl):
         barrier()
         w0 = time.perf_counter()
         e0.record()
+        marks = []
         for _ in range(args.steps):
             out = song_device()
+            if per_song:  # diagnostics only (ACE_BENCH_PER_SONG=1): one extra event record per song
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         drain()  # all gathers complete inside the timed region
         e1.record()
         barrier()
         win["value"] = (w0, time.perf_counter())
+        if per_song:
+            prev, per = e0, []
+            for m in marks:
+                per.append(round(prev.elapsed_time(m), 2))
+                prev = m
+            print(f"[bench rank {rank}] per-song ms in the value region: {per}", file=sys.stderr)
         return e0.elapsed_time(e1), lib.ace_launch_count() - l0, bool(torch.isfinite(out["audio"]).all())
 
     def measure_e2e():
