@@ -308,6 +308,7 @@ def run_b200(args, wl):
 
     def measure_value():
         """EXACTLY K songs, device-resident inputs, CUDA events, barrier + synchronize on both sides."""
+        nonlocal out  # the warm-up's last result is released by the first timed song, as in steady state
         l0 = lib.ace_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
