@@ -395,3 +395,69 @@ def test_output_path_has_no_cpu_fallback():
         latent_flags(torch.zeros(1, 4, 64, dtype=torch.bfloat16))
     with pytest.raises(_lib.B200Error):
         check_latents(torch.zeros(1, 4, 64, dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_real_get_lyric_timestamp_runs_through_the_decoder_shim():
+    """The reference's OWN `LyricTimestampMixin.get_lyric_timestamp` (handler/lyric_timestamp.py:14-147) and its
+    DTW aligner (core/scoring/dit_alignment.py), unmodified, on a host grafted with the B200 backend: the decoder
+    call is answered by the shim (the stock decoder would raise), the aligner consumes the [layers, heads,
+    tokens, frames] stack built from it, and a near-diagonal attention pattern yields monotone timestamps."""
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("vector_quantize_pytorch")
+    stub.ResidualFSQ = type("ResidualFSQ", (torch.nn.Module,), {})
+    sys.modules.setdefault("vector_quantize_pytorch", stub)
+    from acestep.core.generation.handler.lyric_timestamp import LyricTimestampMixin
+
+    class Tok:
+        def encode(self, s, add_special_tokens=False):
+            return [1, 2, 3]
+
+        def decode(self, ids, **k):
+            return "".join(chr(97 + (i % 26)) for i in ids)
+
+        def convert_ids_to_tokens(self, ids):
+            return [chr(97 + (i % 26)) for i in ids]
+
+    class Dec(torch.nn.Module):
+        def forward(self, **kw):
+            raise AssertionError("the stock decoder must not run while the B200 DiT is active")
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.decoder = Dec()
+
+    class Host(LyricTimestampMixin, FakeHandler):
+        def __init__(self):
+            FakeHandler.__init__(self)
+            self.model = Model()
+            self.text_tokenizer = Tok()
+            self.custom_layers_config = {2: [6], 3: [10, 11]}
+
+    class DiagonalDiT(_StubDiT):
+        def set_condition(self, enc):
+            self.E = enc.shape[1]
+
+        def cross_attentions(self, xt, ctx, t, n_layers):
+            self.calls.append(("attn", n_layers, list(t)))
+            bc, T, _ = xt.shape
+            S = (T + 1) // 2
+            g = torch.Generator().manual_seed(0)
+            p = torch.rand(n_layers, bc, 16, S, self.E, generator=g) + 5 * torch.eye(S, self.E)[None, None, None]
+            return (p / p.sum(-1, keepdim=True)).to(torch.bfloat16)
+
+    h = install(Host())
+    h.b200_dit, h.use_b200_dit = DiagonalDiT(), True
+    T, E = 40, 20
+    ids = torch.tensor([[1, 2, 3] + list(range(10, 22)) + [151643] + [0] * 4])
+    out = h.get_lyric_timestamp(pred_latent=torch.randn(1, T, 64), encoder_hidden_states=torch.randn(1, E, 32),
+                                encoder_attention_mask=torch.ones(1, E), context_latents=torch.randn(1, T, 128),
+                                lyric_token_ids=ids, total_duration_seconds=1.6, inference_steps=8)
+    assert out["success"] is True and out["error"] is None, out
+    assert len(out["token_timestamps"]) == 12 and out["lrc_text"].startswith("[00:00")
+    starts = [t.start for t in out["token_timestamps"]]
+    assert starts == sorted(starts) and starts[-1] > starts[0]
+    # early exit at max(custom_layers_config) + 1 = 4 layers, t = 1 / inference_steps
+    assert h.b200_dit.calls[-1] == ("attn", 4, [0.125])
+    assert isinstance(h.model.decoder, Dec)  # restored
