@@ -461,3 +461,62 @@ def test_real_get_lyric_timestamp_runs_through_the_decoder_shim():
     # early exit at max(custom_layers_config) + 1 = 4 layers, t = 1 / inference_steps
     assert h.b200_dit.calls[-1] == ("attn", 4, [0.125])
     assert isinstance(h.model.decoder, Dec)  # restored
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_real_decode_step_is_an_identity_after_the_b200_peak_normalisation():
+    """The reference's OWN `_decode_generate_music_pred_latents` (handler/generate_music_decode.py:98-201),
+    unmodified, over the wrapped `tiled_decode`: the B200 seam returns waveforms that are already peak-normalised
+    (`decode_normalized`; stubbed here with the oracle expression the CUDA kernel is bit-exact against), so the
+    reference's own normalisation at :191-195 must leave them untouched and the result must equal the reference
+    normalising the raw waveforms itself — bit for bit."""
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("vector_quantize_pytorch")
+    stub.ResidualFSQ = type("ResidualFSQ", (torch.nn.Module,), {})
+    sys.modules.setdefault("vector_quantize_pytorch", stub)
+    from acestep.core.generation.handler.generate_music_decode import GenerateMusicDecodeMixin
+    from oracle import output as oout
+
+    raw = {}
+
+    class Engine:
+        def decode(self, lat):
+            g = torch.Generator().manual_seed(3)
+            gains = torch.tensor([0.2, 1.7, 3.1]).view(-1, 1, 1)[: lat.shape[0]]
+            raw["w"] = torch.randn(lat.shape[0], 2, lat.shape[2] * 1920, generator=g) * gains
+            return raw["w"].clone()
+
+        def decode_normalized(self, lat):
+            return oout.peak_normalize(self.decode(lat))[0]
+
+    class Vae(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        @property
+        def dtype(self):
+            return torch.float32
+
+    class Host(GenerateMusicDecodeMixin, FakeHandler):
+        def __init__(self):
+            FakeHandler.__init__(self)
+            self.vae, self.use_mlx_vae, self.mlx_vae, self.current_offload_cost = Vae(), False, None, 0.0
+
+        def _empty_cache(self):
+            pass
+
+        def _memory_allocated(self):
+            return 0
+
+        def _max_memory_allocated(self):
+            return 0
+
+    h = install(Host())
+    h.b200_vae, h.use_b200_vae = Engine(), True
+    wavs, lat_cpu, costs = h._decode_generate_music_pred_latents(torch.randn(3, 5, 64), None, True,
+                                                                {"total_time_cost": 1.0})
+    want, _ = oout.peak_normalize(raw["w"])
+    assert torch.equal(wavs, want) and h.ref_calls == []
+    assert wavs.abs().amax(dim=[1, 2]).tolist()[1:] == [1.0, 1.0] and float(wavs.abs().amax(dim=[1, 2])[0]) < 1.0
+    assert lat_cpu.shape == (3, 5, 64) and "vae_decode_time_cost" in costs
