@@ -520,3 +520,64 @@ def test_real_decode_step_is_an_identity_after_the_b200_peak_normalisation():
     assert torch.equal(wavs, want) and h.ref_calls == []
     assert wavs.abs().amax(dim=[1, 2]).tolist()[1:] == [1.0, 1.0] and float(wavs.abs().amax(dim=[1, 2])[0]) < 1.0
     assert lat_cpu.shape == (3, 5, 64) and "vae_decode_time_cost" in costs
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_real_reference_audio_callers_reach_the_b200_encoder():
+    """the reference's OWN callers of `tiled_encode` — `infer_refer_latent`
+    (handler/conditioning_embed.py:18-69, with its per-request encode cache), `_encode_audio_to_latents`
+    (handler/batch_prep.py:63-76) and `_prepare_target_latents_and_wavs` (handler/conditioning_target.py:18-107,
+    with its same-audio cache and silence shortcut) — run unmodified on a grafted host and reach the B200 VAE
+    through the wrapped seam with the shapes / layouts they expect."""
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("vector_quantize_pytorch")
+    stub.ResidualFSQ = type("ResidualFSQ", (torch.nn.Module,), {})
+    sys.modules.setdefault("vector_quantize_pytorch", stub)
+    from acestep.core.generation.handler.batch_prep import BatchPrepMixin
+    from acestep.core.generation.handler.conditioning_embed import ConditioningEmbedMixin
+    from acestep.core.generation.handler.conditioning_target import ConditioningTargetMixin
+
+    class CountingVae(StubVae):
+        def __init__(self):
+            self.encodes = []
+
+        def encode(self, audio, sample=True):
+            self.encodes.append(tuple(audio.shape))
+            return torch.full((audio.shape[0], 64, audio.shape[2] // 1920), float(len(self.encodes)))
+
+    class Host(ConditioningEmbedMixin, ConditioningTargetMixin, BatchPrepMixin, FakeHandler):
+        def __init__(self):
+            FakeHandler.__init__(self)
+            self.silence_latent = torch.full((1, 800, 64), -1.0)
+
+        def _ensure_silence_latent_on_device(self):
+            pass
+
+        def is_silence(self, audio):
+            return bool(torch.all(audio.abs() < 1e-6))
+
+        def _decode_audio_codes_to_latents(self, code_hint):
+            return None
+
+    h = install(Host())
+    h.b200_vae, h.use_b200_vae = CountingVae(), True
+    # reference clips are 30 s = 750 frames (the silence shortcut returns silence_latent[:, :750], :47)
+    ref_a = torch.rand(2, 1920 * 750) - 0.5
+    ref_b = torch.rand(1, 1920 * 750) - 0.5  # mono: duplicated to stereo by the caller (:33-35)
+    # item 0: two references, the first one twice (cache hit on data_ptr); item 1: all-zero audio -> silence latent
+    lat, order = h.infer_refer_latent([[ref_a, ref_b, ref_a], [torch.zeros(2, 1920 * 3)]])
+    assert h.b200_vae.encodes == [(1, 2, 1920 * 750), (1, 2, 1920 * 750)] and h.ref_calls == []
+    assert order.tolist() == [0, 0, 0, 1] and lat.shape == (4, 750, 64)
+    assert float(lat[0, 0, 0]) == 1.0 and float(lat[1, 0, 0]) == 2.0 and float(lat[2, 0, 0]) == 1.0
+    assert float(lat[3, 0, 0]) == -1.0
+    a = torch.rand(2, 1920 * 6) - 0.5
+    z = h._encode_audio_to_latents(a)  # [2, N] -> [T, 64] in the handler dtype on the handler device
+    assert z.shape == (6, 64) and z.dtype == h.dtype and float(z[0, 0]) == 3.0
+    # batch prep: item 1 repeats item 0's audio (cached, no second encode), item 2 is silence
+    h.b200_vae.encodes.clear()
+    wavs = torch.stack([a, a, torch.zeros_like(a)])
+    tw, tl, masks, max_len, sil = h._prepare_target_latents_and_wavs(3, wavs, [None, None, None])
+    assert h.b200_vae.encodes == [(1, 2, 1920 * 6)] and h.ref_calls == []
+    assert tl.shape == (3, 128, 64) and max_len == 128 and masks.sum(1).tolist() == [6, 6, 6]
+    assert float(tl[0, 0, 0]) == float(tl[1, 0, 0]) == 1.0 and float(tl[2, 0, 0]) == -1.0
+    assert float(tl[0, 6, 0]) == -1.0  # padded with the silence latent (:84-89)
