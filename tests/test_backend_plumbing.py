@@ -581,3 +581,63 @@ def test_real_reference_audio_callers_reach_the_b200_encoder():
     assert tl.shape == (3, 128, 64) and max_len == 128 and masks.sum(1).tolist() == [6, 6, 6]
     assert float(tl[0, 0, 0]) == float(tl[1, 0, 0]) == 1.0 and float(tl[2, 0, 0]) == -1.0
     assert float(tl[0, 6, 0]) == -1.0  # padded with the silence latent (:84-89)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_real_get_lyric_score_runs_through_the_decoder_shim():
+    """The reference's OWN `get_lyric_score` (handler/lyric_score.py:14-160) + `MusicLyricScorer`: one decoder call
+    at batch 2 (pure noise at t = 1 and the regressed latent at t = 1 / steps), answered by the shim."""
+    sys.path.insert(0, REF)
+    stub = types.ModuleType("vector_quantize_pytorch")
+    stub.ResidualFSQ = type("ResidualFSQ", (torch.nn.Module,), {})
+    sys.modules.setdefault("vector_quantize_pytorch", stub)
+    from acestep.core.generation.handler.lyric_score import LyricScoreMixin
+
+    class Tok:
+        def encode(self, s, add_special_tokens=False):
+            return [1, 2, 3]
+
+        def decode(self, ids, **k):
+            return "".join(chr(97 + (i % 26)) for i in ids)
+
+        def convert_ids_to_tokens(self, ids):
+            return [chr(97 + (i % 26)) for i in ids]
+
+    class Dec(torch.nn.Module):
+        def forward(self, **kw):
+            raise AssertionError("the stock decoder must not run while the B200 DiT is active")
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.decoder = Dec()
+
+    class Host(LyricScoreMixin, FakeHandler):
+        def __init__(self):
+            FakeHandler.__init__(self)
+            self.model, self.text_tokenizer = Model(), Tok()
+            self.custom_layers_config = {2: [6], 3: [10, 11]}
+
+    class DiagonalDiT(_StubDiT):
+        def set_condition(self, enc):
+            self.E = enc.shape[1]
+
+        def cross_attentions(self, xt, ctx, t, n_layers):
+            self.calls.append(("attn", tuple(xt.shape), list(t), n_layers))
+            bc, T, _ = xt.shape
+            S = (T + 1) // 2
+            g = torch.Generator().manual_seed(0)
+            p = torch.rand(n_layers, bc, 16, S, self.E, generator=g) + 5 * torch.eye(S, self.E)[None, None, None]
+            return (p / p.sum(-1, keepdim=True)).to(torch.bfloat16)
+
+    h = install(Host())
+    h.b200_dit, h.use_b200_dit = DiagonalDiT(), True
+    T, E = 40, 20
+    ids = torch.tensor([[1, 2, 3] + list(range(10, 22)) + [151643] + [0] * 4])
+    out = h.get_lyric_score(pred_latent=torch.randn(1, T, 64), encoder_hidden_states=torch.randn(1, E, 32),
+                            encoder_attention_mask=torch.ones(1, E), context_latents=torch.randn(1, T, 128),
+                            lyric_token_ids=ids, inference_steps=8)
+    assert out["success"] is True and out["error"] is None, out
+    assert isinstance(out["lm_score"], float) and isinstance(out["dit_score"], float)
+    assert h.b200_dit.calls[-1] == ("attn", (2, T, 64), [1.0, 0.125], 4)
+    assert isinstance(h.model.decoder, Dec)
