@@ -123,3 +123,16 @@ def test_engines_refuse_cpu():
 
     with pytest.raises(_lib.B200Error):
         B200DiT(random_dit_state(shape, 0, "cpu", torch.float32), shape, "cpu")
+
+
+def test_argument_errors_are_reported_before_any_device_work(lib):
+    """Entry points validate their arguments first and report through the int status + ace_last_error(): these
+    calls never reach a CUDA API, so they behave the same on a box without a GPU."""
+    assert lib.ace_peak_normalize_db(None, 1, 8, None, 0.0, None) != 0
+    assert b"target_amp" in lib.ace_last_error()
+    assert lib.ace_peak_normalize(None, 1, 8, None, None) != 0
+    assert b"null argument" in lib.ace_last_error()
+    assert lib.ace_peak_normalize(None, 0, 8, None, None) == 0  # empty batch: nothing to do
+    assert lib.ace_latent_guard(None, 8, None, None) != 0
+    assert lib.ace_dit_cross_attentions(None, None, None, None, 1, None, None) != 0
+    assert b"not bound" in lib.ace_last_error()
