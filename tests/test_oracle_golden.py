@@ -212,3 +212,20 @@ def test_cross_attention_probabilities_match_reference(dit):
     assert len(got) == cfg.num_hidden_layers == g["probs"].shape[0]
     assert rel_l2(torch.stack(got), g["probs"]) < TOL
     assert rel_l2(vt, g["vt"]) < TOL  # the eager path's velocity equals the sdpa one to fp32 round-off
+
+
+def test_sft_explicit_timesteps(dit):
+    """The SFT model's `timesteps` override (sft/modeling_acestep_v15_base.py:1864-1875: replaces the
+    linspace/shift schedule and infer_steps) against the REAL sft module (tools/make_golden_sft.py)."""
+    _, _, vel = dit
+    g = golden("sft_timesteps")
+    out = osamp.sample_base(vel, g["enc"], g["ctx"], g["src"], [int(s) for s in g["seeds"]], null_emb=g["null_emb"],
+                            infer_steps=99, guidance_scale=6.0, shift=2.0, timesteps=g["timesteps"],
+                            new_cache=CrossCache)
+    assert rel_l2(out, g["out"]) < TOL
+    g = golden("sft_timesteps_cover")
+    out = osamp.sample_base(vel, g["enc"], g["ctx"], g["src"], g["seed"], null_emb=g["null_emb"], infer_steps=99,
+                            guidance_scale=4.0, shift=3.0, timesteps=g["timesteps"], cover_noise_strength=0.25,
+                            audio_cover_strength=0.6, enc_non_cover=g["enc_nc"], ctx_non_cover=g["ctx_nc"],
+                            new_cache=CrossCache)
+    assert rel_l2(out, g["out"]) < TOL
