@@ -113,6 +113,27 @@ def test_base_cfg_matches_reference(env, name, kw):
     _check(out["target_latents"], want, run16, g["out"])
 
 
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: not yet run on a B200; "
+                                        "XPASS at round end = promote to a plain test next round")
+def test_sft_explicit_timesteps_matches_reference(env):
+    """SFT variant: explicit `timesteps` replace the linspace/shift schedule and infer_steps
+    (sft/modeling_acestep_v15_base.py:1864-1875); golden from the real sft module (tools/make_golden_sft.py)."""
+    cfg, dit, vel32, vel16 = env
+    g = golden("sft_timesteps")
+    seed = [int(s) for s in g["seeds"]]
+    noise = prepare_noise((2, 40, 64), seed, "cpu", torch.float32)
+    ts = [float(x) for x in g["timesteps"]]
+    kw = dict(infer_steps=99, shift=2.0, timesteps=ts)
+    s = B200Sampler(dit, g["null_emb"])
+    out = s.generate_base(_b(g["enc"]), _b(g["ctx"]), _b(g["src"]), seed, diffusion_guidance_sale=6.0, noise=_b(noise), **kw)
+    f = lambda x: _b(x).float()
+    want = osamp.sample_base(vel32, f(g["enc"]), f(g["ctx"]), f(g["src"]), seed, null_emb=f(g["null_emb"]),
+                             guidance_scale=6.0, noise=f(noise), new_cache=CrossCache, **kw)
+    run16 = lambda: osamp.sample_base(vel16, _b(g["enc"]), _b(g["ctx"]), _b(g["src"]), seed, null_emb=_b(g["null_emb"]),
+                                      guidance_scale=6.0, noise=_b(noise), new_cache=CrossCache, **kw)
+    _check(out["target_latents"], want, run16, g["out"])
+
+
 def test_base_nocfg_sde_and_cover(env):
     cfg, dit, vel32, vel16 = env
     g = golden("base_cover")
