@@ -10,9 +10,13 @@ Pinning status (see DESIGN.md "Oracle"):
     modules imported from /root/reference (tools/make_golden.py -> tests/golden/*.npz).
   * Oobleck VAE: the arithmetic lives in third-party `diffusers` (unpinned version, not installed
     in this image, source absent from /root/reference).  The restatement follows the in-tree MLX
-    re-implementation (acestep/models/mlx/vae_model.py, vae_convert.py) which cannot run here
-    (no mlx).  PARITY UNPINNED for the codec arithmetic; the tiling glue IS pinned against the
-    reference's own handler code driven with this oracle as the `vae` object.
+    re-implementation (acestep/models/mlx/vae_model.py, vae_convert.py).  PINNED against that
+    implementation, executed unmodified through a torch-backed stand-in for the mlx primitives
+    (tools/mlx_shim.py, tools/make_golden_vae_mlx.py -> tests/golden/vae_mlx_reference.npz);
+    `diffusers` itself remains unchecked.  The tiling glue is pinned against the reference's own
+    handler code driven with this oracle as the `vae` object.
+  * Output path (peak / dB normalisation), lyric-alignment attentions, SFT timesteps: PINNED
+    (tools/make_golden_output.py, make_golden_attn.py, make_golden_sft.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.

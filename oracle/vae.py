@@ -12,7 +12,13 @@ this restates its published structure as mirrored in-tree by the MLX backend:
 Tiling follows acestep/core/generation/handler/vae_decode_chunks.py:13-112 and
 vae_encode.py:15-82 / vae_encode_chunks.py:10-41.
 
-PARITY UNPINNED for the conv arithmetic (no runnable reference, no golden vectors in the tree).
+PINNED against the reference's in-tree implementation: tools/make_golden_vae_mlx.py executes the reference's own
+`MLXAutoEncoderOobleck` + `convert_vae_weights`, unmodified, through a torch-backed stand-in for the `mlx`
+primitives (tools/mlx_shim.py: conv1d / conv_transpose1d in NLC with MLX weight layouts, elementwise ops), and
+tests/test_oracle_golden.py requires this file to reproduce its decode, encoder moments and mean to 1e-4 (measured
+0.5-1.8e-5), including a config with odd strides.  What that pins: structure, paddings, strides, dilations, Snake,
+weight-norm fusion, weight axis conventions, mean / scale split.  What it does not: `diffusers` itself (absent), so
+a divergence between diffusers and the reference's own MLX mirror of it would go unseen.
 Weights use the diffusers state_dict key names (encoder.block.{i}.res_unit{j}.conv1.weight_g ...).
 """
 from __future__ import annotations

@@ -229,3 +229,26 @@ def test_sft_explicit_timesteps(dit):
                             audio_cover_strength=0.6, enc_non_cover=g["enc_nc"], ctx_non_cover=g["ctx_nc"],
                             new_cache=CrossCache)
     assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("tag,cfg", [
+    ("tiny", ovae.VaeConfig.tiny()),
+    ("odd", ovae.VaeConfig(encoder_hidden_size=32, downsampling_ratios=[2, 3, 5], channel_multiples=[1, 2, 4],
+                           decoder_channels=32, decoder_input_channels=16, audio_channels=2)),
+])
+def test_vae_arithmetic_matches_reference_mlx_implementation(tag, cfg):
+    """oracle.vae decode / encode vs the reference's OWN in-tree Oobleck implementation
+    (acestep/models/mlx/vae_model.py + vae_convert.py, unmodified, run through tools/mlx_shim.py by
+    tools/make_golden_vae_mlx.py): layer order, paddings (incl. ceil(s / 2) with odd strides, where every
+    transposed conv yields L*s - 1 samples), dilations, Snake, weight-norm fusion, ConvTranspose weight axes,
+    mean / scale split.  fp32 vs fp32 through 26+ layers with the fusion done in numpy there: 1e-4."""
+    g = golden("vae_mlx_reference")
+    sd = make_vae_weights(cfg, seed=int(g[f"{tag}_seed"]))
+    dec = ovae.decode(sd, cfg, g[f"{tag}_z"].transpose(1, 2))
+    want = g[f"{tag}_decoded"].transpose(1, 2)
+    assert dec.shape == want.shape and rel_l2(dec, want) < 1e-4
+    mean, scale = ovae.encode_moments(sd, cfg, g[f"{tag}_wav"].transpose(1, 2))
+    moments = g[f"{tag}_moments"].transpose(1, 2)
+    assert mean.shape[-1] == moments.shape[-1]
+    assert rel_l2(torch.cat([mean, scale], dim=1), moments) < 1e-4
+    assert rel_l2(mean, g[f"{tag}_mean"].transpose(1, 2)) < 1e-4
