@@ -112,7 +112,8 @@ __device__ __forceinline__ void tmem_st_32x32_u32(uint32_t taddr, const uint32_t
 // PT = true (NSW == 4 only): P_j is written back into tensor memory over the first 32 columns of the S buffer
 // it was computed from (64 bf16 keys = 32 packed words per row) and P.V reads its A operand from there: no
 // shared-memory store, no generic->async proxy fence, and the P.V MMAs read half as much shared memory.
-// The tensor pipe runs MMAs in issue order, so S_{j+2} (same buffer) cannot overtake PV_j.
+// Barrier rules of this variant (each one was a race found by tools/attn_stress.py): P_FULL is one mbarrier per S
+// buffer; every softmax warp waits for PV_{j-1} in every block; S_j waits for PV_{j-2} before overwriting P_{j-2}.
 template <int NSW, bool PT>
 __global__ void __launch_bounds__(128 + 32 * NSW, NSW == 4 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
