@@ -86,43 +86,60 @@ SIGNATURES = {
                                    C.POINTER(C.c_int)]),
     "ace_profile_gemm_shapes": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "ace_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+}
+# exported only by the probe build (libacestep_b200_probe.so, -DACE_PROBE): A/B hooks for tools/ and the
+# two-path equivalence tests; the release library has none of them
+PROBE_SIGNATURES = {
     "ace_debug_set_gemm_reference": (None, [C.c_int]),
     "ace_debug_set_vae_fused": (None, [C.c_int]),
     "ace_debug_set_attention_p_in_tmem": (None, [C.c_int]),
-    "ace_debug_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
-    "ace_debug_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
+PROBE_LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200_probe.so")
 
 _lib: Optional[C.CDLL] = None
+_probe: Optional[C.CDLL] = None
+
+
+def _open(path: str, signatures) -> C.CDLL:
+    if not os.path.exists(path):
+        raise B200Error(
+            f"{path} not found — build it with `python -m acestep_b200.build` "
+            "(the B200 backend has no CPU/PyTorch fallback)")
+    try:
+        lib = C.CDLL(path)
+    except OSError as exc:
+        raise B200Error(f"cannot load {path}: {exc}") from exc
+    for name, (res, args) in signatures.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise B200Error(f"{path} does not export {name}") from exc
+        fn.restype = res
+        fn.argtypes = args
+    return lib
 
 
 def load() -> C.CDLL:
     """Load the shared library (once) and declare every prototype.  Raises B200Error if absent."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise B200Error(
-            f"{LIB_PATH} not found — build it with `python -m acestep_b200.build` "
-            "(the B200 backend has no CPU/PyTorch fallback)")
-    try:
-        lib = C.CDLL(LIB_PATH)
-    except OSError as exc:
-        raise B200Error(f"cannot load {LIB_PATH}: {exc}") from exc
-    for name, (res, args) in SIGNATURES.items():
-        try:
-            fn = getattr(lib, name)
-        except AttributeError as exc:
-            raise B200Error(f"{LIB_PATH} does not export {name}") from exc
-        fn.restype = res
-        fn.argtypes = args
-    _lib = lib
-    return lib
+    if _lib is None:
+        _lib = _open(LIB_PATH, SIGNATURES)
+    return _lib
 
 
-def check(status: int, what: str = "") -> None:
+def load_probe() -> C.CDLL:
+    """The probe build (same ABI + the ace_debug_set_* hooks and ACE_* environment switches).  Tests and
+    tools only: engines take it through their `lib=` argument; nothing in the product path calls this."""
+    global _probe
+    if _probe is None:
+        _probe = _open(PROBE_LIB_PATH, {**SIGNATURES, **PROBE_SIGNATURES})
+    return _probe
+
+
+def check(status: int, what: str = "", lib: Optional[C.CDLL] = None) -> None:
     if status != 0:
-        msg = load().ace_last_error()
+        msg = (lib or load()).ace_last_error()
         raise B200Error(f"{what or 'libacestep_b200 call'} failed (status {status}): "
                         f"{msg.decode(errors='replace') if msg else '?'}")
 

@@ -16,6 +16,7 @@ generate_music.py:181-190).
 """
 from __future__ import annotations
 
+import inspect
 import types
 from typing import Any, Dict, Optional, Tuple
 
@@ -49,12 +50,16 @@ class B200BackendMixin:
         if dit:
             decoder = self.model.decoder
             shape = DiTShape.from_config(self.model.config)
-            if self.b200_dit is not None:
-                self.b200_dit.close()
-            # adapter-aware: active PEFT LoRA deltas are folded into the packed weights
-            self.b200_dit = B200DiT(effective_decoder_state(decoder), shape, device)
+            # adapter-aware: active PEFT LoRA / LoKr deltas are folded into the packed weights.  The new engine is
+            # built FIRST and swapped in only once it exists, so a failed repack (unsupported adapter, bad keys,
+            # out of memory) leaves the previous engine — and the sampler that points at it — intact.
+            new_dit = B200DiT(effective_decoder_state(decoder), shape, device)
+            old_dit, self.b200_dit = self.b200_dit, new_dit
             self.b200_sampler = B200Sampler(self.b200_dit, getattr(self.model, "null_condition_emb", None))
+            if old_dit is not None:
+                old_dit.close()
             self.use_b200_dit = True
+            self._b200_dit_wanted = True  # survives a temporary switch-off by the LoRA hooks (see _make_repacking)
             dit_status = "Active (B200 tcgen05)"
             if cond and getattr(self.model, "encoder", None) is not None:
                 # condition encoder: same layer kernels, weights from model.encoder
@@ -75,6 +80,19 @@ class B200BackendMixin:
     def _b200_is_turbo(self) -> bool:
         cfg = getattr(self, "config", None)
         return bool(getattr(cfg, "is_turbo", False))
+
+    def _b200_honours_timesteps(self) -> bool:
+        """The reference's own rule: turbo and sft `generate_audio` take a `timesteps` parameter
+        (turbo :1795, sft/modeling_acestep_v15_base.py:1866-1868); the plain base model's does not — the
+        keyword is swallowed by **kwargs and linspace(infer_steps) + shift is used
+        (base/modeling_acestep_v15_base.py:1812, :1862-1866).  Decided from the loaded model's signature."""
+        fn = getattr(getattr(self, "model", None), "generate_audio", None)
+        if fn is None:
+            return True
+        try:
+            return "timesteps" in inspect.signature(fn).parameters
+        except (TypeError, ValueError):
+            return True
 
     # ------------------------------------------------------------------ DiT
     def _b200_run_diffusion(
@@ -111,6 +129,8 @@ class B200BackendMixin:
             if not hasattr(self, required_attr) or getattr(self, required_attr) is None:
                 raise AttributeError(f"B200BackendMixin host is missing required attribute '{required_attr}'")
         s = self.b200_sampler
+        if timesteps is not None and not self._b200_honours_timesteps():
+            timesteps = None  # plain base model: ignored, exactly like its generate_audio(**kwargs)
         if self._b200_is_turbo():
             out = s.generate_turbo(
                 encoder_hidden_states, context_latents, src_latents, seed, infer_method=infer_method, shift=shift,
@@ -307,23 +327,29 @@ _ATTENTION_CALLERS = ("get_lyric_timestamp", "get_lyric_score")
 
 # Weight-mutation hooks.  Every LoRA lifecycle / control entry point of the handler
 # (handler/lora/lifecycle.py:164-440 add_lora / load_lora / add_voice_lora / remove_lora / unload_lora,
-# handler/lora/controls.py:35-150 set_use_lora / set_lora_scale) changes what model.decoder computes; a
-# backend that owns PACKED weights must repack or it silently keeps generating with the old ones.
+# handler/lora/controls.py:35-206 set_use_lora / set_lora_scale / set_active_lora_adapter — the last one calls
+# model.decoder.set_adapter(name), i.e. changes WHICH adapter the decoder applies) changes what model.decoder
+# computes; a backend that owns PACKED weights must repack or it silently keeps generating with the old ones.
 _LORA_MUTATORS = ("add_lora", "load_lora", "add_voice_lora", "remove_lora", "unload_lora", "set_use_lora",
-                  "set_lora_scale")
+                  "set_lora_scale", "set_active_lora_adapter")
 
 
 def _make_repacking(name):
     def wrapper(self, *args, **kwargs):
         status = getattr(self, "_ref_" + name)(*args, **kwargs)
-        if getattr(self, "use_b200_dit", False) and getattr(self, "model", None) is not None:
+        # repack whenever the backend was installed AND enabled, also while a previous failure has it switched
+        # off: unload_lora / remove_lora after an unsupported adapter must bring it back
+        wanted = getattr(self, "_b200_dit_wanted", False) or getattr(self, "use_b200_dit", False)
+        if wanted and getattr(self, "model", None) is not None:
             try:
                 self._init_b200_backends(dit=True, vae=False, cond=False)
-            except UnsupportedAdapterError as exc:
-                # not silent: the B200 DiT is switched off, the stock path takes over, and the status
-                # string the UI shows says so
+            except Exception as exc:  # noqa: BLE001 — the reference already mutated the model: never raise here
+                # not silent: the B200 DiT is switched off, the stock path takes over with the mutated PyTorch
+                # decoder, and the status string the UI shows says so
                 self.use_b200_dit = False
-                note = f" | ⚠️ B200 DiT disabled ({exc}); using the PyTorch decoder"
+                self._b200_dit_wanted = True
+                why = str(exc) if isinstance(exc, UnsupportedAdapterError) else f"{type(exc).__name__}: {exc}"
+                note = f" | ⚠️ B200 DiT disabled ({why}); using the PyTorch decoder"
                 status = status + note if isinstance(status, str) else status
         return status
 
@@ -337,7 +363,7 @@ _WRAPPED = {
     "tiled_decode": tiled_decode,
     "tiled_encode": tiled_encode,
 }
-_MIXIN_ATTRS = ("_init_b200_backends", "_b200_is_turbo", "_b200_run_diffusion", "_b200_prepare_condition",
+_MIXIN_ATTRS = ("_init_b200_backends", "_b200_is_turbo", "_b200_honours_timesteps", "_b200_run_diffusion", "_b200_prepare_condition",
                 "_b200_vae_decode", "_b200_vae_encode_sample")
 
 
@@ -373,6 +399,7 @@ def install(target):
         setattr(target, "_ref_" + name, bind(original))
         setattr(target, name, bind(_make_attention_caller(name)))
     for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("use_b200_cond", False), ("b200_dit", None),
+                      ("_b200_dit_wanted", False),
                       ("b200_sampler", None), ("b200_vae", None), ("b200_cond", None)):
         if not hasattr(target, flag):
             setattr(target, flag, val)

@@ -17,6 +17,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200.so")
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
+# probe build: same sources + -DACE_PROBE (A/B switches, scalar reference GEMM, alternative kernel variants,
+# ace_debug_set_* hooks) for tools/ and the two-path equivalence tests; never loaded by the product path
+PROBE_LIB_PATH = os.path.join(PKG_DIR, "libacestep_b200_probe.so")
+PROBE_OBJ_DIR = os.path.join(PKG_DIR, "_obj_probe")
 
 SOURCES = ["runtime.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dit.cu", "vae.cu", "cond.cu"]
 NVCC_FLAGS = [
@@ -45,21 +49,29 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link the shared library; returns its path."""
-    stamp = os.path.join(OBJ_DIR, "digest.txt")
+def build(force: bool = False, verbose: bool = False, probe: bool = True) -> str:
+    """Compile every .cu for sm_100a and link the release library (returns its path); with `probe` also the
+    probe library next to it."""
+    path = _build_one(LIB_PATH, OBJ_DIR, [], force, verbose)
+    if probe:
+        _build_one(PROBE_LIB_PATH, PROBE_OBJ_DIR, ["-DACE_PROBE"], force, verbose)
+    return path
+
+
+def _build_one(lib_path: str, obj_dir: str, defines, force: bool, verbose: bool) -> str:
+    stamp = os.path.join(obj_dir, "digest.txt")
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp):
         with open(stamp) as f:
             if f.read().strip() == digest:
-                return LIB_PATH
-    os.makedirs(OBJ_DIR, exist_ok=True)
+                return lib_path
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,13 +83,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(digest)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

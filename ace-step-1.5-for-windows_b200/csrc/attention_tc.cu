@@ -10,7 +10,7 @@
 //   warp 2      TMEM allocator (256 columns: S0 S1 O)
 //   warps 4-11  softmax, TWO threads per query row (each owns 32 of the block's 64 keys; the row
 //               maximum is combined through smem + a 64-thread named barrier — the single-warp-
-//               per-scheduler version was ALU-latency bound, profiles/r1_notes.md):
+//               per-scheduler version was ALU-latency bound in the round-1 ncu capture, profiles/r1_v3_ncu_full_summary.txt):
 //               tcgen05.ld S -> scale (+ band / tail mask only on boundary blocks) -> exp2 ->
 //               bf16 P written back to TENSOR MEMORY over the S columns it came from (tcgen05.st) and read
 //               by the PV MMA as its A operand (tcgen05.mma with A in TMEM): no shared-memory store, no
@@ -483,8 +483,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
 }  // namespace
 
+#ifdef ACE_PROBE
 static int g_attn_ptmem_override = -1;
 void set_attention_p_in_tmem(int mode) { g_attn_ptmem_override = mode < 0 ? -1 : (mode != 0); }
+#endif
 
 int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
   plan->p = p;
@@ -522,10 +524,11 @@ int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
   const int kvh = plan.heads / p.group;
   prof_begin(PROF_ATTN, 4.0 * p.Sq * keys * HD * plan.heads * plan.batch,
              2.0 * HD * plan.batch * ((double)p.Sq * plan.heads * 2 + (double)p.Skv * kvh * 2), stream);
-  // Default: the 4-softmax-warp CTA (two co-resident CTAs per SM overlap each other's softmax and
-  // MMA phases).  It measured faster than the 8-softmax-warp / 1-CTA-per-SM variant at both the
-  // 60 s (6.19 vs 6.42 ms per step) and 240 s (21.7 vs 22.7 ms) shapes; ACE_ATTN_NSW=8 selects the
-  // latter for experiments.
+  // The shipped variant: 4 softmax warps per CTA (two co-resident CTAs per SM overlap each other's softmax and
+  // MMA phases), P written back to tensor memory.  It measured faster than the 8-softmax-warp / 1-CTA-per-SM
+  // variant at both the 60 s (6.19 vs 6.42 ms per step) and 240 s (21.7 vs 22.7 ms) shapes.  Probe builds keep the
+  // alternatives selectable (ACE_ATTN_NSW=8, ACE_ATTN_PTMEM=0 / ace_debug_set_attention_p_in_tmem).
+#ifdef ACE_PROBE
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("ACE_ATTN_NSW");
@@ -534,13 +537,16 @@ int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream) {
   const int nsw = forced == 8 ? 8 : 4;
   static int ptmem_env = -1;
   if (ptmem_env < 0) {
-    const char* e = getenv("ACE_ATTN_PTMEM");  // default on; ACE_ATTN_PTMEM=0 keeps P in shared memory (A/B)
+    const char* e = getenv("ACE_ATTN_PTMEM");
     ptmem_env = (e && e[0] == '0') ? 0 : 1;
   }
   const int ptmem = g_attn_ptmem_override >= 0 ? g_attn_ptmem_override : ptmem_env;
   const int st = nsw == 8 ? launch_attention_tc_n<8, false>(plan, grid, stream)
                           : (ptmem ? launch_attention_tc_n<4, true>(plan, grid, stream)
                                    : launch_attention_tc_n<4, false>(plan, grid, stream));
+#else
+  const int st = launch_attention_tc_n<4, true>(plan, grid, stream);
+#endif
   prof_end(stream);
   return st;
 }

@@ -15,9 +15,22 @@
 #define ACE_HANG_GUARD 1  // bounded mbarrier waits: trap instead of hanging the GPU
 #endif
 
+// ACE_PROBE (tools/ and the probe library libacestep_b200_probe.so only): compiles in the A/B switches — the
+// ACE_* environment toggles, the scalar reference GEMM, the alternative kernel variants and the ace_debug_set_*
+// hooks.  The release library has none of them: one kernel per op, no environment reads, no dispatch.
+#ifdef ACE_PROBE
+#include <stdlib.h>
+#endif
+
 namespace ace {
 
 typedef __nv_bfloat16 bf16;
+
+#ifdef ACE_PROBE
+inline const char* probe_env(const char* name) { return getenv(name); }
+#else
+inline const char* probe_env(const char*) { return nullptr; }
+#endif
 
 // ----------------------------------------------------------------------------
 // host-side error plumbing (C ABI returns int status; message kept per thread)
@@ -75,7 +88,11 @@ int prof_stop(float* ms, double* flops, double* bytes, int* launches);
 void prof_tag_gemm(int m, int n, int k);  // shape of the next GEMM launch (profiling only)
 int prof_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms);
 
-bool pdl_enabled();  // programmatic dependent launch (ACE_NO_PDL=1 disables)
+#ifdef ACE_PROBE
+bool pdl_enabled();  // programmatic dependent launch (probe builds: ACE_NO_PDL=1 disables)
+#else
+constexpr bool pdl_enabled() { return true; }
+#endif
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------

@@ -157,7 +157,6 @@ int ace_enc_forward(AceEnc* e, const uint16_t* d_in, const int* d_kv_len, uint16
   ACE_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)d_in & 15) == 0, "unaligned buffer");
   ACE_REQUIRE(ws_bytes >= ace_enc_workspace_bytes(e, batch, seq), "encoder workspace too small: %zu < %zu", ws_bytes,
               ace_enc_workspace_bytes(e, batch, seq));
-  ACE_REQUIRE(!attention_use_legacy() || d_kv_len == nullptr, "the legacy attention kernel has no key-padding mask");
   cudaStream_t st = (cudaStream_t)stream;
   const int D = e->D, I = e->I, NQ = e->NQ, NKV = e->NKV, S = seq, M = batch * seq;
   const long QKVW = NQ + 2 * NKV;
@@ -194,9 +193,7 @@ int ace_enc_forward(AceEnc* e, const uint16_t* d_in, const int* d_kv_len, uint16
     ACE_PROPAGATE(launch_gemm(pq, EpiQKV{qkv, QKVW, NQ, NKV, w.qn, w.kn, rope_cos, rope_sin, S, eps}, st));
     AttnParams ap{qkv, qkv + NQ, qkv + NQ + NKV, attn, QKVW, QKVW, QKVW, (long)NQ, S, S, window, group, scale_log2,
                   d_kv_len};
-    if (attention_use_legacy()) {
-      ACE_PROPAGATE(launch_attention(ap, e->cfg.num_heads, batch, st));
-    } else {
+    {
       AttnPlan plan;
       ACE_PROPAGATE(make_attn_plan(&plan, ap, e->cfg.num_heads, batch));
       ACE_PROPAGATE(launch_attention_tc(plan, st));

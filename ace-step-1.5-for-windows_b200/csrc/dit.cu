@@ -129,12 +129,16 @@ int check_device() {
   return ACE_OK;
 }
 
-// Timing experiments only (results become garbage): ACE_SKIP=attn,norm,gemm drops a kernel class
+#ifdef ACE_PROBE
+// Probe builds, timing experiments only (results become garbage): ACE_SKIP=attn,norm,gemm drops a kernel class
 // from the step so its share of the REAL (graph + PDL) step time can be read off by difference.
 bool skip_class(const char* what) {
   const char* e = getenv("ACE_SKIP");
   return e != nullptr && strstr(e, what) != nullptr;
 }
+#else
+constexpr bool skip_class(const char*) { return false; }
+#endif
 #define LAUNCH_GEMM(...) do { if (!skip_gemm) ACE_PROPAGATE(launch_gemm(__VA_ARGS__)); } while (0)
 #define LAUNCH_NORM(...) do { if (!skip_norm) ACE_PROPAGATE(launch_adaln_rmsnorm(__VA_ARGS__)); } while (0)
 
@@ -167,14 +171,7 @@ int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs
     LAUNCH_NORM(d->h, w.self_norm, mod + 0 * D, mod + 1 * D, 6L * D, d->hn, M, D, S, eps, st);
     LAUNCH_GEMM(p.qkv, EpiQKV{d->qkv, QKVW, NQ, NKV, w.self_qn, w.self_kn, d->rope_cos,
                                             d->rope_sin, S, eps}, st);
-    AttnParams ap{d->qkv, d->qkv + NQ, d->qkv + NQ + NKV, d->attn, QKVW, QKVW, QKVW, (long)NQ, S, S,
-                  d->cfg.layer_is_sliding[l] ? d->cfg.sliding_window : -1, group, scale_log2};
-    if (skip_attn) {
-    } else if (attention_use_legacy()) {
-      ACE_PROPAGATE(launch_attention(ap, d->cfg.num_heads, Bc, st));
-    } else {
-      ACE_PROPAGATE(launch_attention_tc(p.self_attn, st));
-    }
+    if (!skip_attn) ACE_PROPAGATE(launch_attention_tc(p.self_attn, st));
     LAUNCH_GEMM(p.self_o, EpiGatedResid{d->h, (long)D, gate_msa, 6L * D, S}, st);
     // --- cross attention ---
     LAUNCH_NORM(d->h, w.cross_norm, nullptr, nullptr, 0, d->hn, M, D, S, eps, st);
@@ -187,14 +184,7 @@ int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs
                                        group, st));
       if (l == probs_layers - 1) return ACE_OK;
     }
-    AttnParams cp{d->qc, kv, kv + NKV, d->attn, (long)NQ, 2L * NKV, 2L * NKV, (long)NQ, S, E, -1, group,
-                  scale_log2};
-    if (skip_attn) {
-    } else if (attention_use_legacy()) {
-      ACE_PROPAGATE(launch_attention(cp, d->cfg.num_heads, Bc, st));
-    } else {
-      ACE_PROPAGATE(launch_attention_tc(p.cross_attn, st));
-    }
+    if (!skip_attn) ACE_PROPAGATE(launch_attention_tc(p.cross_attn, st));
     LAUNCH_GEMM(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S}, st);
     // --- MLP ---
     LAUNCH_NORM(d->h, w.mlp_norm, mod + 3 * D, mod + 4 * D, 6L * D, d->hn, M, D, S, eps, st);
@@ -219,8 +209,10 @@ int ace_init(int device) {
   return check_device();
 }
 
+#ifdef ACE_PROBE
 void ace_debug_set_gemm_reference(int on) { set_gemm_debug_reference(on != 0); }
 void ace_debug_set_attention_p_in_tmem(int mode) { set_attention_p_in_tmem(mode); }
+#endif
 
 uint64_t ace_launch_count(void) { return launch_count(); }
 void ace_profile_start(void) { prof_start(); }
@@ -270,7 +262,7 @@ int ace_dit_create(AceDit** out, const AceDitConfig* cfg, const uint16_t* weight
   d->NQ = cfg->num_heads * 128;
   d->NKV = cfg->num_kv_heads * 128;
   d->n_elems = n_elems;
-  const char* ng = getenv("ACE_NO_GRAPH");
+  const char* ng = probe_env("ACE_NO_GRAPH");  // probe builds only
   d->use_graph = !(ng && ng[0] == '1');
   if (cudaMalloc(&d->weights, n_elems * sizeof(bf16)) != cudaSuccess) {
     delete d;
@@ -442,8 +434,8 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
   // cp.async.bulk.prefetch.L2).  OFF by default: it paid off with the first, issue-bound main loops, but
   // A/B runs of the current kernels on one B200 have the step FASTER without it at every shape
   // (T=1500: 5.19 -> 4.98 ms, T=6000: 18.5 -> 18.2, T=250: 3.34 -> 3.27) — the prefetch traffic competes
-  // with the running GEMM's own operand stream.  ACE_PREFETCH=1 re-enables it for experiments.
-  if (getenv("ACE_PREFETCH") && getenv("ACE_PREFETCH")[0] == '1') {
+  // with the running GEMM's own operand stream.  Probe builds: ACE_PREFETCH=1 re-enables it for experiments.
+  if (probe_env("ACE_PREFETCH") && probe_env("ACE_PREFETCH")[0] == '1') {
     auto chain = [](GemmPlan& cur, const GemmPlan& next) {
       cur.shp.pf_ptr = reinterpret_cast<const uint8_t*>(next.b_ptr);
       cur.shp.pf_bytes = (unsigned long long)next.shp.N * next.b_ld * sizeof(bf16);
@@ -596,20 +588,13 @@ int ace_adg(const uint16_t* xt, const uint16_t* cond, const uint16_t* uncond, fl
                     (bf16*)out, b, t, (cudaStream_t)stream);
 }
 
-int ace_debug_linear(const uint16_t* a, const uint16_t* b, const uint16_t* bias, uint16_t* out, int m, int n,
-                     int k, void* stream) {
-  GemmPlan p;
-  ACE_PROPAGATE(make_gemm_plan(&p, (const bf16*)a, m, k, k, (const bf16*)b, n, k, m, 1, nullptr, 0));
-  return launch_gemm(p, EpiBias{(bf16*)out, (long)n, (const bf16*)bias}, (cudaStream_t)stream);
-}
-
-int ace_debug_attention(const uint16_t* q, const uint16_t* k, const uint16_t* v, uint16_t* o, int batch,
+int ace_attention(const uint16_t* q, const uint16_t* k, const uint16_t* v, uint16_t* o, int batch,
                         int heads, int kv_heads, int sq, int skv, int window, void* stream) {
   ACE_REQUIRE(kv_heads >= 1 && heads % kv_heads == 0, "bad head counts");
   AttnParams p{(const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, heads * 128L, kv_heads * 128L,
                kv_heads * 128L, heads * 128L, sq, skv, window, heads / kv_heads,
                (1.0f / sqrtf(128.0f)) * 1.4426950408889634f};
-  if (attention_use_legacy()) return launch_attention(p, heads, batch, (cudaStream_t)stream);
+  ACE_REQUIRE(q && k && v && o && batch >= 1 && sq >= 1 && skv >= 1, "ace_attention: bad argument");
   AttnPlan plan;
   ACE_PROPAGATE(make_attn_plan(&plan, p, heads, batch));
   return launch_attention_tc(plan, (cudaStream_t)stream);

@@ -8,7 +8,7 @@
 // Memory access pattern: tcgen05.ld hands each THREAD one accumulator ROW, so storing straight from
 // registers makes every 16-byte store of a warp hit 32 different 128-byte lines.  Measured on the
 // DiT's o_proj GEMM that made the epilogue LSU-bound at 6.4 us — 30 % of the kernel
-// (profiles/r1_notes.md).  The DiT epilogues therefore go through the warp's slab: the thread-per-row
+// (round-1 A/B measurement; the raw log was not kept — the kernel-level ncu rows of that build are in profiles/r1_v3_ncu_full_summary.txt).  The DiT epilogues therefore go through the warp's slab: the thread-per-row
 // side writes/reads 16-byte chunks XOR-swizzled by row (bank-conflict free), and the global side
 // moves the slab with 8 lanes per row (4 rows x 128 contiguous bytes per instruction).  The codec's
 // EpiConv stays thread-per-row (measured faster there, see its comment).
@@ -431,7 +431,7 @@ __device__ __forceinline__ float snake_f(float x, float a, float ib) {
 // convolution's "-padding" shift and its ragged ends are cropped.
 // Thread-per-row on purpose: the codec's rows are short (128..2048 channels) and its GEMMs have few
 // k-blocks, so the epilogue's latency is exposed; the staged/coalesced variant measured 11 % slower
-// on the whole decode (profiles/r1_notes.md), the 16-byte-per-thread stores merge in L2.
+// on the whole decode (round-1 A/B measurement; the raw log was not kept — the kernel-level ncu rows of that build are in profiles/r1_v3_ncu_full_summary.txt), the 16-byte-per-thread stores merge in L2.
 struct EpiConv {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out_main;        // may be null

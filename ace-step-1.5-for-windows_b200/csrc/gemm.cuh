@@ -106,9 +106,13 @@ int gemm_plan_enable_splitk(GemmPlan* plan, void* scratch, size_t scratch_bytes)
 
 // Debug switch (tests only): route launches through the scalar reference kernels below so the
 // epilogues and the surrounding pipeline can be validated independently of the tcgen05 main loop.
+#ifdef ACE_PROBE
 void set_gemm_debug_reference(bool on);
 bool gemm_debug_reference();
 float* gemm_debug_scratch(size_t elems);  // grows a device scratch buffer; nullptr on failure
+#else
+constexpr bool gemm_debug_reference() { return false; }
+#endif
 int num_sms();
 
 #ifdef __CUDACC__
@@ -397,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // A tile and rows [128r, 128r+128) of the B tile (half of N); the tensor core reads both halves of
 // B from the two CTAs' shared memories, so each CTA pulls 32 KB from L2 per 64-deep K block for
 // 2 x 128 x 256 x 64 FLOPs — twice the arithmetic intensity of the 128 x 128 single-CTA tile,
-// which measured L2-bandwidth-bound (profiles/r1_notes.md).  Accumulators: CTA r's TMEM holds its
+// which measured L2-bandwidth-bound (round-1 A/B measurement; the raw log was not kept — the kernel-level ncu rows of that build are in profiles/r1_v3_ncu_full_summary.txt).  Accumulators: CTA r's TMEM holds its
 // 128 rows x 256 columns, double-buffered (2 x 256 = all 512 TMEM columns).
 //   barriers: full[s]  (leader only, 2 arrivals: leader expect_tx + peer remote arrive; all four
 //                       TMA loads credit the leader's barrier)
@@ -610,6 +614,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (threadIdx.x == 64) ACE_STAMP(7);
 }
 
+#ifdef ACE_PROBE
 // ---------------------------------------------------------------------------------------------
 // Scalar reference path (tests / bring-up only; selected with ace_debug_set_gemm_reference).
 // ---------------------------------------------------------------------------------------------
@@ -630,8 +635,11 @@ gemm_ref_epilogue_kernel(const float* __restrict__ scratch, int ld, GemmShape sh
   epi.template run<BN>(acc, row, n0, shp.M, shp.N, stg);
 }
 
+#endif  // ACE_PROBE
+
 template <int BN, int STAGES, class Epi>
 int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
+#ifdef ACE_PROBE
   if (gemm_debug_reference()) {
     const int m_pad = ceil_div(p.shp.M, GEMM_BM) * GEMM_BM;
     const int n_pad = ceil_div(p.shp.N, BN) * BN;
@@ -650,6 +658,7 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
     ACE_CUDA_CHECK(cudaGetLastError());
     return ACE_OK;
   }
+#endif
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -18,8 +18,6 @@ struct AttnParams {
   const int* kv_len;        // device [batch] or null: keys >= kv_len[b] are padding and masked (the
                             // padding-aware create_4d_mask of the condition encoders, turbo :53-132)
 };
-// legacy mma.sync kernel (attention.cu) — kept for A/B measurements (ACE_ATTN=legacy)
-int launch_attention(const AttnParams& p, int heads, int batch, cudaStream_t stream);
 // softmax(q k^T / sqrt(128)) with the eager path's bf16 roundings -> out [batch][heads][S][E] (bf16); q rows
 // [batch*S] at pitch ldq (head h at column 128 h), k rows [batch*E] at pitch ldk (kv head h / group)
 int launch_cross_probs(const bf16* q, long ldq, const bf16* k, long ldk, bf16* out, int heads, int batch, int S,
@@ -33,9 +31,10 @@ struct AttnPlan {
 };
 int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch);
 int launch_attention_tc(const AttnPlan& plan, cudaStream_t stream);
-bool attention_use_legacy();
-// tests: 1 = P through tensor memory (default), 0 = P through shared memory, -1 = environment default
+#ifdef ACE_PROBE
+// probe builds: 1 = P through tensor memory (default), 0 = P through shared memory, -1 = environment default
 void set_attention_p_in_tmem(int mode);
+#endif
 
 // x[b, t, :] = [ctx[b, t, 0:128] | xt[b, t, 0:64]] for t < T, zeros for T <= t < Tpad
 int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int T, int Tpad,

@@ -162,7 +162,7 @@ static EncodeTiledFn get_encode_fn() {
 static CUtensorMapL2promotion tmap_l2_promotion() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("ACE_TMAP_L2");
+    const char* e = probe_env("ACE_TMAP_L2");
     v = e ? atoi(e) : 256;
   }
   return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
@@ -231,7 +231,7 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
     // directions (halves L2 operand traffic per FLOP); ACE_GEMM_BN=128|256 overrides for experiments
     static int forced = -1;
     if (forced < 0) {
-      const char* e = getenv("ACE_GEMM_BN");
+      const char* e = probe_env("ACE_GEMM_BN");
       forced = e ? atoi(e) : 0;
     }
     bn = forced ? forced : ((n >= 256 && m > 128) ? 256 : 128);
@@ -240,7 +240,7 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
     // waves of CTA pairs x tile width (the main loop time of one pair tile is proportional to bn).
     static int forced = -1;
     if (forced < 0) {
-      const char* e = getenv("ACE_GEMM_BN");
+      const char* e = probe_env("ACE_GEMM_BN");
       forced = e ? atoi(e) : 0;
     }
     if (forced) {
@@ -281,7 +281,7 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
 int gemm_plan_enable_splitk(GemmPlan* plan, void* scratch, size_t scratch_bytes) {
   static int disabled = -1;
   if (disabled < 0) {
-    const char* e = getenv("ACE_NO_SPLITK");
+    const char* e = probe_env("ACE_NO_SPLITK");
     disabled = (e && e[0] == '1') ? 1 : 0;
   }
   const GemmShape& sh = plan->shp;
@@ -318,6 +318,7 @@ int gemm_plan_enable_splitk(GemmPlan* plan, void* scratch, size_t scratch_bytes)
   return ACE_OK;
 }
 
+#ifdef ACE_PROBE
 static bool g_debug_ref = false;
 void set_gemm_debug_reference(bool on) { g_debug_ref = on; }
 bool gemm_debug_reference() { return g_debug_ref; }
@@ -360,17 +361,12 @@ __global__ void gemm_ref_kernel(const bf16* __restrict__ A, long lda, int a_rows
   out[(size_t)m * ld_out + n] = acc;
 }
 
+#endif  // ACE_PROBE
+
 }  // namespace ace
 
+#ifdef ACE_PROBE
 namespace ace {
-bool attention_use_legacy() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ACE_ATTN");
-    v = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
-  }
-  return v == 1;
-}
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -380,3 +376,4 @@ bool pdl_enabled() {
   return v == 1;
 }
 }  // namespace ace
+#endif

@@ -314,6 +314,7 @@ int conv_gemm(const bf16* a, long a_rows, int kc, long a_ld, const ConvW& w, int
 // Residual unit on x [L, C] (and its Snake'd copy xs): returns new x / xs in the `o*` buffers.
 //   h  = conv7_d(snake1(x))            A = xs           epilogue: snake2 -> hs
 //   x' = x + conv1(snake2(h))          A = hs           epilogue: + x, also snake_next(x') -> oxs
+#ifdef ACE_PROBE
 int g_fused_override = -1;  // ace_debug_set_vae_fused: -1 = environment default, 0 / 1 = forced
 bool fused_res_unit_enabled() {
   if (g_fused_override >= 0) return g_fused_override != 0;
@@ -324,6 +325,9 @@ bool fused_res_unit_enabled() {
   }
   return on != 0;
 }
+#else
+constexpr bool fused_res_unit_enabled() { return true; }
+#endif
 
 int res_unit(const ResUnitW& r, int dil, long L, int C, const bf16* x, const bf16* xs, bf16* hs, bf16* ox,
              bf16* oxs, const SnakeW& next, cudaStream_t st) {
@@ -371,7 +375,9 @@ size_t enc_max_elems(const AceVae* v, long samples) {
 
 extern "C" {
 
+#ifdef ACE_PROBE
 void ace_debug_set_vae_fused(int on) { g_fused_override = on < 0 ? -1 : (on != 0); }
+#endif
 
 size_t ace_vae_packed_bytes(const AceVaeConfig* cfg) {
   if (!cfg || cfg->num_stages < 1 || cfg->num_stages > 8) return 0;

@@ -48,14 +48,15 @@ class DiTShape:
 class B200DiT:
     """tcgen05 DiT decoder.  All tensors are bf16 CUDA; results stay on the device."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], shape: DiTShape, device="cuda:0", prefix: str = ""):
-        self.lib = _lib.load()
+    def __init__(self, state_dict: Dict[str, torch.Tensor], shape: DiTShape, device="cuda:0", prefix: str = "",
+                 lib=None):
+        self.lib = lib or _lib.load()  # `lib`: tests / tools hand in the probe build (_lib.load_probe())
         self.device = torch.device(device)
         self.shape = shape
         if self.device.type != "cuda":
             raise _lib.B200Error("B200DiT needs a CUDA device (there is no CPU path)")
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.ace_init(self.device.index or 0), "ace_init")
+            _lib.check(self.lib.ace_init(self.device.index or 0), "ace_init", self.lib)
             cfg = _lib.AceDitConfig()
             cfg.hidden_size, cfg.intermediate_size = shape.hidden_size, shape.intermediate_size
             cfg.num_layers, cfg.num_heads = shape.num_hidden_layers, shape.num_attention_heads
@@ -70,8 +71,7 @@ class B200DiT:
             if blob.numel() != expect:
                 raise _lib.B200Error(f"packed DiT blob has {blob.numel()} elements, library expects {expect}")
             handle = C.c_void_p()
-            _lib.check(self.lib.ace_dit_create(C.byref(handle), C.byref(cfg), blob.data_ptr(), blob.numel()),
-                       "ace_dit_create")
+            _lib.check(self.lib.ace_dit_create(C.byref(handle), C.byref(cfg), blob.data_ptr(), blob.numel()), "ace_dit_create", self.lib)
             self.handle = handle
         self.bound = None  # (bc, T, E)
         self._ws = None
@@ -98,7 +98,7 @@ class B200DiT:
                 raise _lib.B200Error(f"invalid DiT shape bc={bc} T={T} E={E}")
             torch.cuda.synchronize(self.device)
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            _lib.check(self.lib.ace_dit_bind(self.handle, bc, T, E, self._ws.data_ptr(), need), "ace_dit_bind")
+            _lib.check(self.lib.ace_dit_bind(self.handle, bc, T, E, self._ws.data_ptr(), need), "ace_dit_bind", self.lib)
         self.bound = (bc, T, E)
 
     def io_views(self):
@@ -109,7 +109,7 @@ class B200DiT:
             raise _lib.B200Error("io_views: handle not bound")
         bc, T, _ = self.bound
         px, pc, pv = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _lib.check(self.lib.ace_dit_io_slots(self.handle, C.byref(px), C.byref(pc), C.byref(pv)), "ace_dit_io_slots")
+        _lib.check(self.lib.ace_dit_io_slots(self.handle, C.byref(px), C.byref(pc), C.byref(pv)), "ace_dit_io_slots", self.lib)
         base = self._ws.data_ptr()
 
         def view(ptr, ch):
@@ -128,8 +128,7 @@ class B200DiT:
             raise _lib.B200Error(f"set_condition: enc {tuple(enc.shape)} does not match bound shape {self.bound}")
         enc = enc.to(device=self.device, dtype=torch.bfloat16).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.ace_dit_set_condition(self.handle, enc.data_ptr(), _lib.stream_handle(self.device)),
-                       "ace_dit_set_condition")
+            _lib.check(self.lib.ace_dit_set_condition(self.handle, enc.data_ptr(), _lib.stream_handle(self.device)), "ace_dit_set_condition", self.lib)
         self._enc_keepalive = enc
 
     def step(self, xt: torch.Tensor, ctx: torch.Tensor, t: Sequence[float], out: Optional[torch.Tensor] = None):
@@ -144,7 +143,7 @@ class B200DiT:
         tv = (C.c_float * bc)(*[float(x) for x in t])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ace_dit_step(self.handle, xt.data_ptr(), ctx.data_ptr(), tv, out.data_ptr(),
-                                             _lib.stream_handle(self.device)), "ace_dit_step")
+                                             _lib.stream_handle(self.device)), "ace_dit_step", self.lib)
         return out
 
     def cross_attentions(self, xt: torch.Tensor, ctx: torch.Tensor, t: Sequence[float], n_layers: int) -> torch.Tensor:
@@ -164,6 +163,5 @@ class B200DiT:
         tv = (C.c_float * bc)(*[float(x) for x in t])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ace_dit_cross_attentions(self.handle, xt.data_ptr(), ctx.data_ptr(), tv, n_layers,
-                                                         probs.data_ptr(), _lib.stream_handle(self.device)),
-                       "ace_dit_cross_attentions")
+                                                         probs.data_ptr(), _lib.stream_handle(self.device)), "ace_dit_cross_attentions", self.lib)
         return probs

@@ -40,14 +40,18 @@ class B200Pipeline:
         return x.to(self.device, torch.bfloat16, non_blocking=True)
 
     def generate(self, encoder_hidden_states, context_latents, src_latents=None, seed=None, *,
-                 noise=None, to_host: bool = True, decode: bool = True, latent_shift: float = 0.0,
+                 noise=None, to_host: bool = True, reuse_host_buffer: bool = False, decode: bool = True,
+                 latent_shift: float = 0.0,
                  latent_rescale: float = 1.0, normalization_db: Optional[float] = None,
                  **sampler_kwargs) -> Dict[str, Any]:
         """Returns {"audio": fp32 [B,2,N] (peak-normalised like the reference when |x|max > 1),
         "target_latents": bf16 [B,T,64], "peak": fp32 [B] raw peaks, "time_costs": {...}}.
         `normalization_db` (e.g. -1.0, GenerationParams.normalization_db) also applies the front-end's
         `normalize_audio` per song (inference.py:674-679) inside the same device pass, so the host copy that
-        comes back is the final audio and the reference's three host passes over it are not needed."""
+        comes back is the final audio and the reference's three host passes over it are not needed.
+        With `to_host` the waveform comes back in a pinned host tensor owned by the caller (a fresh one per call);
+        `reuse_host_buffer=True` returns the pipeline's single reusable pinned buffer instead — valid only until
+        the next call (serving loops / the benchmark, which consume each result before asking for the next)."""
         t0 = time.time()
         enc, ctx = self._dev(encoder_hidden_states), self._dev(context_latents)
         src = self._dev(src_latents) if src_latents is not None else ctx[..., :64].contiguous()
@@ -66,11 +70,15 @@ class B200Pipeline:
             # per-sample peak normalisation (generate_music_decode.py:191-195), in place, no host decision
             res["peak"] = peak_normalize_(wav, normalization_db=normalization_db)
             if to_host:
-                if self._pinned_wav is None or self._pinned_wav.shape != wav.shape:
-                    self._pinned_wav = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
-                self._pinned_wav.copy_(wav, non_blocking=True)
+                if not reuse_host_buffer:
+                    host = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
+                else:
+                    if self._pinned_wav is None or self._pinned_wav.shape != wav.shape:
+                        self._pinned_wav = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
+                    host = self._pinned_wav
+                host.copy_(wav, non_blocking=True)
                 torch.cuda.synchronize(self.device)
-                wav = self._pinned_wav
+                wav = host
             else:
                 torch.cuda.synchronize(self.device)
             res["audio"] = wav
@@ -81,7 +89,7 @@ class B200Pipeline:
     # ------------------------------------------------------------------
     def repaint(self, encoder_hidden_states, src_audio, repaint_start_frame: int, repaint_end_frame: int,
                 silence_latent, seed=None, *, posterior_eps=None, noise=None, to_host: bool = True,
-                **sampler_kwargs) -> Dict[str, Any]:
+                reuse_host_buffer: bool = False, **sampler_kwargs) -> Dict[str, Any]:
         """Repaint / edit (BASELINE config 5): reference audio -> VAE encode -> DiT loop -> VAE decode.
 
         Mirrors the slice of the reference between `_encode_audio_to_latents` (handler/batch_prep.py:63-76)
@@ -115,7 +123,8 @@ class B200Pipeline:
         mask = torch.zeros(B, T, 64, device=self.device, dtype=torch.bfloat16)
         mask[:, s0:s1] = 1.0
         ctx = torch.cat([src, mask], dim=-1)
-        out = self.generate(encoder_hidden_states, ctx, src, seed, noise=noise, to_host=to_host, **sampler_kwargs)
+        out = self.generate(encoder_hidden_states, ctx, src, seed, noise=noise, to_host=to_host,
+                            reuse_host_buffer=reuse_host_buffer, **sampler_kwargs)
         out["src_latents"] = target
         out["time_costs"]["vae_encode_time_cost"] = t_enc
         out["time_costs"]["total_time_cost"] = time.time() - t0

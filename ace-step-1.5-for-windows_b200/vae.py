@@ -48,14 +48,14 @@ class B200Vae:
     MAX_FRAMES_PER_PASS = 8192  # ~5.5 min; longer inputs are tiled with HALO_FRAMES of overlap
     HALO_FRAMES = 16
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], shape: VaeShape, device="cuda:0"):
-        self.lib = _lib.load()
+    def __init__(self, state_dict: Dict[str, torch.Tensor], shape: VaeShape, device="cuda:0", lib=None):
+        self.lib = lib or _lib.load()  # `lib`: tests / tools hand in the probe build (_lib.load_probe())
         self.device = torch.device(device)
         self.shape = shape
         if self.device.type != "cuda":
             raise _lib.B200Error("B200Vae needs a CUDA device (there is no CPU path)")
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.ace_init(self.device.index or 0), "ace_init")
+            _lib.check(self.lib.ace_init(self.device.index or 0), "ace_init", self.lib)
             cfg = _lib.AceVaeConfig()
             cfg.num_stages = len(shape.downsampling_ratios)
             for i, (r, m) in enumerate(zip(shape.downsampling_ratios, shape.channel_multiples)):
@@ -68,8 +68,7 @@ class B200Vae:
             if blob.numel() != expect:
                 raise _lib.B200Error(f"packed VAE blob has {blob.numel()} bytes, library expects {expect}")
             handle = C.c_void_p()
-            _lib.check(self.lib.ace_vae_create(C.byref(handle), C.byref(cfg), blob.data_ptr(), blob.numel()),
-                       "ace_vae_create")
+            _lib.check(self.lib.ace_vae_create(C.byref(handle), C.byref(cfg), blob.data_ptr(), blob.numel()), "ace_vae_create", self.lib)
             self.handle = handle
         self._ws: Optional[torch.Tensor] = None
 
@@ -100,7 +99,7 @@ class B200Vae:
             need = self.lib.ace_vae_decode_workspace_bytes(self.handle, T)
             ws = self._workspace(need)
             _lib.check(self.lib.ace_vae_decode(self.handle, z.data_ptr(), T, wav.data_ptr(), ws.data_ptr(),
-                                               ws.numel(), _lib.stream_handle(self.device)), "ace_vae_decode")
+                                               ws.numel(), _lib.stream_handle(self.device)), "ace_vae_decode", self.lib)
         return wav
 
     def decode(self, latents: torch.Tensor) -> torch.Tensor:
@@ -147,8 +146,7 @@ class B200Vae:
             need = self.lib.ace_vae_encode_workspace_bytes(self.handle, N)
             ws = self._workspace(need)
             _lib.check(self.lib.ace_vae_encode(self.handle, wav.data_ptr(), N, _lib.ptr(eps_tc), z.data_ptr(),
-                                               ws.data_ptr(), ws.numel(), _lib.stream_handle(self.device)),
-                       "ace_vae_encode")
+                                               ws.data_ptr(), ws.numel(), _lib.stream_handle(self.device)), "ace_vae_encode", self.lib)
         return z
 
     def encode(self, audio: torch.Tensor, sample: bool = True, generator: Optional[torch.Generator] = None):

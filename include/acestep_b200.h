@@ -222,8 +222,21 @@ int ace_profile_stop(float* ms, double* flops, double* bytes, int* launches);
 int ace_profile_gemm_shapes(int max_out, int* m, int* n, int* k, int* launches, float* ms);
 
 /* ------------------------------------------------------------------------------------------ */
-/* Test / bring-up hooks (never used by the product path)                                       */
+/* Single-op entry points (kernel-level parity tests and callers that need one op)              */
 /* ------------------------------------------------------------------------------------------ */
+/* softmax(q k^T / sqrt(128) [|i - j| <= window]) v on token-major bf16 buffers through the tcgen05 attention
+ * kernel: q [batch*sq, heads*128], k / v [batch*skv, kv_heads*128], o [batch*sq, heads*128]; window < 0 = full.
+ * (What AceStepAttention.forward hands to SDPA, modeling_acestep_v15_turbo.py:348-364.)  `ace_linear` above is the
+ * matching single nn.Linear. */
+int ace_attention(const uint16_t* d_q, const uint16_t* d_k, const uint16_t* d_v, uint16_t* d_o,
+                  int batch, int heads, int kv_heads, int sq, int skv, int window, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Probe hooks: exported ONLY by libacestep_b200_probe.so (built with -DACE_PROBE for tools/ and  */
+/* the two-path equivalence tests).  The release library has no A/B switch, no environment read, */
+/* no alternative kernel.                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+#ifdef ACE_PROBE
 /* 1: route every GEMM through the scalar reference kernels (validates epilogues independently). */
 void ace_debug_set_gemm_reference(int on);
 /* Codec residual units of the 128-channel stages: 1 = single fused kernel (csrc/resunit.cuh),
@@ -233,12 +246,7 @@ void ace_debug_set_vae_fused(int on);
 /* Attention: 1 = P goes back to tensor memory and P.V reads its A operand from there (default), 0 = P through
  * shared memory, -1 = default.  The stress test compares the two on long KV loops. */
 void ace_debug_set_attention_p_in_tmem(int mode);
-/* D = A[m,k] * B[n,k]^T + bias, bf16 in/out, through the tcgen05 path (tests/bench). */
-int ace_debug_linear(const uint16_t* d_a, const uint16_t* d_b, const uint16_t* d_bias, uint16_t* d_out,
-                     int m, int n, int k, void* stream);
-/* softmax(q k^T * scale [band]) v on token-major buffers (tests). */
-int ace_debug_attention(const uint16_t* d_q, const uint16_t* d_k, const uint16_t* d_v, uint16_t* d_o,
-                        int batch, int heads, int kv_heads, int sq, int skv, int window, void* stream);
+#endif
 
 #ifdef __cplusplus
 }

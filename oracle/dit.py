@@ -59,14 +59,15 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     return w * (xf * torch.rsqrt(var + eps)).to(x.dtype)
 
 
-def rope_tables(cfg: DiTConfig, seq_len: int, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Qwen3RotaryEmbedding (default rope): returns cos, sin of shape [S, head_dim]."""
+def rope_tables(cfg: DiTConfig, seq_len: int, dtype=torch.float32, device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Qwen3RotaryEmbedding (default rope): returns cos, sin of shape [S, head_dim].  The tables are always
+    built on the CPU (identical values whatever device the oracle runs on) and then moved."""
     d = cfg.head_dim
     inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
     pos = torch.arange(seq_len, dtype=torch.float32)
     freqs = pos[:, None] * inv_freq[None, :]
     emb = torch.cat([freqs, freqs], dim=-1)
-    return emb.cos().to(dtype), emb.sin().to(dtype)
+    return emb.cos().to(dtype).to(device), emb.sin().to(dtype).to(device)
 
 
 def _rotate_half(x: torch.Tensor) -> torch.Tensor:
@@ -79,12 +80,18 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return x * cos[None, None] + _rotate_half(x) * sin[None, None]
 
 
-def band_mask(seq_len: int, window: int, dtype=torch.float32) -> torch.Tensor:
+def band_mask(seq_len: int, window: int, dtype=torch.float32, device="cpu") -> torch.Tensor:
     """create_4d_mask(..., is_sliding_window=True, is_causal=False) (:92-132): |i-j| <= window."""
-    idx = torch.arange(seq_len)
+    idx = torch.arange(seq_len, device=device)
     keep = (idx[:, None] - idx[None, :]).abs() <= window
-    m = torch.full((seq_len, seq_len), torch.finfo(dtype).min, dtype=dtype)
+    m = torch.full((seq_len, seq_len), torch.finfo(dtype).min, dtype=dtype, device=device)
     return m.masked_fill(keep, 0.0)[None, None]
+
+
+# "eager" (matmul + fp32 softmax, eager_attention_forward :349-368) or "sdpa" (ALL_ATTENTION_FUNCTIONS["sdpa"]:
+# repeat_kv + F.scaled_dot_product_attention with the dense additive mask — what the reference's GPU path runs,
+# handler/init_service_loader.py:45-71).  bench.py's torch-gpu baseline arm switches this to "sdpa".
+ATTN_IMPL = "eager"
 
 
 def attention(q, k, v, mask, n_rep: int, scaling: float, probs_out: Optional[list] = None) -> torch.Tensor:
@@ -93,6 +100,8 @@ def attention(q, k, v, mask, n_rep: int, scaling: float, probs_out: Optional[lis
     if n_rep > 1:
         k = k.repeat_interleave(n_rep, dim=1)
         v = v.repeat_interleave(n_rep, dim=1)
+    if ATTN_IMPL == "sdpa" and probs_out is None:
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=scaling)
     s = torch.matmul(q, k.transpose(-1, -2)) * scaling
     if mask is not None:
         s = s + mask
@@ -109,7 +118,7 @@ def timestep_sinusoid(t: torch.Tensor, dim: int = 256, scale: float = 1000.0, ma
     reproduces that quirk of the reference's bf16 execution while the rest stays fp32."""
     t = (t.to(torch.bfloat16) * scale).float() if bf16_time else t * scale
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -203,8 +212,8 @@ def dit_forward(w: Dict[str, torch.Tensor], cfg: DiTConfig, xt: torch.Tensor, t:
     S = h.shape[1]
     enc_e = F.linear(enc, w["condition_embedder.weight"], w["condition_embedder.bias"])
 
-    cos, sin = rope_tables(cfg, S, h.dtype)
-    masks = {"full_attention": None, "sliding_attention": band_mask(S, cfg.sliding_window, h.dtype)}
+    cos, sin = rope_tables(cfg, S, h.dtype, h.device)
+    masks = {"full_attention": None, "sliding_attention": band_mask(S, cfg.sliding_window, h.dtype, h.device)}
     for i in range(cfg.num_hidden_layers):
         if cache is not None and i in cache.kv:
             kv = cache.kv[i]

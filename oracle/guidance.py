@@ -42,7 +42,7 @@ def apg(pred_cond: torch.Tensor, pred_uncond: torch.Tensor, guidance_scale: floa
 def adg(latents, pred_cond, pred_uncond, sigma, guidance_scale: float, angle_clip: float = 3.14 / 6):
     """adg_forward (:107-180), apply_norm=False, apply_clip=True.  `sigma` is the scalar t_curr."""
     n, t, c = pred_cond.shape
-    sigma = torch.as_tensor(sigma, dtype=latents.dtype).view(1, 1, 1).expand(n, 1, 1)
+    sigma = torch.as_tensor(sigma, dtype=latents.dtype).to(latents.device).view(1, 1, 1).expand(n, 1, 1)
     weight = guidance_scale - 1
     weight = weight * (weight > 0) + 1e-3
     x_text = latents - sigma * pred_cond

@@ -87,14 +87,14 @@ def sample_turbo(velocity: Callable, enc, ctx, src_latents, seed, *, shift=3.0, 
         sched = sched[sched.index(nearest):]
     else:
         xt = noise
-    t_sched = torch.tensor(sched, dtype=dtype)
+    t_sched = torch.tensor(sched, dtype=dtype)  # host scalars (.item()) like the reference
     n = len(sched)
     cover_steps = int(n * audio_cover_strength)
     cache = new_cache()
     switched = False
     for i in range(n):
         t_cur = t_sched[i].item()
-        t_vec = t_cur * torch.ones((bsz,), dtype=dtype)
+        t_vec = t_cur * torch.ones((bsz,), dtype=dtype, device=ctx.device)
         if i >= cover_steps and not switched:
             switched = True
             enc, ctx = enc_non_cover, ctx_non_cover
@@ -110,7 +110,7 @@ def sample_turbo(velocity: Callable, enc, ctx, src_latents, seed, *, shift=3.0, 
             xt = t_next * eps + (1 - t_next) * x0
         else:
             dt = t_cur - t_next
-            xt = xt - vt * (dt * torch.ones((bsz,), dtype=dtype))[:, None, None]
+            xt = xt - vt * (dt * torch.ones((bsz,), dtype=dtype, device=xt.device))[:, None, None]
     return xt
 
 
@@ -167,7 +167,7 @@ def sample_base(velocity: Callable, enc, ctx, src_latents, seed, *, null_emb, in
             enc, ctx = enc_non_cover, ctx_non_cover
             cache = new_cache()
         x = torch.cat([xt, xt], dim=0) if do_cfg else xt
-        t_vec = t_cur * torch.ones((x.shape[0],), dtype=dtype)
+        t_vec = t_cur * torch.ones((x.shape[0],), dtype=dtype, device=x.device)
         vt = velocity(x, t_vec, ctx, enc, cache)
         in_interval = bool(t_cur >= cfg_interval_start and t_cur <= cfg_interval_end)
         if do_cfg:
@@ -178,12 +178,12 @@ def sample_base(velocity: Callable, enc, ctx, src_latents, seed, *, null_emb, in
             else:
                 vt = pc
         if infer_method == "sde":
-            tb = t_cur * torch.ones((bsz,), dtype=dtype)
+            tb = t_cur * torch.ones((bsz,), dtype=dtype, device=xt.device)
             x0 = xt - vt * tb[:, None, None]
             nxt = 1.0 - float(i + 1) / infer_steps  # NOTE: ignores `shift` (base :1972)
             eps = sde_noise[i] if sde_noise is not None else torch.randn_like(x0)
             xt = nxt * eps + (1 - nxt) * x0
         else:
             dt = t_cur - t_prev
-            xt = xt - vt * (dt * torch.ones((bsz,), dtype=dtype))[:, None, None]
+            xt = xt - vt * (dt * torch.ones((bsz,), dtype=dtype, device=xt.device))[:, None, None]
     return xt

@@ -24,19 +24,39 @@ def lib():
     return _lib.load()
 
 
-def _header_functions():
+def _header_functions(probe_section: bool):
+    """Function names the header declares outside (False) / inside (True) its `#ifdef ACE_PROBE` block."""
     src = open(os.path.join(ROOT, "include", "acestep_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ace_[a-z0-9_]+)\s*\(", src)))
+    m = re.search(r"#ifdef ACE_PROBE(.*?)#endif", src, flags=re.S)
+    assert m, "header has no ACE_PROBE section"
+    part = m.group(1) if probe_section else src.replace(m.group(0), "")
+    return sorted(set(re.findall(r"\b(ace_[a-z0-9_]+)\s*\(", part)))
 
 
 def test_library_exports_every_declared_symbol(lib):
-    names = _header_functions()
+    names = _header_functions(False)
     assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), f"libacestep_b200.so does not export {n}"
     # and the ctypes binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == names
+
+
+def test_release_library_has_no_debug_switches(lib):
+    """Release hygiene: the A/B hooks and every ACE_* environment switch exist only in the probe build
+    (libacestep_b200_probe.so, -DACE_PROBE); the release library exports none and never reads the environment."""
+    probe_names = _header_functions(True)
+    assert sorted(_lib.PROBE_SIGNATURES) == probe_names and len(probe_names) == 3
+    for n in probe_names:
+        assert not hasattr(lib, n), f"release library exports the probe hook {n}"
+    blob = open(LIB_PATH, "rb").read()
+    for needle in (b"ACE_SKIP", b"ACE_ATTN", b"ACE_GEMM_BN", b"ACE_NO_GRAPH", b"ACE_NO_PDL", b"ACE_PREFETCH",
+                   b"ACE_VAE_FUSED", b"ACE_NO_SPLITK", b"ACE_TMAP_L2", b"gemm_ref_kernel", b"getenv"):
+        assert needle not in blob, f"release library still contains {needle!r}"
+    probe = _lib.load_probe()
+    for n in probe_names + _header_functions(False):
+        assert hasattr(probe, n), f"probe library does not export {n}"
 
 
 def test_abi_version_and_error_string(lib):

@@ -237,6 +237,61 @@ def test_lora_mutators_trigger_a_repack():
     assert "B200 DiT disabled" in msg and h.use_b200_dit is False  # loud, not silent
 
 
+def test_adapter_switch_repacks_and_unload_reenables_after_a_failed_repack(monkeypatch):
+    """(a) `set_active_lora_adapter` (handler/lora/controls.py:193-206 -> decoder.set_adapter) changes which LoRA
+    the decoder applies, so it must repack like the other mutators; (b) a repack that fails for ANY reason never
+    raises out of the reference's method (the model is already mutated), switches the backend off loudly, keeps
+    the previous engine alive until a new one exists, and the next successful mutation (unload_lora) brings the
+    backend back."""
+    import acestep_b200.backend as backend
+
+    class LoraHost(FakeHandler):
+        def load_lora(self, path):
+            return "✅ loaded"
+
+        def unload_lora(self):
+            return "✅ unloaded"
+
+        def set_active_lora_adapter(self, name):
+            self.ref_calls.append(("active", name))
+            return f"✅ active {name}"
+
+    built, closed = [], []
+
+    class FakeDit:
+        def __init__(self, state, shape, device):
+            if state == "boom":
+                raise KeyError("layers.0.self_attn.q_proj.conv.weight")
+            built.append(self)
+
+        def close(self):
+            closed.append(self)
+
+    h = install(LoraHost())
+    h.model.decoder = object()
+    h.model.config = object()
+    state = {"v": "ok"}
+    monkeypatch.setattr(backend, "B200DiT", FakeDit)
+    monkeypatch.setattr(backend, "B200Sampler", lambda dit, null=None: ("sampler", dit))
+    monkeypatch.setattr(backend, "effective_decoder_state", lambda dec: state["v"])
+    monkeypatch.setattr(backend.DiTShape, "from_config", classmethod(lambda cls, cfg: "shape"))
+    h._init_b200_backends(dit=True, vae=False, cond=False)
+    first = h.b200_dit
+    assert h.use_b200_dit and built == [first] and closed == []
+    # (a) two adapters loaded, switch the active one: a repack, the old engine closed only after the new one exists
+    assert h.set_active_lora_adapter("voice") == "✅ active voice"
+    assert len(built) == 2 and closed == [first] and h.b200_dit is built[1] and h.b200_sampler == ("sampler", built[1])
+    # (b) a repack that dies on an unexpected key: no exception, backend off, previous engine NOT destroyed
+    state["v"] = "boom"
+    msg = h.load_lora("conv-adapter")
+    assert "B200 DiT disabled" in msg and "KeyError" in msg
+    assert h.use_b200_dit is False and h.b200_dit is built[1] and closed == [first]
+    # unload restores a plain decoder: the backend comes back although use_b200_dit was False
+    state["v"] = "ok"
+    assert h.unload_lora() == "✅ unloaded"
+    assert h.use_b200_dit is True and len(built) == 3 and h.b200_dit is built[2] and closed == [first, built[1]]
+
+
 def test_turbo_models_use_the_turbo_sampler():
     h = install(FakeHandler())
     h.config.is_turbo = True
@@ -244,6 +299,28 @@ def test_turbo_models_use_the_turbo_sampler():
     h._execute_service_generate_diffusion(_payload(), {"timesteps": torch.tensor([1.0, 0.5, 0.0])}, 7, "ode", 3.0, 1.0)
     kind, *_, skw = h.b200_sampler.calls[0]
     assert kind == "turbo" and skw["timesteps"] is not None and len(h.model.calls) == 1
+
+
+def test_plain_base_model_ignores_timesteps_like_the_reference():
+    """base/modeling_acestep_v15_base.py:1812 swallows `timesteps` in **kwargs (only sft and turbo declare it):
+    the backend decides from the loaded model's generate_audio signature."""
+    enc, ctx, src = torch.zeros(1, 2, 8), torch.zeros(1, 4, 128), torch.zeros(1, 4, 64)
+
+    class BaseModel(FakeModel):
+        def generate_audio(self, infer_steps=30, **kwargs):
+            return {}
+
+    class SftModel(FakeModel):
+        def generate_audio(self, infer_steps=30, timesteps=None, **kwargs):
+            return {}
+
+    for model, expect in ((BaseModel(), None), (SftModel(), [1.0, 0.5, 0.0])):
+        h = install(FakeHandler())
+        h.model = model
+        h.b200_sampler, h.use_b200_dit = StubSampler(), True
+        h._b200_run_diffusion(enc, None, ctx, src, 0, timesteps=[1.0, 0.5, 0.0])
+        kind, *_, skw = h.b200_sampler.calls[0]
+        assert kind == "base" and skw["timesteps"] == expect
 
 
 def test_missing_sampler_raises_attribute_error_like_mlx_sibling():

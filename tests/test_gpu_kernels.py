@@ -37,10 +37,30 @@ DEV = torch.device("cuda:0")
 
 @pytest.fixture(scope="module")
 def lib():
+    """The RELEASE library: one kernel per op, no switches."""
     l = _lib.load()
     _lib.check(l.ace_init(0))
     yield l
+
+
+@pytest.fixture(scope="module")
+def probe():
+    """The probe build (-DACE_PROBE): same sources plus the A/B hooks (scalar reference GEMM, two-launch codec
+    residual unit, P-through-shared-memory attention) that the two-path equivalence tests flip."""
+    l = _lib.load_probe()
+    _lib.check(l.ace_init(0), lib=l)
+    yield l
     l.ace_debug_set_gemm_reference(0)
+    l.ace_debug_set_vae_fused(-1)
+    l.ace_debug_set_attention_p_in_tmem(-1)
+
+
+def _pick(lib, probe, ref):
+    """ref = 1: the scalar reference GEMM behind the same epilogues (probe build); ref = 0: the release library."""
+    if ref:
+        probe.ace_debug_set_gemm_reference(1)
+        return probe
+    return lib
 
 
 def _stream():
@@ -49,7 +69,7 @@ def _stream():
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (300, 256, 128), (1500, 2048, 2048), (77, 384, 6144)])
 @pytest.mark.parametrize("ref", [1, 0])
-def test_linear(lib, m, n, k, ref):
+def test_linear(lib, probe, m, n, k, ref):
     g = torch.Generator().manual_seed(m + n + k)
     a = torch.randn(m, k, generator=g).to(torch.bfloat16)
     b = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16)
@@ -57,13 +77,13 @@ def test_linear(lib, m, n, k, ref):
     want = a.double() @ b.double().T + bias.double()
     ad, bd, biasd = a.to(DEV), b.to(DEV), bias.to(DEV)
     out = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
-    lib.ace_debug_set_gemm_reference(ref)
+    use = _pick(lib, probe, ref)
     try:
-        _lib.check(lib.ace_debug_linear(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), out.data_ptr(), m, n, k,
-                                        _stream()))
+        _lib.check(use.ace_linear(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), out.data_ptr(), m, n, k,
+                                  _stream()), lib=use)
         torch.cuda.synchronize()
     finally:
-        lib.ace_debug_set_gemm_reference(0)
+        probe.ace_debug_set_gemm_reference(0)
     got = out.cpu().double()
     assert torch.isfinite(got).all()
     assert max_abs(got, want) <= 2 ** -7 * float(want.abs().max()) + 1e-3
@@ -95,7 +115,7 @@ def test_attention(lib, B, H, HK, Sq, Skv, win):
     want = _attn_ref(q, k, v, H, HK, win)
     qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
     out = torch.full((B, Sq, H * 128), float("nan"), dtype=torch.bfloat16, device=DEV)
-    _lib.check(lib.ace_debug_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), B, H, HK, Sq,
+    _lib.check(lib.ace_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), B, H, HK, Sq,
                                        Skv, win, _stream()))
     torch.cuda.synchronize()
     got = out.cpu().double()
@@ -111,22 +131,22 @@ def _tiny_dit():
 
 
 @pytest.mark.parametrize("ref", [1, 0])
-def test_dit_forward_tiny_vs_oracle(lib, ref):
+def test_dit_forward_tiny_vs_oracle(lib, probe, ref):
     cfg, w = _tiny_dit()
     g = golden("dit_forward_tiny")
     xt, ctx, enc = (g[k].to(torch.bfloat16) for k in ("xt", "ctx", "enc"))
     t = g["t"].to(torch.bfloat16)
     want = dit_forward(w, cfg, xt.float(), t.float(), ctx.float(), enc.float(), bf16_time=True)
-    lib.ace_debug_set_gemm_reference(ref)
+    use = _pick(lib, probe, ref)
     try:
-        dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+        dit = B200DiT(w, DiTShape.from_config(cfg), DEV, lib=use)
         dit.bind(xt.shape[0], xt.shape[1], enc.shape[1])
         dit.set_condition(enc.to(DEV))
         vt = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())
         vt2 = dit.step(xt.to(DEV), ctx.to(DEV), t.float().tolist())  # second call: CUDA-graph replay
         torch.cuda.synchronize()
     finally:
-        lib.ace_debug_set_gemm_reference(0)
+        probe.ace_debug_set_gemm_reference(0)
     assert torch.isfinite(vt.float()).all()
     assert rel_l2(vt.cpu().float(), want) <= 2e-2
     assert max_abs(vt2, vt) == 0.0
@@ -168,19 +188,19 @@ def _tiny_vae():
 
 
 @pytest.mark.parametrize("ref", [1, 0])
-def test_vae_decode_tiny(lib, ref):
+def test_vae_decode_tiny(lib, probe, ref):
     cfg, sd, shape = _tiny_vae()
     wf = folded_vae_state(sd)
     g = torch.Generator().manual_seed(40)
     z = torch.randn(2, 64, 75, generator=g).to(torch.bfloat16)
     want = ovae.decode(wf, cfg, z.float())
-    lib.ace_debug_set_gemm_reference(ref)
+    use = _pick(lib, probe, ref)
     try:
-        vae = B200Vae(sd, shape, DEV)
+        vae = B200Vae(sd, shape, DEV, lib=use)
         got = vae.decode(z.to(DEV))
         torch.cuda.synchronize()
     finally:
-        lib.ace_debug_set_gemm_reference(0)
+        probe.ace_debug_set_gemm_reference(0)
     assert got.shape == want.shape and got.dtype == torch.float32
     wb = {k: v.to(torch.bfloat16) for k, v in wf.items()}
     floor = _bf16_floor(lambda: want, lambda: ovae.decode(wb, cfg, z))
@@ -188,7 +208,7 @@ def test_vae_decode_tiny(lib, ref):
 
 
 @pytest.mark.parametrize("ref", [1, 0])
-def test_vae_encode_tiny(lib, ref):
+def test_vae_encode_tiny(lib, probe, ref):
     cfg, sd, shape = _tiny_vae()
     wf = folded_vae_state(sd)
     g = torch.Generator().manual_seed(41)
@@ -197,14 +217,14 @@ def test_vae_encode_tiny(lib, ref):
     mean, scale = ovae.encode_moments(wf, cfg, audio.to(torch.bfloat16).float())
     want_mean = mean[0].T
     want = (mean + (torch.nn.functional.softplus(scale) + 1e-4) * eps.float().T[None])[0].T
-    lib.ace_debug_set_gemm_reference(ref)
+    use = _pick(lib, probe, ref)
     try:
-        vae = B200Vae(sd, shape, DEV)
+        vae = B200Vae(sd, shape, DEV, lib=use)
         got_mean = vae.encode_samples(audio[0].to(DEV), None)
         got = vae.encode_samples(audio[0].to(DEV), eps.to(DEV))
         torch.cuda.synchronize()
     finally:
-        lib.ace_debug_set_gemm_reference(0)
+        probe.ace_debug_set_gemm_reference(0)
     wb = {k: v.to(torch.bfloat16) for k, v in wf.items()}
     floor = _bf16_floor(lambda: mean, lambda: ovae.encode_moments(wb, cfg, audio.to(torch.bfloat16))[0])
     tol = max(1.1 * floor, 2e-2)
@@ -213,28 +233,32 @@ def test_vae_encode_tiny(lib, ref):
 
 
 @pytest.mark.parametrize("frames", [5, 75, 301, 13000])
-def test_fused_res_unit_matches_two_launch_path(lib, frames):
+def test_fused_res_unit_matches_two_launch_path(lib, probe, frames):
     """csrc/resunit.cuh (one kernel per residual unit at the 128-channel stages) rounds at the same
-    points as the two-launch tap-shifted GEMM path, so decode and encode must agree bit for bit."""
+    points as the two-launch tap-shifted GEMM path, so decode and encode must agree bit for bit — the RELEASE
+    library's fused kernels against the probe build's two-launch path (and the probe build's own fused path)."""
     cfg, sd, shape = _tiny_vae()
     g = torch.Generator().manual_seed(50 + frames)
     z = torch.randn(1, 64, frames, generator=g).to(torch.bfloat16)
     audio = torch.rand(2, cfg.hop * frames, generator=g) - 0.5
     eps = torch.randn(frames, 64, generator=g).to(torch.bfloat16)
-    vae = B200Vae(sd, shape, DEV)
     out = {}
     try:
-        for mode in (0, 1):
-            lib.ace_debug_set_vae_fused(mode)
+        for mode in (0, 1, 2):  # 0: probe two-launch, 1: probe fused, 2: release
+            if mode < 2:
+                probe.ace_debug_set_vae_fused(mode)
+            vae = B200Vae(sd, shape, DEV, lib=probe if mode < 2 else lib)
             dec = vae.decode(z.to(DEV))
             enc = vae.encode_samples(audio.to(DEV), eps.to(DEV))
             torch.cuda.synchronize()
             out[mode] = (dec.cpu(), enc.cpu())
+            vae.close()
     finally:
-        lib.ace_debug_set_vae_fused(-1)
-    assert torch.isfinite(out[1][0]).all()
-    assert torch.equal(out[0][0], out[1][0]), max_abs(out[0][0], out[1][0])
-    assert torch.equal(out[0][1], out[1][1]), max_abs(out[0][1].float(), out[1][1].float())
+        probe.ace_debug_set_vae_fused(-1)
+    assert torch.isfinite(out[2][0]).all()
+    for mode in (1, 2):
+        assert torch.equal(out[0][0], out[mode][0]), (mode, max_abs(out[0][0], out[mode][0]))
+        assert torch.equal(out[0][1], out[mode][1]), (mode, max_abs(out[0][1].float(), out[mode][1].float()))
 
 
 def _cond_inputs(cfg, B, Ll, Lt, Lr, lyric_lens, text_lens, order, seed):
@@ -393,7 +417,7 @@ def test_vae_full_size_short_clip(lib):
     vae.close()
 
 
-def test_attention_p_in_tmem_stress(lib):
+def test_attention_p_in_tmem_stress(lib, probe):
     """P through tensor memory (default) against P through shared memory on long KV loops, many launches, both
     co-resident CTAs busy: the two paths round identically, so outputs must be bit-identical and finite.  (A
     missing PV_{j-2} -> S_j ordering passed every small test and produced NaNs only after ~10^3 launches.)"""
@@ -404,14 +428,16 @@ def test_attention_p_in_tmem_stress(lib):
     v = torch.randn(B, S, HK * 128, generator=g).to(torch.bfloat16).to(DEV)
     outs = {}
     try:
-        for mode in (0, 1):
-            lib.ace_debug_set_attention_p_in_tmem(mode)
+        for mode in (0, 1):  # 0: probe build, P through shared memory; 1: the release library (P in tensor memory)
+            use = lib if mode == 1 else probe
+            if mode == 0:
+                probe.ace_debug_set_attention_p_in_tmem(0)
             o = torch.empty(B, S, H * 128, dtype=torch.bfloat16, device=DEV)
             ref = None
             for it in range(150 if mode == 1 else 2):
                 for win in (-1, 128):
-                    _lib.check(lib.ace_debug_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK,
-                                                       S, S, win, _stream()))
+                    _lib.check(use.ace_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK,
+                                                 S, S, win, _stream()), lib=use)
                     if win == -1:
                         cur = o.clone()
                         if ref is None:
@@ -421,7 +447,7 @@ def test_attention_p_in_tmem_stress(lib):
             torch.cuda.synchronize()
             outs[mode] = ref
     finally:
-        lib.ace_debug_set_attention_p_in_tmem(-1)
+        probe.ace_debug_set_attention_p_in_tmem(-1)
     assert torch.isfinite(outs[1].float()).all()
     assert torch.equal(outs[0], outs[1]), max_abs(outs[0].float(), outs[1].float())
 

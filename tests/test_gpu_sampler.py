@@ -113,8 +113,6 @@ def test_base_cfg_matches_reference(env, name, kw):
     _check(out["target_latents"], want, run16, g["out"])
 
 
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: not yet run on a B200; "
-                                        "XPASS at round end = promote to a plain test next round")
 def test_sft_explicit_timesteps_matches_reference(env):
     """SFT variant: explicit `timesteps` replace the linspace/shift schedule and infer_steps
     (sft/modeling_acestep_v15_base.py:1864-1875); golden from the real sft module (tools/make_golden_sft.py)."""

@@ -9,7 +9,7 @@ import torch
 
 from acestep_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_probe()
 dev = torch.device("cuda:0")
 _lib.check(lib.ace_init(0))
 st = torch.cuda.current_stream().cuda_stream
@@ -29,7 +29,7 @@ for mode in (0, 1):
     ref, changed = None, 0
     for it in range(300):
         for win in (-1, 128):
-            _lib.check(lib.ace_debug_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK, S, S, win, st))
+            _lib.check(lib.ace_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, HK, S, S, win, st))
             if win == -1:
                 cur = o.clone()
                 if ref is None:

@@ -12,8 +12,8 @@ timeout 300 python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c
 timeout 200 python bench.py --workload c1 --no-cpu-baseline > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err
 timeout 300 python bench.py --workload c5 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
 if [ -n "$AB" ]; then
-ACE_ATTN_PTMEM=0 timeout 200 python bench.py --workload c2 --no-cpu-baseline > gpurun_out/bench_c2_pt0.json 2>&1
-ACE_ATTN_PTMEM=0 timeout 300 python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_pt0.json 2>&1
+ACE_B200_LIB=$PWD/ace-step-1.5-for-windows_b200/libacestep_b200_probe.so ACE_ATTN_PTMEM=0 timeout 200 python bench.py --workload c2 --no-cpu-baseline > gpurun_out/bench_c2_pt0.json 2>&1
+ACE_B200_LIB=$PWD/ace-step-1.5-for-windows_b200/libacestep_b200_probe.so ACE_ATTN_PTMEM=0 timeout 300 python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_pt0.json 2>&1
 fi
 timeout 120 python tools/profile_output.py > gpurun_out/output_path_timing.log 2>&1; cat gpurun_out/output_path_timing.log
 timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \

@@ -4,7 +4,7 @@ cudaProfilerStart/Stop, for `ncu --profile-from-start off` (see profiles/README.
 import os
 import sys
 
-os.environ.setdefault("ACE_NO_GRAPH", "1")
+# (ncu profiles the kernel nodes of a CUDA-graph launch individually: the release library is profiled as shipped)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 

@@ -4,7 +4,11 @@ times with ACE_SKIP=attn|norm|gemm to read each kernel class's share off by diff
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+if any(k.startswith("ACE_") and k != "ACE_B200_LIB" for k in os.environ):
+    # the A/B switches only exist in the probe build (-DACE_PROBE); the release library ignores the environment
+    os.environ.setdefault("ACE_B200_LIB", os.path.join(ROOT, "ace-step-1.5-for-windows_b200", "libacestep_b200_probe.so"))
 import torch
 
 from acestep_b200.dit import B200DiT, DiTShape
