@@ -26,6 +26,9 @@ SOURCES = ["runtime.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "d
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    # function-local statics of templates would otherwise be STB_GNU_UNIQUE: ONE copy per process even across
+    # RTLD_LOCAL libraries, i.e. shared between the release and the probe library when a test loads both
+    "-Xcompiler", "-fno-gnu-unique", "-Xcompiler", "-fvisibility=hidden",
 ]
 
 

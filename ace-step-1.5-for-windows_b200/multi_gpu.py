@@ -8,6 +8,13 @@ i % world with replicated weights and the result is independent of placement.
 
 Works with any initialised torch.distributed backend: NCCL over NVLink on the B200 box,
 gloo in the CPU tests.
+
+Two gather modes:
+  * ragged (default): lengths are all-gathered first (one tiny collective + a host read), then one padded
+    gather.  Needed when ranks cannot know each other's durations.
+  * `lengths=` given (every rank knows every song's sample count — it is `duration * 48000`, request
+    metadata): no length exchange, no host synchronisation; with `async_op=True` the gather is only ENQUEUED
+    (on NCCL's stream) and a `PendingGather` is returned, so rank r's next song overlaps the transfer.
 """
 from __future__ import annotations
 
@@ -22,12 +29,37 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+class PendingGather:
+    """A waveform gather in flight.  `wait()` -> songs in global order on `dst`, None elsewhere."""
+
+    def __init__(self, work, out, lens, n_items: int, world: int, is_dst: bool, keepalive):
+        self._work, self._out, self._lens = work, out, lens
+        self._n, self._world, self._is_dst = n_items, world, is_dst
+        self._keepalive = keepalive  # the send buffer must outlive the collective
+
+    def wait(self) -> Optional[List[torch.Tensor]]:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        self._keepalive = None
+        if not self._is_dst:
+            return None
+        songs: List[Optional[torch.Tensor]] = [None] * self._n
+        for r in range(self._world):
+            for j, i in enumerate(shard_indices(self._n, r, self._world)):
+                songs[i] = self._out[r][j, :, : int(self._lens[i])]
+        return songs  # type: ignore[return-value]
+
+
 def gather_waveforms(local: Sequence[torch.Tensor], n_items: int, dst: int = 0, group=None,
-                     device: Optional[torch.device] = None) -> Optional[List[torch.Tensor]]:
+                     device: Optional[torch.device] = None, lengths: Optional[Sequence[int]] = None,
+                     async_op: bool = False):
     """Gather per-song waveforms ([C, N_i], ragged N_i allowed) produced under `shard_indices`
     onto rank `dst`, returned in global song order (None on other ranks).
 
-    Collectives: one all_gather of the lengths (a few bytes) + one gather of the padded waveforms.
+    Collectives: (ragged mode) one all_gather of the lengths + one gather of the padded waveforms;
+    (`lengths` given: global per-song sample counts) the one gather only.  `async_op=True` returns a
+    PendingGather instead of waiting.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -38,29 +70,40 @@ def gather_waveforms(local: Sequence[torch.Tensor], n_items: int, dst: int = 0, 
         device = local[0].device if len(local) else torch.device("cpu")
     chans = local[0].shape[0] if len(local) else 2
     dtype = local[0].dtype if len(local) else torch.float32
-    lens = torch.zeros(per_rank, dtype=torch.int64, device=device)
-    for j, w in enumerate(local):
-        lens[j] = w.shape[-1]
-    all_lens = [torch.zeros_like(lens) for _ in range(world)]
-    dist.all_gather(all_lens, lens, group=group)
-    max_len = int(torch.stack(all_lens).max().item())
-    buf = torch.zeros(per_rank, chans, max_len, dtype=dtype, device=device)
-    for j, w in enumerate(local):
-        buf[j, :, : w.shape[-1]] = w
-    out = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, out, dst=dst, group=group)
-    if rank != dst:
-        return None
-    songs: List[Optional[torch.Tensor]] = [None] * n_items
-    for r in range(world):
-        for j, i in enumerate(shard_indices(n_items, r, world)):
-            songs[i] = out[r][j, :, : int(all_lens[r][j])]
-    return songs  # type: ignore[return-value]
+    if lengths is None:
+        lens = torch.zeros(per_rank, dtype=torch.int64, device=device)
+        for j, w in enumerate(local):
+            lens[j] = w.shape[-1]
+        all_lens = [torch.zeros_like(lens) for _ in range(world)]
+        dist.all_gather(all_lens, lens, group=group)
+        table = torch.stack(all_lens).cpu()  # the one host read of the ragged mode
+        glob = [0] * n_items
+        for r in range(world):
+            for j, i in enumerate(shard_indices(n_items, r, world)):
+                glob[i] = int(table[r][j])
+    else:
+        glob = [int(x) for x in lengths]
+        assert len(glob) == n_items, f"lengths has {len(glob)} entries for {n_items} songs"
+        for j, i in enumerate(mine):
+            assert local[j].shape[-1] == glob[i], f"song {i}: {local[j].shape[-1]} samples, lengths says {glob[i]}"
+    max_len = max(glob) if glob else 0
+    if per_rank == 1 and len(local) == 1 and local[0].shape[-1] == max_len and local[0].is_contiguous():
+        buf = local[0].unsqueeze(0)  # the common case (one equal-length song per rank): no staging copy
+    else:
+        buf = torch.zeros(per_rank, chans, max_len, dtype=dtype, device=device)
+        for j, w in enumerate(local):
+            buf[j, :, : w.shape[-1]] = w
+    out = [torch.empty(per_rank, chans, max_len, dtype=dtype, device=device) for _ in range(world)] if rank == dst else None
+    work = dist.gather(buf, out, dst=dst, group=group, async_op=True)
+    pending = PendingGather(work, out, glob, n_items, world, rank == dst, buf)
+    return pending if async_op else pending.wait()
 
 
 def generate_sharded(generate_one: Callable[[int], torch.Tensor], n_items: int, dst: int = 0, group=None,
-                     device: Optional[torch.device] = None) -> Optional[List[torch.Tensor]]:
-    """Run `generate_one(i) -> waveform [C, N]` for this rank's songs, then gather on `dst`."""
+                     device: Optional[torch.device] = None, lengths: Optional[Sequence[int]] = None,
+                     async_op: bool = False):
+    """Run `generate_one(i) -> waveform [C, N]` for this rank's songs, then gather on `dst`
+    (see gather_waveforms for `lengths` / `async_op`)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = [generate_one(i) for i in shard_indices(n_items, rank, world)]
-    return gather_waveforms(local, n_items, dst=dst, group=group, device=device)
+    return gather_waveforms(local, n_items, dst=dst, group=group, device=device, lengths=lengths, async_op=async_op)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the ACE-Step hot path on B200 (contract: see DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|torch-gpu] [--workload c1|c2|c3|c5]
 
 A "step" is one pass of the hot path over one batch of synthetic input: ONE SONG per GPU —
 denoising loop (base sampler, CFG + APG) on synthetic text-conditioning embeddings + VAE decode to
@@ -15,7 +15,14 @@ Metric: generated-audio seconds per wall second (whole job, all GPUs).
   roofline : tcgen05 GEMM launches of one song, event-timed per launch inside this run
              (ace_profile_start/stop), algorithmic FLOPs / summed duration vs the measured bf16 peak.
   cpu_baseline / --impl reference : the oracle port of the reference's PyTorch CPU path on this
-             box's host cores, on a bounded sample of the same workload (stated in `sample`).
+             box's host cores, on a bounded sample of the same workload (stated in `sample`; the full C2 song
+             is ~85 s of CPU time, so K + W songs would not fit the few-minute budget).
+  gpu_baseline / --impl torch-gpu : the reference's own GPU path restated (oracle modules, bf16, SDPA + cuBLAS /
+             cuDNN, tiled decode) on the same B200, same workload, no extrapolation.
+  extra_workloads : c3 (240 s / 60 steps — north_star's target), c5 (repaint 120 s), c1 (10 s turbo) measured in
+             the same run (value, e2e, DiT step alone vs both measured peaks).
+  dit_step_tensor_util : the DiT step alone (song minus event-timed codec passes, / steps) vs the sustained and
+             the burst bf16 peak of MEASURED_PEAKS.json, plus the whole-song figure.
 Weights are random-init of the reference architecture, data synthetic (no checkpoints / network).
 """
 from __future__ import annotations
@@ -145,6 +152,9 @@ def cpu_sample(wl, threads=None):
     from oracle.dit import CrossCache, DiTConfig, dit_forward
     from oracle.weights import make_dit_weights, make_vae_weights
 
+    import oracle.dit as odit
+
+    odit.ATTN_IMPL = "sdpa"  # the reference's default attention implementation (handler/init_service_loader.py:43)
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = DiTConfig()
@@ -211,6 +221,184 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------
+def torch_gpu_arm(wl, dev, dshape, vshape, dit_state, vae_state, cond, null_emb):
+    """The reference's GPU path restated: the oracle modules (same arithmetic as the reference's PyTorch modules,
+    pinned by tests/test_oracle_golden.py) in bf16 on the cuda device with SDPA attention + cuBLAS / cuDNN — what
+    `initialize_service(device="cuda")` runs (handler/init_service_loader.py:45-71: bf16, attn_implementation="sdpa";
+    dense additive masks, per-step Python loop, overlap-discard tiled decode with chunk 512 / overlap 64).
+    Returns song(seed) -> fp32 waveform on the device.  Baseline only: nothing of the product path runs here."""
+    import torch
+
+    import oracle.dit as odit
+    from acestep_b200.pack import folded_vae_state
+    from oracle import sampler as osamp
+    from oracle import vae as ovae
+
+    odit.ATTN_IMPL = "sdpa"
+    cfg = odit.DiTConfig(hidden_size=dshape.hidden_size, intermediate_size=dshape.intermediate_size,
+                         num_hidden_layers=dshape.num_hidden_layers, num_attention_heads=dshape.num_attention_heads,
+                         num_key_value_heads=dshape.num_key_value_heads, sliding_window=dshape.sliding_window)
+    vcfg = ovae.VaeConfig()
+    wb = {k: v.to(dev, torch.bfloat16) for k, v in dit_state.items()}
+    vb = {k: v.to(dev, torch.bfloat16) for k, v in folded_vae_state(vae_state).items()}
+    vel = lambda xt, t, c, e, cache: odit.dit_forward(wb, cfg, xt, t, c, e, cache)
+    enc, ctx, src = cond["enc"], cond["ctx"], cond["src"]
+
+    def song(seed):
+        with torch.no_grad():
+            noise = osamp.prepare_noise((1, wl["T"], 64), [seed], torch.bfloat16, dev)
+            if wl["turbo"]:
+                lat = osamp.sample_turbo(vel, enc, ctx, src, None, shift=wl["shift"], noise=noise,
+                                         new_cache=odit.CrossCache)
+            else:
+                lat = osamp.sample_base(vel, enc, ctx, src, None, null_emb=null_emb, infer_steps=wl["steps"],
+                                        guidance_scale=wl["guidance"], shift=wl["shift"], noise=noise,
+                                        new_cache=odit.CrossCache)
+            wav = ovae.tiled_decode(lambda z: ovae.decode(vb, vcfg, z), lat.transpose(1, 2).contiguous(), 512, 64).float()
+            peak = wav.abs().amax(dim=[1, 2], keepdim=True)
+            return torch.where(peak > 1.0, wav / peak, wav)
+
+    return song
+
+
+def time_torch_gpu(wl, dev, dshape, vshape, dit_state, vae_state, cond, null_emb, songs=2, warmup=1):
+    import torch
+
+    song = torch_gpu_arm(wl, dev, dshape, vshape, dit_state, vae_state, cond, null_emb)
+    for i in range(warmup):
+        song(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(songs):
+        out = song(100 + i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / songs
+    finite = bool(torch.isfinite(out).all())
+    del song, out
+    torch.cuda.empty_cache()
+    return {"value": wl["seconds"] / (ms * 1e-3), "unit": "audio-s/s", "ms_per_song": ms, "songs": songs,
+            "kind": "oracle modules (= the reference's PyTorch modules restated), bf16, cuda, SDPA + cuBLAS/cuDNN, "
+                    "dense masks, tiled decode 512/64; same workload, same box, same run",
+            "outputs_finite": finite}
+
+
+def run_torch_gpu(args, wl):
+    """--impl torch-gpu: the reference's GPU path (see torch_gpu_arm) as a stand-alone arm, rank 0 only."""
+    import torch
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from acestep_b200.dit import DiTShape
+    from acestep_b200.synthetic import random_dit_state, random_vae_state, synthetic_conditioning
+    from acestep_b200.vae import VaeShape
+
+    dev = torch.device("cuda:0")
+    dshape, vshape = DiTShape(), VaeShape()
+    cond = synthetic_conditioning(1, wl["T"], wl["E"], dshape.hidden_size, seed=1234, device=dev)
+    r = time_torch_gpu(wl, dev, dshape, vshape, random_dit_state(dshape, 0, dev), random_vae_state(vshape, 0, dev),
+                       cond, cond["null_emb"], songs=max(args.steps, 1), warmup=max(args.warmup, 1))
+    line = {"impl": "torch-gpu", "metric": "generated-audio-sec/wall-sec", "value": r["value"], "unit": "audio-s/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_song"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "kind": r["kind"]}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank's GPU: the device-resident and the host-buffer song closures."""
+
+    def __init__(self, pipe, wl, dshape, vshape, dev, rank):
+        import torch
+
+        from acestep_b200.synthetic import synthetic_conditioning
+
+        self.pipe, self.wl, self.dev = pipe, wl, dev
+        T, E = wl["T"], wl["E"]
+        self.T, self.E = T, E
+        self.n_samples = T * vshape.hop
+        self.host = synthetic_conditioning(1, T, E, dshape.hidden_size, seed=1234 + rank, device="cpu", pin=True)
+        self.dev_in = {k: v.to(dev) for k, v in self.host.items()}
+        pipe.sampler.null_condition_emb = self.dev_in["null_emb"]
+        pipe.turbo = wl["turbo"]
+        if wl["turbo"]:
+            self.skw = dict(shift=wl["shift"])
+        else:
+            self.skw = dict(infer_steps=wl["steps"], diffusion_guidance_sale=wl["guidance"], shift=wl["shift"])
+        self.rp = wl.get("repaint")
+        self.seed0 = 1000 * rank
+        if self.rp:  # config 5: the source audio is encoded inside the timed region
+            ga = torch.Generator().manual_seed(99 + rank)
+            self.audio_h = (torch.rand(1, 2, self.n_samples, generator=ga) - 0.5).pin_memory()
+            self.eps_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
+            self.sil_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
+            self.audio_d, self.eps_d, self.sil_d = self.audio_h.to(dev), self.eps_h.to(dev), self.sil_h.to(dev)
+
+    # the starting noise is drawn INSIDE the song (seeded torch generator on the device), like the reference's
+    # generate_audio -> prepare_noise (turbo :1917, base :1899)
+    def song_device(self, i):
+        if self.rp:
+            return self.pipe.repaint(self.dev_in["enc"], self.audio_d, self.rp[0], self.rp[1], self.sil_d,
+                                     [self.seed0 + i], posterior_eps=self.eps_d, to_host=False, **self.skw)
+        return self.pipe.generate(self.dev_in["enc"], self.dev_in["ctx"], self.dev_in["src"], [self.seed0 + i],
+                                  to_host=False, **self.skw)
+
+    def song_host(self, i):
+        if self.rp:
+            return self.pipe.repaint(self.host["enc"], self.audio_h, self.rp[0], self.rp[1], self.sil_h,
+                                     [self.seed0 + i], posterior_eps=self.eps_h, to_host=True, reuse_host_buffer=True,
+                                     **self.skw)
+        return self.pipe.generate(self.host["enc"], self.host["ctx"], self.host["src"], [self.seed0 + i],
+                                  to_host=True, reuse_host_buffer=True, **self.skw)
+
+    def h2d_bytes(self):
+        if self.rp:
+            return (self.host["enc"].numel() + self.eps_h.numel() + self.sil_h.numel()) * 2 + self.audio_h.numel() * 4
+        return sum(self.host[k].numel() * self.host[k].element_size() for k in ("enc", "ctx", "src"))
+
+    def codec_ms(self, reps=3):
+        """Event-timed VAE decode (+ encode for repaint) of this workload's length, to split the song time."""
+        import torch
+
+        z = self.dev_in["src"][0]
+        self.pipe.vae.decode_frames(z)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(self.dev)
+        e0.record()
+        for _ in range(reps):
+            self.pipe.vae.decode_frames(z)
+            if self.rp:
+                self.pipe.vae.encode_samples(self.audio_d[0], self.eps_d[0])
+        e1.record()
+        torch.cuda.synchronize(self.dev)
+        return e0.elapsed_time(e1) / reps
+
+    def flops(self):
+        Bc = 2 if self.wl["guidance"] > 1.0 else 1
+        S = (self.T + 1) // 2
+        step = dit_flops(Bc, S, self.E)
+        return step, self.wl["steps"] * step + vae_flops_per_frame() * self.T * (2 if self.rp else 1)
+
+
+def util_block(r, ms_song, codec_ms, peaks):
+    """DiT step alone (song time minus the event-timed codec passes, divided by the steps — i.e. including
+    guidance, Euler update and every host gap of the loop) against both measured peaks, and the whole song."""
+    step_fl, song_fl = r.flops()
+    step_ms = max(ms_song - codec_ms, 1e-6) / r.wl["steps"]
+    tf = step_fl / (step_ms * 1e-3) / 1e12
+    sus, burst = float(peaks.get("bf16_tflops_sustained", 1400.0)), float(peaks.get("bf16_tflops", 1590.0))
+    return {"dit_step_ms": step_ms, "dit_step_algorithmic_tflop": step_fl / 1e12, "dit_step_tflops": tf,
+            "dit_step_frac_of_sustained_peak": tf / sus, "dit_step_frac_of_burst_peak": tf / burst,
+            "codec_ms_per_song": codec_ms,
+            "whole_song_algorithmic_tflop": song_fl / 1e12,
+            "whole_song_tflops": song_fl / (ms_song * 1e-3) / 1e12,
+            "whole_song_frac_of_sustained_peak": song_fl / (ms_song * 1e-3) / 1e12 / sus,
+            "peaks_tflops": {"sustained": sus, "burst": burst}}
+
+
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
@@ -226,142 +414,108 @@ def run_b200(args, wl):
 
     from acestep_b200 import _lib
     from acestep_b200.dit import DiTShape
+    from acestep_b200.multi_gpu import generate_sharded
     from acestep_b200.pipeline import B200Pipeline
-    from acestep_b200.synthetic import random_dit_state, random_vae_state, synthetic_conditioning
+    from acestep_b200.synthetic import random_dit_state, random_vae_state
     from acestep_b200.vae import VaeShape
 
     lib = _lib.load()
     dshape, vshape = DiTShape(), VaeShape()
-    pipe = B200Pipeline(random_dit_state(dshape, 0, dev), random_vae_state(vshape, 0, dev), dshape, vshape,
-                        device=dev, turbo=wl["turbo"])
+    dit_state, vae_state = random_dit_state(dshape, 0, dev), random_vae_state(vshape, 0, dev)
+    pipe = B200Pipeline(dit_state, vae_state, dshape, vshape, device=dev, turbo=wl["turbo"])
     torch.cuda.empty_cache()
-    T, E = wl["T"], wl["E"]
-    host = synthetic_conditioning(1, T, E, dshape.hidden_size, seed=1234 + rank, device="cpu", pin=True)
-    noise_h = torch.randn(1, T, 64, generator=torch.Generator().manual_seed(rank)).to(torch.bfloat16).pin_memory()
-    dev_in = {k: v.to(dev) for k, v in host.items()}
-    noise_d = noise_h.to(dev)
-    pipe.sampler.null_condition_emb = dev_in["null_emb"]
-    if wl["turbo"]:
-        skw = dict(shift=wl["shift"])
-    else:
-        skw = dict(infer_steps=wl["steps"], diffusion_guidance_sale=wl["guidance"], shift=wl["shift"])
-    n_samples = T * vshape.hop
-    gathered = [torch.empty(1, 2, n_samples, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-
-    rp = wl.get("repaint")
-    if rp:  # config 5: the source audio is encoded inside the timed region
-        ga = torch.Generator().manual_seed(99 + rank)
-        audio_h = (torch.rand(1, 2, n_samples, generator=ga) - 0.5).pin_memory()
-        eps_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
-        sil_h = torch.randn(1, T, 64, generator=ga).to(torch.bfloat16).pin_memory()
-        audio_d, eps_d, sil_d = audio_h.to(dev), eps_h.to(dev), sil_h.to(dev)
-
-    def song_local():
-        if rp:
-            return pipe.repaint(dev_in["enc"], audio_d, rp[0], rp[1], sil_d, None, posterior_eps=eps_d, noise=noise_d,
-                                to_host=False, **skw)
-        return pipe.generate(dev_in["enc"], dev_in["ctx"], dev_in["src"], None, noise=noise_d, to_host=False, **skw)
-
-    pending = []
-
-    def song_device():
-        out = song_local()
-        if world > 1:
-            # the one collective of the path: waveform gather to rank 0 over NVLink, issued
-            # asynchronously (NCCL stream) so it overlaps the next song's denoising loop
-            pending.append((dist.gather(out["audio"], gathered, dst=0, async_op=True), out["audio"]))
-        return out
-
-    def drain():
-        for work, _keepalive in pending:
-            work.wait()
-        pending.clear()
-
-    def song_host():
-        if rp:
-            return pipe.repaint(host["enc"], audio_h, rp[0], rp[1], sil_h, None, posterior_eps=eps_h, noise=noise_h,
-                                to_host=True, **skw)
-        return pipe.generate(host["enc"], host["ctx"], host["src"], None, noise=noise_h, to_host=True, **skw)
+    peaks, peak_kind = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop
-    # (`out = song_device()`): otherwise the timed region's second song is the first to need a second set of
-    # output buffers and pays torch's cudaMalloc (+6 ... +24 ms on that one song, seen with ACE_BENCH_PER_SONG=1).
-    # The clock sampler attaches BEFORE the warm-up, and the warm-up runs back to back into the timed region:
-    # after any idle gap a power-capped B200 runs one song fast and then over-corrects for about one song
-    # (148 / 174 / 150 / 150 ... ms per song with ACE_BENCH_PER_SONG=1), so the gap must not sit between them.
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    out = None
-    for _ in range(args.warmup):
-        out = song_device()
-    drain()
-    win = {}
+    def measure(r, steps, warmup, clocks=None, verify=False):
+        """value: EXACTLY `steps` songs per GPU, device-resident inputs, CUDA events, barrier + synchronize on both
+        sides; N > 1 goes through the product's multi-GPU API (acestep_b200.multi_gpu.generate_sharded: song i on
+        rank i, asynchronous waveform gather to rank 0 that overlaps the next song, drained inside the region).
+        e2e: the same through the public API with pinned HOST inputs and a HOST waveform (wall clock)."""
+        lengths = [r.n_samples] * world
+        pending, keep = [], {}
+        counter = [0]
 
-    per_song = os.environ.get("ACE_BENCH_PER_SONG") == "1"
+        def step_device():
+            i = counter[0]
+            counter[0] += 1
+            if world == 1:
+                keep["out"] = r.song_device(i)
+                return
+            def one(_song_index):
+                keep["out"] = r.song_device(i)
+                return keep["out"]["audio"][0]
+            pending.append(generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True))
 
-    def measure_value():
-        """EXACTLY K songs, device-resident inputs, CUDA events, barrier + synchronize on both sides."""
-        nonlocal out  # the warm-up's last result is released by the first timed song, as in steady state
+        def drain():
+            res = None
+            for p in pending:
+                res = p.wait()
+            pending.clear()
+            return res
+
+        # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop;
+        # the clock sampler attaches BEFORE the warm-up and the warm-up runs back to back into the timed region
+        # (after an idle gap a power-capped B200 runs one song fast and then over-corrects for about one song).
+        barrier()
+        if verify and world > 1:
+            # once, through the RAGGED mode of the product API (length exchange + padded gather) and checked
+            def one(_i):
+                keep["out"] = r.song_device(0)
+                return keep["out"]["audio"][0]
+            songs = generate_sharded(one, world, dst=0, device=dev)
+            if rank == 0:
+                assert len(songs) == world and all(s.shape == (2, r.n_samples) for s in songs)
+                assert torch.equal(songs[0], keep["out"]["audio"][0]) and all(bool(torch.isfinite(s).all()) for s in songs)
+        for _ in range(warmup):
+            step_device()
+        drain()
         l0 = lib.ace_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         w0 = time.perf_counter()
         e0.record()
-        marks = []
-        for _ in range(args.steps):
-            out = song_device()
-            if per_song:  # diagnostics only (ACE_BENCH_PER_SONG=1): one extra event record per song
-                marks.append(torch.cuda.Event(enable_timing=True))
-                marks[-1].record()
-        drain()  # all gathers complete inside the timed region
+        for _ in range(steps):
+            step_device()
+        gathered = drain()  # all gathers complete inside the timed region
         e1.record()
         barrier()
-        win["value"] = (w0, time.perf_counter())
-        if per_song:
-            prev, per = e0, []
-            for m in marks:
-                per.append(round(prev.elapsed_time(m), 2))
-                prev = m
-            print(f"[bench rank {rank}] per-song ms in the value region: {per}", file=sys.stderr)
-        return e0.elapsed_time(e1), lib.ace_launch_count() - l0, bool(torch.isfinite(out["audio"]).all())
-
-    def measure_e2e():
-        """K songs through the public API with pinned HOST inputs and a HOST waveform (wall clock)."""
-        song_host()
+        w1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        launches = lib.ace_launch_count() - l0
+        finite = bool(torch.isfinite(keep["out"]["audio"]).all())
+        if gathered is not None:
+            finite = finite and all(bool(torch.isfinite(s).all()) for s in gathered)
+        # ---- e2e
+        r.song_host(0)
         barrier()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            oh = song_host()
+        for i in range(steps):
+            oh = r.song_host(10 + i)
         barrier()
         t1 = time.perf_counter()
-        win["e2e"] = (t0, t1)
-        return t1 - t0, oh["audio"].numel() * 4
+        res = {"ms": ms, "launches": int(launches), "finite": finite, "e2e_s": t1 - t0,
+               "d2h": oh["audio"].numel() * 4, "h2d": r.h2d_bytes(), "win_value": (w0, w1), "win_e2e": (t0, t1)}
+        keep.clear()
+        return res
 
-    # Both regions run under the same power cap; the order is fixed (device-resident first) and the
-    # SM clock of each region is reported so a throttling difference between them is visible.
-    if os.environ.get("ACE_BENCH_ORDER", "value_first") == "e2e_first":
-        (e2e_s, d2h), (ms, launches, finite) = measure_e2e(), measure_value()
-    else:
-        (ms, launches, finite), (e2e_s, d2h) = measure_value(), measure_e2e()
-    clk = None
-    if rank == 0:
-        clk = clocks.stop()
-        clk["sm_mhz"] = clocks.window(*win["value"]) or clk["sm_mhz"]
-        clk["sm_mhz_e2e_region"] = clocks.window(*win["e2e"])
-    if rp:
-        h2d = (host["enc"].numel() + noise_h.numel() + eps_h.numel() + sil_h.numel()) * 2 + audio_h.numel() * 4
-    else:
-        h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "ctx", "src")) + noise_h.numel() * 2
-
+    clocks = ClockSampler(local)
+    clocks.start()
+    main = Runner(pipe, wl, dshape, vshape, dev, rank)
+    m = measure(main, args.steps, args.warmup, clocks, verify=True)
+    my_clk = clocks.window(*m["win_value"])
+    ms_rank, e2e_rank = m["ms"], m["e2e_s"]
+    per_rank = [{"rank": rank, "ms_per_step": ms_rank / args.steps, "sm_mhz": my_clk}]
+    ms, e2e_s = ms_rank, e2e_rank
     if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
         tt = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(tt[0]), float(tt[1])
@@ -372,10 +526,9 @@ def run_b200(args, wl):
         import ctypes as C
 
         lib.ace_profile_start()
-        song_local()  # rank-local: no collective here, the other ranks are already past the timed region
+        main.song_device(0)  # rank-local: no collective here, the other ranks are already past the timed region
         pms, pfl, pby, pln = (C.c_float * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int * 4)()
         _lib.check(lib.ace_profile_stop(pms, pfl, pby, pln))
-        peaks, peak_kind = measured_peaks()
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         gemm_tf = (pfl[0] / (pms[0] * 1e-3)) / 1e12 if pms[0] > 0 else 0.0
         # dominant kernel = the GEMM problem shape with the largest total time in this song
@@ -388,28 +541,36 @@ def run_b200(args, wl):
                   for i in range(ns)]
         dom = shapes[0] if shapes else {"m": 0, "n": 0, "k": 0, "launches": 0, "ms_total": 0.0, "tflops": 0.0}
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed ncu --set full capture
-            with open(tpath) as f:
-                traffic = json.load(f).get(f"{dom['m']}x{dom['n']}x{dom['k']}")
-        Bc = 2 if wl["guidance"] > 1.0 else 1
-        S = (T + 1) // 2
-        song_flops = wl["steps"] * dit_flops(Bc, S, E) + vae_flops_per_frame() * T * (2 if rp else 1)
+        for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed ncu --set full capture
+                with open(tpath) as f:
+                    traffic = json.load(f).get(f"{dom['m']}x{dom['n']}x{dom['k']}")
+                if traffic is not None:
+                    break
         audio_s = wl["seconds"] * world * args.steps
         value = audio_s / (ms * 1e-3)
+        clk = clocks.stop()
+        clk["sm_mhz"] = my_clk or clk["sm_mhz"]
+        clk["sm_mhz_e2e_region"] = clocks.window(*m["win_e2e"])
         line = {
             "metric": "generated-audio-sec/wall-sec", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (random-init weights, N(0,1) text-conditioning embeddings, seeded noise)",
-            "config": {"workload": wl["desc"], "songs_per_gpu_per_step": 1, "latent_frames": T,
-                       "cond_tokens": E, "parallelism": f"songs sharded 1/GPU x{world}, waveform gather",
+            "data": "synthetic (random-init weights, N(0,1) text-conditioning embeddings, seeded noise drawn inside "
+                    "the timed region like the reference's prepare_noise)",
+            "config": {"workload": wl["desc"], "songs_per_gpu_per_step": 1, "latent_frames": main.T,
+                       "cond_tokens": main.E,
+                       "parallelism": (f"songs sharded 1/GPU x{world} through acestep_b200.multi_gpu.generate_sharded "
+                                       "(async NCCL waveform gather to rank 0, drained inside the timed region)"
+                                       if world > 1 else "1 GPU"),
                        "l2_policy": "working set per step (3.2 GB weights) exceeds the 126 MB L2",
-                       "outputs_finite": finite},
-            "e2e": {"value": audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
+                       "outputs_finite": m["finite"]},
+            "e2e": {"value": audio_s / e2e_s, "unit": "audio-s/s", "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": m["launches"],
             "clocks": clk,
+            "per_rank": per_rank,
             "roofline": {"bound": "tensor",
                          "kernel": (f"gemm_tc2_kernel M={dom['m']} N={dom['n']} K={dom['k']} (largest share of the "
                                     f"song: {dom['launches']} launches, {dom['ms_total']} ms)"),
@@ -423,14 +584,57 @@ def run_b200(args, wl):
                          "by_shape": shapes[:8]},
             "breakdown_ms_per_song": {"gemm": float(pms[0]), "attention": float(pms[1]),
                                       "elementwise": float(pms[2]), "simt_conv": float(pms[3]),
+                                      "launches": [int(pln[i]) for i in range(4)],
                                       "attention_tflops": (pfl[1] / (pms[1] * 1e-3)) / 1e12 if pms[1] > 0 else 0.0,
                                       "elementwise_gbs": (pby[2] / (pms[2] * 1e-3)) / 1e9 if pms[2] > 0 else 0.0},
-            "dit_step_tensor_util": {"algorithmic_tflop_per_song": song_flops / 1e12,
-                                     "whole_song_tflops": song_flops / (ms / args.steps * 1e-3) / 1e12,
-                                     "frac_of_peak": song_flops / (ms / args.steps * 1e-3) / 1e12 / peak},
+            "dit_step_tensor_util": util_block(main, ms_rank / args.steps, main.codec_ms(), peaks),
         }
+    else:
+        clocks.stop()
+
+    # ---- the other single-GPU workloads of BASELINE.json in the same run (N = 1 only): 240 s / 60 steps is
+    # north_star's own target, c5 the repaint chain, c1 the 10 s turbo clip
+    if world == 1 and not args.no_extra:
+        extra = {}
+        for name in ("c3", "c5", "c1", "c2"):
+            if WORKLOADS[name] is wl:
+                continue
+            w2 = WORKLOADS[name]
+            try:
+                ck = ClockSampler(local)
+                ck.start()
+                r2 = Runner(pipe, w2, dshape, vshape, dev, rank)
+                k = max(2, min(args.steps, 3))
+                m2 = measure(r2, k, 1)
+                c2 = ck.stop()
+                entry = {"workload": w2["desc"], "steps": k, "warmup": 1,
+                         "value": w2["seconds"] * k / (m2["ms"] * 1e-3), "ms_per_step": m2["ms"] / k,
+                         "e2e": {"value": w2["seconds"] * k / m2["e2e_s"], "h2d_bytes_per_step": m2["h2d"],
+                                 "d2h_bytes_per_step": m2["d2h"]},
+                         "gpu_launches": m2["launches"], "outputs_finite": m2["finite"],
+                         "clocks": {"sm_mhz": ck.window(*m2["win_value"]) or c2["sm_mhz"], "reasons": c2["reasons"]}}
+                entry.update(util_block(r2, m2["ms"] / k, r2.codec_ms(), peaks))
+                extra[name] = entry
+                del r2
+                torch.cuda.empty_cache()
+            except Exception as exc:  # an extra workload never takes the headline line down with it
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        line["extra_workloads"] = extra
     pipe.close()
+    main.pipe = None
+    del pipe
+    torch.cuda.empty_cache()
+
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and not main.rp:
+        # the reference's own GPU path on this B200, same workload, same run (SURVEY §8c last row)
+        try:
+            gb = time_torch_gpu(wl, dev, dshape, vshape, dit_state, vae_state, main.dev_in, main.dev_in["null_emb"])
+            gb["speedup_of_this_repo"] = line["value"] / gb["value"]
+            line["gpu_baseline"] = gb
+        except Exception as exc:
+            line["gpu_baseline"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        T, E, rp = main.T, main.E, main.rp
         try:
             one_sample, threads = cpu_sample(wl)
             one_sample()
@@ -440,7 +644,8 @@ def run_b200(args, wl):
                 "value": wl["seconds"] / song, "unit": "audio-s/s", "cores": threads, "kind": "port",
                 "sample": (f"1 DiT forward (effective batch {2 if wl['guidance'] > 1 else 1}, T={T}, E={E}) = {a:.2f} s and one "
                            f"64-frame VAE decode window = {b:.2f} s on the host CPU (fp32 oracle port), "
-                           f"extrapolated to {wl['steps']} forwards + {T}/64 windows")}
+                           f"extrapolated to {wl['steps']} forwards + {T}/64 windows (the full song would take "
+                           f"{song:.0f} s of CPU time per step)")}
         except Exception as exc:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {exc}"}
@@ -456,13 +661,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads block (c3 / c5 / c1)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
+    if args.impl == "torch-gpu":
+        return run_torch_gpu(args, wl)
     return run_b200(args, wl)
 
 

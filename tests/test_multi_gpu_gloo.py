@@ -24,12 +24,20 @@ def _worker(rank, world, port, n_items, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        out = generate_sharded(_song, n_items, dst=0)
+        out = generate_sharded(_song, n_items, dst=0)  # ragged mode: lengths exchanged first
+        # known-lengths mode, asynchronous: no length exchange, the gather is waited for later
+        lens = [_song(i).shape[-1] for i in range(n_items)]
+        pend = generate_sharded(_song, n_items, dst=0, lengths=lens, async_op=True)
+        # one equal-length song per rank (the benchmark's shape): zero-copy send buffer
+        pend1 = generate_sharded(lambda i: _song(0) + i, world, dst=0, lengths=[_song(0).shape[-1]] * world, async_op=True)
+        out2, out3 = pend.wait(), pend1.wait()
         if rank == 0:
             ok = len(out) == n_items and all(torch.equal(out[i], _song(i)) for i in range(n_items))
+            ok = ok and len(out2) == n_items and all(torch.equal(out2[i], _song(i)) for i in range(n_items))
+            ok = ok and len(out3) == world and all(torch.equal(out3[i], _song(0) + i) for i in range(world))
             q.put(bool(ok))
         else:
-            assert out is None
+            assert out is None and out2 is None and out3 is None
     finally:
         dist.destroy_process_group()
 
