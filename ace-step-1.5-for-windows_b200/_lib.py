@@ -57,6 +57,7 @@ SIGNATURES = {
     "ace_dit_bind": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     "ace_dit_set_condition": (C.c_int, [_P, _P, _P]),
     "ace_dit_step": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), _P, _P]),
+    "ace_dit_prepare_timesteps": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int, _P]),
     "ace_dit_cross_attentions": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.c_int, _P, _P]),
     "ace_euler_step": (C.c_int, [_P, _P, C.c_float, C.c_size_t, _P]),
     "ace_euler_step_dup": (C.c_int, [_P, _P, C.c_float, C.c_size_t, _P, _P]),

@@ -194,6 +194,67 @@ __global__ void mod_table_kernel(const bf16* __restrict__ tables, const bf16* __
   st8(out + (((long)l * B + b) * n + i) * D + c * 8, a);
 }
 
+// Timestep-cache tables (dit.cu): everything of the DiT's modulation that depends on the timestep only, for `nb`
+// consecutive cache entries.  Per entry e (timestep t_e, temb / tproj rows e of this batch):
+//   mods [L][6][D] = bf16(table[l][i] + tproj[e][i])  (i = 1, 4: bf16(1 + that))    — :490-496 of the layer
+//   outmod [2][D]  = bf16(out_table[i] + temb[e])     (i = 1: bf16(1 + that))       — :1488-1493
+//   cv   [L][2][D] = bf16(w_self_norm[l] * mods[l][1]),  bf16(w_mlp_norm[l] * mods[l][4])   (the c vectors of
+//   cout [D]       = bf16(w_norm_out * outmod[1])                                            epilogues.cuh NormOut)
+// One thread per 8-element chunk of one row; rows [0, 6L) mods, [6L, 6L+2) outmod, [6L+2, 8L+2) cv, 8L+2 cout.
+__global__ void tcache_tables_kernel(TCacheTablesArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int nchunk = a.D >> 3, L = a.L, D = a.D;
+  const int rows = 8 * L + 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)a.nb * rows * nchunk) return;
+  const int c = idx % nchunk;
+  const int r = (idx / nchunk) % rows;
+  const int e = idx / ((long)nchunk * rows);
+  uint8_t* ent = a.entries + (size_t)e * a.entry_bytes;
+  auto mod = [&](int l, int i, float (&v)[8]) {  // mods[l][i] chunk c
+    float x[8], t[8];
+    ld8(a.tables + ((long)l * 6 + i) * D + c * 8, x);
+    ld8(a.tproj + (long)e * 6 * D + (long)i * D + c * 8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = bf16_round(x[k] + t[k]);
+      if (i == 1 || i == 4) v[k] = bf16_round(1.0f + v[k]);
+    }
+  };
+  auto omod = [&](int i, float (&v)[8]) {
+    float x[8], t[8];
+    ld8(a.out_table + (long)i * D + c * 8, x);
+    ld8(a.temb + (long)e * D + c * 8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = bf16_round(x[k] + t[k]);
+      if (i == 1) v[k] = bf16_round(1.0f + v[k]);
+    }
+  };
+  float v[8], w[8];
+  if (r < 6 * L) {
+    mod(r / 6, r % 6, v);
+    st8(reinterpret_cast<bf16*>(ent + a.off_mods) + (long)r * D + c * 8, v);
+  } else if (r < 6 * L + 2) {
+    omod(r - 6 * L, v);
+    st8(reinterpret_cast<bf16*>(ent + a.off_outmod) + (long)(r - 6 * L) * D + c * 8, v);
+  } else if (r < 8 * L + 2) {
+    const int l = (r - 6 * L - 2) >> 1, j = (r - 6 * L - 2) & 1;
+    mod(l, j ? 4 : 1, v);
+    ld8((j ? a.mlp_norm0 : a.self_norm0) + (long)l * a.layer_stride + c * 8, w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= w[k];
+    st8(reinterpret_cast<bf16*>(ent + a.off_cv) + ((long)l * 2 + j) * D + c * 8, v);
+  } else {
+    omod(1, v);
+    ld8(a.norm_out_w + c * 8, w);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= w[k];
+    st8(reinterpret_cast<bf16*>(ent + a.off_cout) + c * 8, v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Timestep embedding: tiny GEMVs, bound by reading the weights once (one warp per output row).
 constexpr int TE_MAXB = 16;
@@ -595,6 +656,14 @@ int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long
   if (total == 0) return ACE_OK;
   ELEM(total * 48, mod_table_kernel, (unsigned)((total + 255) / 256), 256, tables, tvec, t_b_stride, t_i_stride,
        out, L, B, n, D, scale_mask);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+int launch_tcache_tables(const TCacheTablesArgs& a, cudaStream_t stream) {
+  const long total = (long)a.nb * (8 * a.L + 3) * (a.D / 8);
+  if (total == 0) return ACE_OK;
+  ELEM(total * 48, tcache_tables_kernel, (unsigned)((total + 255) / 256), 256, a);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

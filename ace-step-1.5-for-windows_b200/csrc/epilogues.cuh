@@ -127,18 +127,134 @@ struct WarpStage {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Deferred RMSNorm / AdaLN (the DiT layer's three norms and the output norm run as NO kernel of their own).
+//
+// Reference (AceStepDiTLayer.forward :490-496, :513, :526-529; output norm :1488-1493):
+//     hn = rmsnorm(h) * w * (1 + scale_b) + shift_b ;   y = hn @ W^T
+// Split by linearity of the GEMM in its A operand:
+//     y[m, n] = rstd[m] * sum_k (h[m,k] * c_b[k]) * W[n,k]  +  sum_k shift_b[k] * W[n,k]
+//             = rstd[m] * (g @ W^T)[m, n] + bs_b[n],      c_b = w * (1 + scale_b),  g = h * c_b
+//   * the PRODUCER of h (the residual-adding epilogue of the previous GEMM) also writes g = bf16(h * c) and this
+//     row's sum of squares, as one fp32 partial per 64-column slab in a fixed slot (NormOut) — no atomics, the
+//     consumer adds the D/64 partials in slot order, so replays are bit-identical;
+//   * the CONSUMER GEMM runs on g and its epilogue applies rstd[m] and bs (NormIn);
+//   * c_b and bs_b = shift_b @ W^T depend on the timestep only: they live in the handle's timestep cache
+//     (dit.cu), one entry per distinct t, indexed per batch item through `slot[b]`.
+// Fewer bf16 roundings than the reference's chain (one on g instead of three on hn), same fp32 statistics.
+// ---------------------------------------------------------------------------------------------
+struct NormOut {
+  bf16* g;            // [M, ldg] A operand of the consuming GEMM; null = this epilogue feeds no norm
+  long ldg;
+  const bf16* cvec;   // c vector(s): cvec + slot[b] * c_stride  (c_stride 0: one constant vector)
+  long c_stride;
+  float* ssp;         // [M, nss] partial sums of squares, nss = D / 64, slot j = columns [64 j, 64 j + 64)
+  int nss;
+  const int* slot;    // [batch] timestep-cache entry of each batch item (null with c_stride 0)
+  int S;              // rows per batch item
+  // called from the epilogue's prefetch hook (main loop still running): this row's c lines -> L1
+  __device__ __forceinline__ void warm(int row, int n0, int M, int N) const {
+    if (g == nullptr || row >= M) return;
+    const bf16* c = cvec + (c_stride ? (long)__ldg(slot + row / S) * c_stride : 0) + n0;
+    l1_prefetch(c);
+    if (n0 + 64 < N) l1_prefetch(c + 64);
+  }
+  // slab `stg` holds bf16 rows [row0, row0 + 32) x columns [col, col + 64) of the new h (lane's own row = `lane`):
+  // writes this row's partial, turns the slab into g in place and stores it.
+  __device__ __forceinline__ void emit(const WarpStage& stg, int lane, int row, int row0, int col, int ncols,
+                                       int M) const {
+    const int b = row < M ? row / S : 0;
+    const uint4* cp = reinterpret_cast<const uint4*>(cvec + (c_stride ? (long)__ldg(slot + b) * c_stride : 0) + col);
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4* sl = stg.at(lane, q);
+      uint4 r = *sl;
+      const uint4 c = __ldg(cp + q);
+      float x0, x1;
+      unpack_bf16x2(r.x, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      unpack_bf16x2(r.y, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      unpack_bf16x2(r.z, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      unpack_bf16x2(r.w, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      r.x = bmul2(r.x, c.x); r.y = bmul2(r.y, c.y); r.z = bmul2(r.z, c.z); r.w = bmul2(r.w, c.w);
+      *sl = r;
+    }
+    if (row < M) ssp[(size_t)row * nss + (col >> 6)] = ss;
+    stg.store_rows(lane, ncols, [&](int r) -> bf16* {
+      return row0 + r < M ? g + (size_t)(row0 + r) * ldg + col : nullptr;
+    });
+  }
+};
+
+struct NormIn {
+  const float* ssp;   // null = plain GEMM (no deferred norm)
+  int nss;
+  float inv_d, eps;
+  const float* bs;    // bias rows: bs + slot[b] * bs_stride + n; null = none (plain RMSNorm: no shift)
+  long bs_stride;
+  const int* slot;
+  int S;
+  // called from the epilogue's prefetch hook: this row's bias lines for 128 columns from n0 -> L1 (they are read
+  // 32 columns at a time between TMEM loads; from L2 each of those reads is a ~700-cycle round trip)
+  __device__ __forceinline__ void warm(int row, int n0, int M, int N) const {
+    if (bs == nullptr || row >= M) return;
+    const float* b = bs + (long)__ldg(slot + row / S) * bs_stride + n0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + 32 * i < N) l1_prefetch(b + 32 * i);
+  }
+  // rstd of this thread's row (called before the accumulator is ready)
+  __device__ __forceinline__ float rstd(int row, int M) const {
+    if (ssp == nullptr) return 1.0f;
+    if (row >= M) return 0.0f;
+    const float4* p = reinterpret_cast<const float4*>(ssp + (size_t)row * nss);
+    float tot = 0.f;
+    for (int j = 0; j < (nss >> 2); ++j) {  // fixed order: bit-identical on replay
+      const float4 v = p[j];
+      tot += v.x; tot += v.y; tot += v.z; tot += v.w;
+    }
+    return rsqrtf(tot * inv_d + eps);
+  }
+  __device__ __forceinline__ const float* bias_row(int row, int M) const {
+    if (bs == nullptr) return nullptr;
+    const int b = row < M ? row / S : 0;
+    return bs + (long)__ldg(slot + b) * bs_stride;
+  }
+  // v[i] = v[i] * rstd + bias[n + i]  for 32 consecutive columns
+  __device__ __forceinline__ void apply32(float (&v)[32], float rs, const float* brow, int n) const {
+    if (ssp == nullptr) return;
+    if (brow != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + n) + i);
+        v[4 * i + 0] = fmaf(v[4 * i + 0], rs, b4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], rs, b4.y);
+        v[4 * i + 2] = fmaf(v[4 * i + 2], rs, b4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], rs, b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= rs;
+    }
+  }
+};
+
 // out[row, n] = bf16(acc + bias[n])                       (proj_in, condition_embedder)
 struct EpiBias {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
   bf16* out;
   long ldo;
   const bf16* bias;  // may be null
-  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
+  NormOut no = {};   // no.g != null: also feed the next norm (proj_in -> layer 0's self-attention norm)
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    no.warm(row, n0, M, N);
+    return 0.f;
+  }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg,
+                                      float) const {
     const int lane = threadIdx.x & 31, row0 = row - lane;
 #pragma unroll 1
     for (int s = 0; s < BN; s += 64) {
+      if (n0 + s >= N) break;  // warp-uniform
 #pragma unroll
       for (int c32 = 0; c32 < 2; ++c32) {
         float v[32];
@@ -155,6 +271,29 @@ struct EpiBias {
       stg.store_rows(lane, ncols, [&](int r) -> bf16* {
         return row0 + r < M ? out + (size_t)(row0 + r) * ldo + n0 + s : nullptr;
       });
+      if (no.g != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
+    }
+  }
+};
+
+// out[row * ldo + n] = acc (fp32, thread-per-row: rows are few)      — the bias rows bs = shift @ W^T of the
+// timestep cache (dit.cu); row r of the GEMM is cache entry first + r.
+struct EpiStoreF32 {
+  static constexpr bool kHalfTile = true;
+  float* out;
+  long ldo;
+  __device__ __forceinline__ float prefetch(int, int, int, int, const WarpStage&) const { return 0.f; }
+  template <int BN, class Acc>
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage&, float) const {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      acc.load32(c, v);
+      if (row < M && n0 + c < N) {
+        float4* o = reinterpret_cast<float4*>(out + (size_t)row * ldo + n0 + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
     }
   }
 };
@@ -175,9 +314,12 @@ struct EpiQKV {
   const bf16* sin_tab;   // [S, 64]
   int S;                 // tokens per batch item (position = row % S)
   float eps;
-  // norm weights and this row's RoPE table lines -> L1 while the main loop is still running
-  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage&) const {
-    if (n0 >= nq + nk || row >= M) return;
+  NormIn ni = {};        // ni.ssp != null: A was g = h * c, apply rstd[row] and the shift bias here (deferred AdaLN)
+  // norm weights and this row's RoPE table lines -> L1 while the main loop is still running; returns rstd[row]
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    ni.warm(row, n0, M, N);
+    const float rs = ni.rstd(row, M);
+    if (n0 >= nq + nk || row >= M) return rs;
     const bf16* w = (n0 < nq) ? q_norm_w : k_norm_w;
     l1_prefetch(w);
     l1_prefetch(w + 64);
@@ -185,11 +327,14 @@ struct EpiQKV {
       l1_prefetch(cos_tab + (size_t)(row % S) * 64);
       l1_prefetch(sin_tab + (size_t)(row % S) * 64);
     }
+    return rs;
   }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg,
+                                      float rs) const {
     static_assert(BN == 128, "EpiQKV needs one head per tile");
     const int lane = threadIdx.x & 31, row0 = row - lane;
+    const float* brow = ni.bias_row(row, M);
     auto out_addr = [&](int col0) {
       return [=](int r) -> bf16* { return row0 + r < M ? out + (size_t)(row0 + r) * ldo + n0 + col0 : nullptr; };
     };
@@ -200,6 +345,7 @@ struct EpiQKV {
         for (int c32 = 0; c32 < 2; ++c32) {
           float v[32];
           acc.load32(s + c32 * 32, v);
+          ni.apply32(v, rs, brow, n0 + s + c32 * 32);
           stg.put32(lane, c32, v);
         }
         stg.store_rows(lane, 64, out_addr(s));
@@ -214,6 +360,7 @@ struct EpiQKV {
     for (int c = 0; c < 4; ++c) {
       float v[32];
       acc.load32(c * 32, v);
+      ni.apply32(v, rs, brow, n0 + c * 32);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const uint32_t t = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -276,28 +423,37 @@ struct EpiGatedResid {
   static constexpr bool kHalfTile = true;
   bf16* h;  // read-modify-write in place
   long ldh;
-  const bf16* gate;  // [Bc, gate_ld] or null
+  const bf16* gate;  // gate vector of batch item b at gate + gsel(b) * gate_ld, gsel(b) = slot ? slot[b] : b; or null
   long gate_ld;
   int S;  // rows per batch item
+  const int* slot = nullptr;  // [batch] timestep-cache entry per batch item (the DiT); null: gate is [batch, gate_ld]
+  NormOut no = {};            // no.g != null: also feed the next norm
+  __device__ __forceinline__ int gsel(int row, int M) const {
+    const int b = row < M ? row / S : 0;
+    return slot != nullptr ? __ldg(slot + b) : b;
+  }
   // called BEFORE the accumulator is ready (the main loop is still running): stage the first
   // residual slab so its L2 latency is off the critical path
-  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage& stg) const {
     const int lane = threadIdx.x & 31, row0 = row - lane;
-    if (n0 >= N) return;
+    if (n0 >= N) return 0.f;
     const int ncols = N - n0 < 64 ? N - n0 : 64;
     if (gate != nullptr && row < M) {  // this row's gate vector: pulled into L1 for the loads in run()
-      const bf16* g = gate + (size_t)(row / S) * gate_ld + n0;
+      const bf16* g = gate + (size_t)gsel(row, M) * gate_ld + n0;
       l1_prefetch(g);
       if (n0 + 64 < N) l1_prefetch(g + 64);
     }
+    no.warm(row, n0, M, N);
     stg.load_rows(lane, ncols, [&](int r) -> const bf16* {
       return row0 + r < M ? h + (size_t)(row0 + r) * ldh + n0 : nullptr;
     });
+    return 0.f;
   }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg,
+                                      float) const {
     const int lane = threadIdx.x & 31, row0 = row - lane;
-    const int b = row < M ? row / S : 0;
+    const int b = gate != nullptr ? gsel(row, M) : 0;
     uint4 nxt[8];
 #pragma unroll 1
     for (int s = 0; s < BN; s += 64) {
@@ -337,6 +493,7 @@ struct EpiGatedResid {
         }
       }
       stg.store_rows(lane, ncols, addr);
+      if (no.g != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
       if (has_next) stg.commit_rows(lane, nxt);
     }
   }
@@ -348,17 +505,25 @@ struct EpiSwiGLU {
   static constexpr bool kHalfTile = false;
   bf16* out;
   long ldo;
-  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
+  NormIn ni = {};  // deferred AdaLN of the MLP norm (see NormIn)
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    ni.warm(row, n0, M, N);
+    return ni.rstd(row, M);
+  }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg,
+                                      float rs) const {
     static_assert(BN == 128, "EpiSwiGLU packs 64 gate + 64 up columns per tile");
     const int lane = threadIdx.x & 31, row0 = row - lane;
     const int f0 = (n0 >> 7) << 6;
+    const float* brow = ni.bias_row(row, M);
 #pragma unroll
     for (int c32 = 0; c32 < 2; ++c32) {
       float g[32], u[32];
       acc.load32(c32 * 32, g);
       acc.load32(c32 * 32 + 64, u);
+      ni.apply32(g, rs, brow, n0 + c32 * 32);
+      ni.apply32(u, rs, brow, n0 + c32 * 32 + 64);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint32_t o[4];
@@ -385,17 +550,24 @@ struct EpiProjOut {
   bf16* vt;  // [Bc, T, 64]
   const bf16* bias;  // [64]
   int S, T;
-  __device__ __forceinline__ void prefetch(int, int, int, int, const WarpStage&) const {}
+  NormIn ni = {};  // deferred output AdaLN (:1488-1493)
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    ni.warm(row, n0, M, N);
+    return ni.rstd(row, M);
+  }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage& stg,
+                                      float rs) const {
     static_assert(BN == 128, "EpiProjOut");
     const int lane = threadIdx.x & 31, row0 = row - lane;
+    const float* brow = ni.bias_row(row, M);
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {  // kernel tap k = 64-column half k
 #pragma unroll
       for (int c32 = 0; c32 < 2; ++c32) {
         float v[32], bb[32];
         acc.load32(k * 64 + c32 * 32, v);
+        ni.apply32(v, rs, brow, n0 + k * 64 + c32 * 32);
         load_bf16x32(bias + c32 * 32, bb);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += bb[i];
@@ -443,15 +615,16 @@ struct EpiConv {
   long ldo, off, total;
   int chan_mod;          // channel of column n is n % chan_mod (a multiple of 32)
   // residual rows are re-read by the thread that produces the output row: pull them into L1 early
-  __device__ __forceinline__ void prefetch(int row, int n0, int M, int N, const WarpStage&) const {
-    if (resid == nullptr || row >= M) return;
+  __device__ __forceinline__ float prefetch(int row, int n0, int M, int N, const WarpStage&) const {
+    if (resid == nullptr || row >= M) return 0.f;
     const long idx = (long)row * ldo + n0 + off;
-    if (idx < 0 || idx >= total) return;
+    if (idx < 0 || idx >= total) return 0.f;
     l1_prefetch(resid + idx);
     l1_prefetch(resid + idx + 64);
+    return 0.f;
   }
   template <int BN, class Acc>
-  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage&) const {
+  __device__ __forceinline__ void run(const Acc& acc, int row, int n0, int M, int N, const WarpStage&, float) const {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       const long idx = (long)row * ldo + n0 + c + off;

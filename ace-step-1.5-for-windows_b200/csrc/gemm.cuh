@@ -298,13 +298,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
       const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
-      if (S == 1 && live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+      float pre = 0.f;
+      if (S == 1 && live) pre = epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
       __syncwarp();
       AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
       if (S == 1) {
-        if (live) epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+        if (live) epi.template run<EBN>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg, pre);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -383,8 +384,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         int m_end = m0 + sp * R + R;
         if (m_end > shp.M) m_end = shp.M;
         const AccSmem racc{red + (size_t)(lr < R ? lr : R - 1) * BN + sub};
-        epi.prefetch(row, n0, m_end, shp.N, stg);
-        epi.template run<EBN>(racc, row, n0, m_end, shp.N, stg);
+        const float spre = epi.prefetch(row, n0, m_end, shp.N, stg);
+        epi.template run<EBN>(racc, row, n0, m_end, shp.N, stg, spre);
       }
     }
   }
@@ -587,7 +588,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
       const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
-      if (live) epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+      float pre = 0.f;
+      if (live) pre = epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);
       if (threadIdx.x == 128) ACE_STAMP(5);
       tcgen05_fence_after();
@@ -595,9 +597,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       if (live) {
         AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + sub)};
         if (BN == 256 || sub == 0) {
-          epi.template run<128>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+          epi.template run<128>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg, pre);
         } else {
-          epi.template run<(BN == 256 ? 128 : BN - 128)>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
+          epi.template run<(BN == 256 ? 128 : BN - 128)>(acc, m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg, pre);
         }
       }
       tcgen05_fence_before();
@@ -631,8 +633,8 @@ gemm_ref_epilogue_kernel(const float* __restrict__ scratch, int ld, GemmShape sh
   const int row = m0 + threadIdx.x;
   AccGlobal acc{scratch + (size_t)row * ld + n0};
   const WarpStage stg{stage_mem + (threadIdx.x >> 5) * 4096};
-  epi.prefetch(row, n0, shp.M, shp.N, stg);
-  epi.template run<BN>(acc, row, n0, shp.M, shp.N, stg);
+  const float pre = epi.prefetch(row, n0, shp.M, shp.N, stg);
+  epi.template run<BN>(acc, row, n0, shp.M, shp.N, stg, pre);
 }
 
 #endif  // ACE_PROBE

@@ -50,6 +50,23 @@ int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift, const 
 int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long t_i_stride, bf16* out, int L,
                      int B, int n, int D, unsigned scale_mask, cudaStream_t stream);
 
+// Timestep-cache tables for `nb` consecutive entries starting at `entries` (see tcache_tables_kernel).
+struct TCacheTablesArgs {
+  uint8_t* entries;        // first entry
+  size_t entry_bytes;
+  size_t off_mods, off_outmod, off_cv, off_cout;  // byte offsets inside an entry
+  int nb, L, D;
+  const bf16* tables;      // [L][6][D] scale_shift_table of every layer
+  const bf16* out_table;   // [2][D]
+  const bf16* tproj;       // [nb][6 D]
+  const bf16* temb;        // [nb][D]
+  const bf16* self_norm0;  // layer 0's self_attn_norm / mlp_norm weights; layer l at + l * layer_stride
+  const bf16* mlp_norm0;
+  long layer_stride;
+  const bf16* norm_out_w;  // [D]
+};
+int launch_tcache_tables(const TCacheTablesArgs& a, cudaStream_t stream);
+
 // Timestep embedding (TimestepEmbedding.forward): sinusoid -> linear_1 -> SiLU -> linear_2 -> temb;
 // SiLU -> time_proj -> proj.  Weights bf16 row-major [out, in].
 struct TimeEmbedWeights {

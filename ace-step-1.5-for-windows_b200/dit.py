@@ -131,6 +131,17 @@ class B200DiT:
             _lib.check(self.lib.ace_dit_set_condition(self.handle, enc.data_ptr(), _lib.stream_handle(self.device)), "ace_dit_set_condition", self.lib)
         self._enc_keepalive = enc
 
+    def prepare_timesteps(self, ts: Sequence[float]) -> None:
+        """Fill the handle's timestep cache for a whole schedule in one batched pass (ace_dit_prepare_timesteps);
+        values already cached cost nothing.  Optional: step() computes missing entries on first sight."""
+        vals = [float(x) for x in ts]
+        if not vals:
+            return
+        tv = (C.c_float * len(vals))(*vals)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ace_dit_prepare_timesteps(self.handle, tv, len(vals), _lib.stream_handle(self.device)),
+                       "ace_dit_prepare_timesteps", self.lib)
+
     def step(self, xt: torch.Tensor, ctx: torch.Tensor, t: Sequence[float], out: Optional[torch.Tensor] = None):
         """One velocity prediction vt = decoder(xt, t, ctx).  xt [bc,T,64], ctx [bc,T,128] bf16."""
         bc, T, _ = xt.shape

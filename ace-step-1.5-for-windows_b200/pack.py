@@ -25,6 +25,64 @@ class UnsupportedAdapterError(RuntimeError):
     """model.decoder carries a parametrisation this packer cannot fold into plain Linear weights."""
 
 
+def _lokr_delta(mod) -> torch.Tensor:
+    """Weight delta of one LyCORIS LoKr module — what its (non-bypass) forward adds to the wrapped Linear's weight:
+    multiplier * scale * kron(w1, w2), with w1 = lokr_w1 or lokr_w1_a @ lokr_w1_b and w2 = lokr_w2 or
+    lokr_w2_a @ lokr_w2_b (third-party `lycoris-lora`, unpinned in the reference's requirements and absent here;
+    this restates its published LokrModule.get_diff_weight for Linear layers).  The module's own
+    `get_diff_weight` is used when it exists, so a newer library version stays authoritative."""
+    mult = float(getattr(mod, "multiplier", 1.0))
+    if bool(getattr(mod, "wd", False)) or getattr(mod, "dora_scale", None) is not None:
+        raise UnsupportedAdapterError("LoKr module with weight decomposition (DoRA) is not a linear fold")
+    if getattr(mod, "use_tucker", False) or getattr(mod, "tucker", False) or getattr(mod, "lokr_t2", None) is not None:
+        raise UnsupportedAdapterError("LoKr module with Tucker decomposition (conv layers) is not supported")
+    fn = getattr(mod, "get_diff_weight", None)
+    if callable(fn):
+        out = fn(mult)
+        d = out[0] if isinstance(out, (tuple, list)) else out
+        return d.detach().float()
+
+    def factor(name):
+        full = getattr(mod, name, None)
+        if full is not None:
+            return full.detach().float()
+        a, b_ = getattr(mod, name + "_a", None), getattr(mod, name + "_b", None)
+        if a is None or b_ is None:
+            raise UnsupportedAdapterError(f"LoKr module has neither {name} nor {name}_a / {name}_b")
+        return a.detach().float() @ b_.detach().float()
+
+    scale = float(getattr(mod, "scale", 1.0))
+    return torch.kron(factor("lokr_w1"), factor("lokr_w2")) * (scale * mult)
+
+
+def _lycoris_deltas(decoder) -> Dict[str, torch.Tensor]:
+    """{decoder module name: weight delta} for the LyCORIS net `_load_lokr_adapter` attaches as
+    `decoder._lycoris_net` (handler/lora/lifecycle.py:101-156): `net.loras` wrap the decoder's own Linear modules
+    (`org_module[0]`), whose parameters — and state_dict keys — stay untouched; scale / enable go through each
+    module's `multiplier` (controls.py:13-31, :121-128)."""
+    net = getattr(decoder, "_lycoris_net", None)
+    if net is None:
+        return {}
+    loras = getattr(net, "loras", None)
+    if loras is None:
+        raise UnsupportedAdapterError("decoder._lycoris_net has no `loras` list to fold")
+    by_id = {id(m): n for n, m in decoder.named_modules()}
+    deltas: Dict[str, torch.Tensor] = {}
+    for lo in loras:
+        org = getattr(lo, "org_module", None)
+        org = org[0] if isinstance(org, (list, tuple)) and org else org
+        name = by_id.get(id(org))
+        if name is None:
+            raise UnsupportedAdapterError(f"LyCORIS module {getattr(lo, 'lora_name', '?')} wraps a module outside the decoder")
+        if not isinstance(org, torch.nn.Linear):
+            raise UnsupportedAdapterError(f"LyCORIS module on non-Linear layer {name}")
+        d = _lokr_delta(lo)
+        if tuple(d.shape) != tuple(org.weight.shape):
+            d = d.reshape(org.weight.shape)
+        deltas[name] = deltas[name] + d if name in deltas else d
+    return deltas
+
+
 def effective_decoder_state(decoder) -> Dict[str, torch.Tensor]:
     """`state_dict()` of the PLAIN decoder that computes what `decoder` computes right now.
 
@@ -34,10 +92,10 @@ def effective_decoder_state(decoder) -> Dict[str, torch.Tensor]:
     dict keys gain a `base_model.model.` prefix and `.base_layer` infixes.  This folds every ACTIVE
     adapter into its base weight, W + sum_a scaling[a] * B_a @ A_a (what PEFT's `get_delta_weight` adds
     on merge), and restores the reference key names so pack_dit can walk it.  A decoder without
-    adapters is returned as its own state dict.  LoKr / LyCORIS nets (`_lycoris_net`,
-    lifecycle.py:101-156) are not Linear-foldable here: UnsupportedAdapterError."""
-    if getattr(decoder, "_lycoris_net", None) is not None:
-        raise UnsupportedAdapterError("decoder carries a LyCORIS (LoKr) net; the B200 packer folds PEFT LoRA only")
+    adapters is returned as its own state dict.  LoKr / LyCORIS nets (`_lycoris_net`, lifecycle.py:101-156) are
+    folded the same way, W + multiplier * scale * kron(w1, w2) (see _lokr_delta); DoRA-style weight decomposition
+    and Tucker (conv) factors are not linear folds: UnsupportedAdapterError."""
+    lyco = _lycoris_deltas(decoder)
     deltas: Dict[str, torch.Tensor] = {}
     for name, mod in decoder.named_modules():
         if not (hasattr(mod, "base_layer") and hasattr(mod, "lora_A") and hasattr(mod, "lora_B")):
@@ -72,6 +130,8 @@ def effective_decoder_state(decoder) -> Dict[str, torch.Tensor]:
         t = v.detach()
         if owner is not None and key.endswith(".weight") and owner in deltas:
             t = (t.float() + deltas[owner].to(t.device)).to(t.dtype)
+        if key.endswith(".weight") and k[: -len(".weight")] in lyco:
+            t = (t.float() + lyco[k[: -len(".weight")]].to(t.device)).to(t.dtype)
         for pre in ("base_model.model.", "base_model."):
             if key.startswith(pre):
                 key = key[len(pre):]

@@ -144,6 +144,7 @@ class B200Sampler:
         cover_steps = int(n * audio_cover_strength)
         self.dit.bind(B, T, enc.shape[1])
         self.dit.set_condition(enc)
+        self.dit.prepare_timesteps(t_sched)  # timestep cache: a no-op once this schedule has been seen
         # loop state in the handle's static I/O slots: no per-step copies (see generate_base)
         xin, ctxin, vt = self.dit.io_views()
         ctxin.copy_(ctx)
@@ -231,6 +232,7 @@ class B200Sampler:
         Bc = enc.shape[0]
         self.dit.bind(Bc, T, enc.shape[1])
         self.dit.set_condition(enc)
+        self.dit.prepare_timesteps(ts[:-1])  # timestep cache: a no-op once this schedule has been seen
         # The loop state lives in the DiT handle's static I/O slots (xin = [xt | xt copy for the unconditional
         # half], ctx, vt), so a step is: set t -> CUDA graph -> guidance -> Euler, with no copies in between.
         xin, ctxin, vt = self.dit.io_views()

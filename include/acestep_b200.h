@@ -77,8 +77,8 @@ void ace_dit_destroy(AceDit* dit);
 
 /* Workspace for an effective batch `bc` (songs x (2 if CFG)), `t` latent frames, `e` condition tokens. */
 size_t ace_dit_workspace_bytes(const AceDit* dit, int bc, int t, int e);
-/* Binds shapes + workspace: encodes all TMA descriptors and (unless ACE_NO_GRAPH=1) captures the
- * denoising step into a CUDA graph on first use.  Re-bind when bc / t / e or the workspace change. */
+/* Binds shapes + workspace: encodes all TMA descriptors and captures the denoising step into a CUDA
+ * graph on first use.  Re-bind when bc / t / e or the workspace change. */
 int ace_dit_bind(AceDit* dit, int bc, int t, int e, void* d_workspace, size_t workspace_bytes);
 
 /* condition_embedder + cross-attention K/V of all layers for d_enc [bc, e, hidden] (bf16); replaces
@@ -90,6 +90,14 @@ int ace_dit_set_condition(AceDit* dit, const uint16_t* d_enc, void* stream);
  * rounded to the model dtype by the caller) -> d_vt [bc,t,64] (bf16). */
 int ace_dit_step(AceDit* dit, const uint16_t* d_xt, const uint16_t* d_ctx, const float* h_t,
                  uint16_t* d_vt, void* stream);
+
+/* Everything of the forward that depends on the timestep only (TimestepEmbedding.forward :245-251, the six
+ * modulation vectors of every layer :490-496, the output norm's :1488-1493, and the AdaLN shift terms folded into
+ * bias rows of the consuming GEMMs) is kept in a per-handle cache keyed by the VALUE of t: ace_dit_step computes an
+ * entry the first time it sees a timestep (about a millisecond) and finds it afterwards — a sampler visits the same
+ * 8 / 27 / 60 values for every song.  This call fills the entries of a whole schedule in one batched pass
+ * (h_t: n host floats, rounded like ace_dit_step's; duplicates and cached values are skipped).  Optional. */
+int ace_dit_prepare_timesteps(AceDit* dit, const float* h_t, int n, void* stream);
 
 /* One forward through layers [0, n_layers) that exports the CROSS-ATTENTION PROBABILITIES of each of them,
  * d_probs [n_layers][bc][heads][S][e] bf16 with S = ceil(t / 2) tokens, and stops there — what

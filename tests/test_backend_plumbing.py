@@ -204,9 +204,53 @@ def test_effective_decoder_state_folds_active_lora():
     assert torch.equal(effective_decoder_state(m)["q_proj.weight"], lin.base_layer.weight.detach())
     plain = torch.nn.Linear(4, 3)
     assert set(effective_decoder_state(plain)) == {"weight", "bias"}
-    plain._lycoris_net = object()
+    plain._lycoris_net = object()  # a net without a `loras` list cannot be folded: loud, not silent
     with pytest.raises(UnsupportedAdapterError):
         effective_decoder_state(plain)
+
+
+def test_effective_decoder_state_folds_lycoris_lokr():
+    """LoKr (handler/lora/lifecycle.py:101-156): `decoder._lycoris_net.loras` wrap the decoder's own Linear modules;
+    the fold is W + multiplier * scale * kron(w1, w2) with either factor optionally low-rank (w_a @ w_b), the
+    module's own get_diff_weight taking precedence; multiplier 0 (set_use_lora(False), controls.py:13-31) folds
+    nothing; DoRA / Tucker variants are rejected."""
+    from acestep_b200.pack import UnsupportedAdapterError, effective_decoder_state
+
+    class Dec(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = torch.nn.Linear(6, 4, bias=False)
+            self.o_proj = torch.nn.Linear(4, 6, bias=False)
+
+    class Lokr:  # duck-typed LokrModule
+        def __init__(self, org, w1, w2=None, w2a=None, w2b=None, scale=1.0, multiplier=1.0):
+            self.org_module, self.lora_name = [org], "lycoris_x"
+            self.lokr_w1, self.lokr_w2, self.lokr_w2_a, self.lokr_w2_b = w1, w2, w2a, w2b
+            self.scale, self.multiplier = scale, multiplier
+
+    class Net:
+        def __init__(self, loras):
+            self.loras = loras
+
+    g = torch.Generator().manual_seed(3)
+    dec = Dec()
+    w1, w2 = torch.randn(2, 3, generator=g), torch.randn(2, 2, generator=g)          # kron -> [4, 6]
+    v1, v2a, v2b = torch.randn(3, 2, generator=g), torch.randn(2, 1, generator=g), torch.randn(1, 2, generator=g)  # -> [6, 4]
+    a, b = Lokr(dec.q_proj, w1, w2=w2, multiplier=0.5), Lokr(dec.o_proj, v1, w2a=v2a, w2b=v2b, scale=0.25, multiplier=2.0)
+    dec._lycoris_net = Net([a, b])
+    sd = effective_decoder_state(dec)
+    assert set(sd) == {"q_proj.weight", "o_proj.weight"}
+    assert torch.allclose(sd["q_proj.weight"], dec.q_proj.weight.detach() + 0.5 * torch.kron(w1, w2))
+    assert torch.allclose(sd["o_proj.weight"], dec.o_proj.weight.detach() + 2.0 * 0.25 * torch.kron(v1, v2a @ v2b))
+    a.multiplier = b.multiplier = 0.0  # adapter switched off through its multiplier
+    sd0 = effective_decoder_state(dec)
+    assert torch.equal(sd0["q_proj.weight"], dec.q_proj.weight.detach()) and torch.equal(sd0["o_proj.weight"], dec.o_proj.weight.detach())
+    a.multiplier = 1.0
+    a.get_diff_weight = lambda m: (torch.full((4, 6), 3.0) * m, None)  # the library's own method wins
+    assert torch.allclose(effective_decoder_state(dec)["q_proj.weight"], dec.q_proj.weight.detach() + 3.0)
+    a.wd = True
+    with pytest.raises(UnsupportedAdapterError):
+        effective_decoder_state(dec)
 
 
 def test_lora_mutators_trigger_a_repack():

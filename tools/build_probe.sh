@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_bin
 CS=ace-step-1.5-for-windows_b200/csrc
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -lcuda"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -lcuda -DACE_PROBE"
 nvcc $FLAGS -o tools/_bin/gemm_probe tools/gemm_probe.cu $CS/runtime.cu
 nvcc $FLAGS -DACE_GEMM_TIMING -o tools/_bin/gemm_timing tools/gemm_timing.cu $CS/runtime.cu
 nvcc $FLAGS -DACE_GEMM_TIMING -o tools/_bin/gemm_l2_probe tools/gemm_l2_probe.cu $CS/runtime.cu

@@ -30,16 +30,42 @@ int main() {
       printf("plan: %s\n", get_error());
       return 1;
     }
+    // deferred-norm side buffers (epilogues.cuh NormOut / NormIn)
+    bf16 *Gn, *Cv;
+    float *Ssp, *Bs;
+    int* Slot;
+    cudaMalloc(&Gn, (size_t)M * N * 2);
+    cudaMalloc(&Cv, (size_t)2 * N * 2);
+    cudaMalloc(&Ssp, (size_t)M * 32 * 4);
+    cudaMalloc(&Bs, (size_t)2 * N * 4);
+    cudaMalloc(&Slot, 64);
+    cudaMemset(Cv, 0, (size_t)2 * N * 2);
+    cudaMemset(Ssp, 0, (size_t)M * 32 * 4);
+    cudaMemset(Bs, 0, (size_t)2 * N * 4);
+    cudaMemset(Slot, 0, 64);
     EpiGatedResid epi{H, (long)N, G, (long)N, S};
     EpiGatedResid epi_nogate{H, (long)N, nullptr, 0, S};
     EpiBias epi_bias{H, (long)N, nullptr};
-    for (int rep = 0; rep < 5; ++rep) {
+    NormOut no{Gn, (long)N, Cv, (long)N, Ssp, N / 64, Slot, S};
+    NormIn ni{Ssp, 32, 1.0f / 2048.0f, 1e-6f, Bs, (long)N, Slot, S};
+    EpiGatedResid epi_no{H, (long)N, G, (long)N, S, Slot, no};
+    EpiQKV epi_qkv{H, (long)N, N / 2, N / 4, G, G, nullptr, nullptr, S, 1e-6f};
+    EpiQKV epi_qkv_ni{H, (long)N, N / 2, N / 4, G, G, nullptr, nullptr, S, 1e-6f, ni};
+    EpiSwiGLU epi_sw{H, (long)N / 2};
+    EpiSwiGLU epi_sw_ni{H, (long)N / 2, ni};
+    for (int rep = 0; rep < 10; ++rep) {
       if (rep < 2) cudaMemset(flush, rep, 256u << 20);  // reps 0,1: cold L2; rep 2: warm
       cudaDeviceSynchronize();
-      // rep 2: gated residual (warm); rep 3: residual without gate; rep 4: plain store (EpiBias)
+      // rep 2: gated residual (warm); rep 3: residual without gate; rep 4: plain store (EpiBias); rep 5: gated
+      // residual + NormOut; 6 / 7: EpiQKV without / with NormIn; 8 / 9: EpiSwiGLU without / with NormIn
       if (rep <= 2) launch_gemm(p, epi, 0);
       else if (rep == 3) launch_gemm(p, epi_nogate, 0);
-      else launch_gemm(p, epi_bias, 0);
+      else if (rep == 4) launch_gemm(p, epi_bias, 0);
+      else if (rep == 5) launch_gemm(p, epi_no, 0);
+      else if (rep == 6) launch_gemm(p, epi_qkv, 0);
+      else if (rep == 7) launch_gemm(p, epi_qkv_ni, 0);
+      else if (rep == 8) launch_gemm(p, epi_sw, 0);
+      else launch_gemm(p, epi_sw_ni, 0);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("kernel: %s\n", cudaGetErrorString(e));
