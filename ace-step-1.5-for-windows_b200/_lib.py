@@ -74,6 +74,8 @@ SIGNATURES = {
     "ace_vae_encode_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
     "ace_vae_decode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "ace_vae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "ace_vae_encode_moments": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ace_vae_posterior_sample": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "ace_dit_io_slots": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "ace_enc_packed_elems": (C.c_size_t, [C.POINTER(AceEncConfig)]),
     "ace_enc_create": (C.c_int, [C.POINTER(_P), C.POINTER(AceEncConfig), _P, C.c_size_t]),

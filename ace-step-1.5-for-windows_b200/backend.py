@@ -194,7 +194,12 @@ class B200BackendMixin:
         """audio [B, 2, N] -> sampled latents [B, 64, N // 1920]; cf. _mlx_vae_encode_sample."""
         if self.b200_vae is None:
             raise RuntimeError("B200 VAE encode requested but b200_vae is not initialized.")
-        return self.b200_vae.encode(audio_torch, sample=True)
+        # Every caller of tiled_encode (infer_refer_latent / _encode_audio_to_latents / _prepare_target_latents_and_wavs,
+        # handler/conditioning_embed.py:18-69, batch_prep.py:63-76, conditioning_target.py:18-107) passes
+        # offload_latent_to_cpu=True and moves the result straight back to the device; here the latents never
+        # leave it, and the posterior moments of a clip seen before (the same reference audio across requests)
+        # come from a device-resident cache: only the posterior noise is drawn again.
+        return self.b200_vae.encode_cached(audio_torch, sample=True)
 
 
 # ---------------------------------------------------------------------------------------------

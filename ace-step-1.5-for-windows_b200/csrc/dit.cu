@@ -78,6 +78,8 @@ struct AceDit {
   bf16 *xin, *ctxin, *vout;  // static I/O slots so the graph never sees caller pointers
   bf16 *xcat, *h, *hn, *qkv, *attn, *qc, *act, *enc_e, *ckv;
   bf16 *rope_cos, *rope_sin;
+  CUtensorMap tm_h, tm_hn;  // [D cols, M rows] maps over h / hn for the GEMM tail path (EpiGatedResid::tail_box)
+  int use_tma = 1;
   float* ssp;     // [M][D / 64] per-row partial sums of squares of h (NormOut -> NormIn)
   int* slot_dev;  // [16] timestep-cache entry of each batch item for the step in flight
   uint8_t* splitk = nullptr;  // split-K scratch (partial tiles + counters), shared by all GEMMs of the step
@@ -313,6 +315,13 @@ int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs
   auto norm_in = [&](const float* bs) {  // consumer side
     return NormIn{d->ssp, nss, 1.0f / (float)D, eps, bs, es32, slot, S};
   };
+  auto gated = [&](const bf16* gate, long gate_ld, const NormOut& no) {  // h += gate * y, feeding the next norm
+    EpiGatedResid e{d->h, (long)D, gate, gate_ld, S, slot, no};
+    e.use_tma = d->use_tma;
+    e.tm_h = d->tm_h;
+    e.tm_g = d->tm_hn;
+    return e;
+  };
 
   ACE_PROPAGATE(launch_concat_patches(d->ctxin, d->xin, d->xcat, Bc, d->T, d->Tpad, st));
   LAUNCH_GEMM(d->plan_in, EpiBias{d->h, (long)D, d->proj_in_b, norm_out(cv0, es16)}, st);
@@ -325,8 +334,10 @@ int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs
     LAUNCH_GEMM(p.qkv, EpiQKV{d->qkv, QKVW, NQ, NKV, w.self_qn, w.self_kn, d->rope_cos, d->rope_sin, S, eps,
                               norm_in(bsq0 + (size_t)l * QKVW)}, st);
     if (!skip_attn) ACE_PROPAGATE(launch_attention_tc(p.self_attn, st));
-    // h += gate_msa * o_proj(attn); feeds the cross-attention RMSNorm (constant weight vector, no shift)
-    LAUNCH_GEMM(p.self_o, EpiGatedResid{d->h, (long)D, mod + 2 * D, es16, S, slot, norm_out(w.cross_norm, 0)}, st);
+    // h += gate_msa * o_proj(attn); feeds the cross-attention RMSNorm.  That norm has no modulation, so its
+    // weight vector is folded into the cross q_proj weight at pack time (pack.py) and the q GEMM reads h itself:
+    // this epilogue only adds the row statistics (no g).
+    LAUNCH_GEMM(p.self_o, gated(mod + 2 * D, es16, NormOut{nullptr, 0, nullptr, 0, d->ssp, nss, slot, S}), st);
     // --- cross attention ---
     LAUNCH_GEMM(p.cross_q, EpiQKV{d->qc, (long)NQ, NQ, 0, w.cross_qn, w.cross_kn, nullptr, nullptr, S, eps,
                                   norm_in(nullptr)}, st);
@@ -339,14 +350,12 @@ int enqueue_forward(AceDit* d, cudaStream_t st, bf16* probs = nullptr, int probs
     }
     if (!skip_attn) ACE_PROPAGATE(launch_attention_tc(p.cross_attn, st));
     // h += o_proj(attn); feeds the MLP's AdaLN norm
-    LAUNCH_GEMM(p.cross_o, EpiGatedResid{d->h, (long)D, nullptr, 0, S, slot,
-                                         norm_out(cv0 + ((size_t)l * 2 + 1) * D, es16)}, st);
+    LAUNCH_GEMM(p.cross_o, gated(nullptr, 0, norm_out(cv0 + ((size_t)l * 2 + 1) * D, es16)), st);
     // --- MLP ---
     LAUNCH_GEMM(p.gate_up, EpiSwiGLU{d->act, (long)I, norm_in(bsg0 + (size_t)l * 2 * I)}, st);
     // h += gate_mlp * down(act); feeds the next layer's self-attention norm, or the output norm (:1488-1493)
-    LAUNCH_GEMM(p.down, EpiGatedResid{d->h, (long)D, mod + 5 * D, es16, S, slot,
-                                      l + 1 < L ? norm_out(cv0 + (size_t)(l + 1) * 2 * D, es16)
-                                                : norm_out(cout0, es16)}, st);
+    LAUNCH_GEMM(p.down, gated(mod + 5 * D, es16, l + 1 < L ? norm_out(cv0 + (size_t)(l + 1) * 2 * D, es16)
+                                                           : norm_out(cout0, es16)), st);
   }
   LAUNCH_GEMM(d->plan_out, EpiProjOut{d->vout, d->proj_out_b, S, d->T, norm_in(bso0)}, st);
   return ACE_OK;
@@ -584,6 +593,12 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
   carve_workspace(d, d->ws, bc, t, e);
   const int D = d->D, I = d->I, NQ = d->NQ, NKV = d->NKV, M = d->M;
   const int ME = bc * e;
+  ACE_PROPAGATE(encode_tmap_2d(&d->tm_h, d->h, (uint64_t)D, (uint64_t)M, (uint64_t)D * sizeof(bf16), 128u));
+  ACE_PROPAGATE(encode_tmap_2d(&d->tm_hn, d->hn, (uint64_t)D, (uint64_t)M, (uint64_t)D * sizeof(bf16), 128u));
+  {
+    const char* nt = probe_env("ACE_NO_TMA_TAIL");  // probe builds only: A/B of the epilogue tail path
+    d->use_tma = (nt && nt[0] == '1') ? 0 : 1;
+  }
   ACE_PROPAGATE(make_gemm_plan(&d->plan_in, d->xcat, M, 384, 384, d->proj_in_w, D, 384, M, 1, nullptr, 0));
   ACE_PROPAGATE(make_gemm_plan(&d->plan_out, d->hn, M, D, D, d->proj_out_w, 128, D, M, 1, nullptr, 0));
   d->lp.resize(d->L);
@@ -592,7 +607,7 @@ int ace_dit_bind(AceDit* d, int bc, int t, int e, void* ws, size_t ws_bytes) {
     LayerPlans& p = d->lp[l];
     ACE_PROPAGATE(make_gemm_plan(&p.qkv, d->hn, M, D, D, w.self_qkv, NQ + 2 * NKV, D, M, 1, nullptr, 0));
     ACE_PROPAGATE(make_gemm_plan(&p.self_o, d->attn, M, NQ, NQ, w.self_o, D, NQ, M, 1, nullptr, -192));
-    ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->hn, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 0));
+    ACE_PROPAGATE(make_gemm_plan(&p.cross_q, d->h, M, D, D, w.cross_q, NQ, D, M, 1, nullptr, 0));  // A = h, see enqueue_forward
     ACE_PROPAGATE(make_gemm_plan(&p.cross_o, d->attn, M, NQ, NQ, w.cross_o, D, NQ, M, 1, nullptr, -192));
     ACE_PROPAGATE(make_gemm_plan(&p.gate_up, d->hn, M, D, D, w.gate_up, 2 * I, D, M, 1, nullptr, 0));
     ACE_PROPAGATE(make_gemm_plan(&p.down, d->act, M, I, I, w.down, D, I, M, 1, nullptr, -192));

@@ -27,6 +27,13 @@ namespace ace {
 
 constexpr int EPI_STAGE_BYTES = 4096;  // per warp: 32 rows x 64 bf16
 
+#ifdef ACE_GEMM_TIMING
+__device__ long long g_tail_clk[32];  // probe builds: block 0 / thread 128, clock64 at the steps of the tail path
+#define ACE_TCLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 128) g_tail_clk[i] = clock64(); } while (0)
+#else
+#define ACE_TCLK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void l1_prefetch(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
@@ -144,11 +151,13 @@ struct WarpStage {
 // Fewer bf16 roundings than the reference's chain (one on g instead of three on hn), same fp32 statistics.
 // ---------------------------------------------------------------------------------------------
 struct NormOut {
-  bf16* g;            // [M, ldg] A operand of the consuming GEMM; null = this epilogue feeds no norm
+  bf16* g;            // [M, ldg] A operand of the consuming GEMM; null with ssp set = statistics only (the consumer
+                      // reads h itself: a norm without modulation has its weight folded into the consumer's W)
   long ldg;
   const bf16* cvec;   // c vector(s): cvec + slot[b] * c_stride  (c_stride 0: one constant vector)
   long c_stride;
-  float* ssp;         // [M, nss] partial sums of squares, nss = D / 64, slot j = columns [64 j, 64 j + 64)
+  float* ssp;         // [M, nss] partial sums of squares, nss = D / 64, slot j = columns [64 j, 64 j + 64);
+                      // null = this epilogue feeds no norm at all
   int nss;
   const int* slot;    // [batch] timestep-cache entry of each batch item (null with c_stride 0)
   int S;              // rows per batch item
@@ -163,6 +172,20 @@ struct NormOut {
   // writes this row's partial, turns the slab into g in place and stores it.
   __device__ __forceinline__ void emit(const WarpStage& stg, int lane, int row, int row0, int col, int ncols,
                                        int M) const {
+    if (g == nullptr) {  // statistics only
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 r = *stg.at(lane, q);
+        float x0, x1;
+        unpack_bf16x2(r.x, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(r.y, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(r.z, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(r.w, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      }
+      if (row < M) ssp[(size_t)row * nss + (col >> 6)] = ss;
+      return;
+    }
     const int b = row < M ? row / S : 0;
     const uint4* cp = reinterpret_cast<const uint4*>(cvec + (c_stride ? (long)__ldg(slot + b) * c_stride : 0) + col);
     float ss = 0.f;
@@ -240,6 +263,7 @@ struct NormIn {
 // out[row, n] = bf16(acc + bias[n])                       (proj_in, condition_embedder)
 struct EpiBias {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kTmaTail = false;
   bf16* out;
   long ldo;
   const bf16* bias;  // may be null
@@ -271,7 +295,7 @@ struct EpiBias {
       stg.store_rows(lane, ncols, [&](int r) -> bf16* {
         return row0 + r < M ? out + (size_t)(row0 + r) * ldo + n0 + s : nullptr;
       });
-      if (no.g != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
+      if (no.ssp != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
     }
   }
 };
@@ -280,6 +304,7 @@ struct EpiBias {
 // timestep cache (dit.cu); row r of the GEMM is cache entry first + r.
 struct EpiStoreF32 {
   static constexpr bool kHalfTile = true;
+  static constexpr bool kTmaTail = false;
   float* out;
   long ldo;
   __device__ __forceinline__ float prefetch(int, int, int, int, const WarpStage&) const { return 0.f; }
@@ -305,6 +330,7 @@ struct EpiStoreF32 {
 // Follows AceStepAttention.forward (modeling_acestep_v15_turbo.py:301, 317-318, 335-340).
 struct EpiQKV {
   static constexpr bool kHalfTile = false;
+  static constexpr bool kTmaTail = false;
   bf16* out;
   long ldo;
   int nq, nk;
@@ -421,6 +447,11 @@ struct EpiQKV {
 // AceStepDiTLayer.forward lines 508, 523, 530.
 struct EpiGatedResid {
   static constexpr bool kHalfTile = true;
+  // The CTA-pair kernel runs the LAST tile of every CTA (every tile of a single-wave problem: M = 1500 at N = 2048)
+  // through tail_box() instead of run(): the residual tile arrives by TMA in the operand ring's freed slots while
+  // the main loop drains, the update happens in place in shared memory, and h (and g) leave by TMA stores — the
+  // epilogue warps only read TMEM and touch shared memory.  Needs the tensor maps below (use_tma).
+  static constexpr bool kTmaTail = true;
   bf16* h;  // read-modify-write in place
   long ldh;
   const bf16* gate;  // gate vector of batch item b at gate + gsel(b) * gate_ld, gsel(b) = slot ? slot[b] : b; or null
@@ -428,6 +459,90 @@ struct EpiGatedResid {
   int S;  // rows per batch item
   const int* slot = nullptr;  // [batch] timestep-cache entry per batch item (the DiT); null: gate is [batch, gate_ld]
   NormOut no = {};            // no.g != null: also feed the next norm
+  int use_tma = 0;            // tm_h / tm_g valid: [N cols, M rows] bf16 maps over h and no.g, box [64 x 128], SWIZZLE_128B
+  CUtensorMap tm_h = {};
+  CUtensorMap tm_g = {};
+  // One 64-column box of the tail path.  `hbox`: this CTA's [128 rows x 64 cols] residual box as TMA wrote it
+  // (128-byte rows, 16-byte chunks XOR-swizzled by row & 7), updated IN PLACE to the new h; `gbox`: same layout,
+  // receives g.  `r` = this thread's row inside the CTA tile, `row` its global row, `col` the box's first column.
+  // Called by every tail-path thread while the main loop is still running: resolves this row's gate / c vectors
+  // (the timestep-cache indirection is a dependent L2 round trip — about 900 cycles that must not sit between the
+  // accumulator and the stores) and pulls their lines for columns [col0, col0 + ncols) into L1.
+  struct TailPre {
+    const bf16* grow;  // this row's gate vector (column 0) or null
+    const bf16* crow;  // this row's c vector (column 0) or null
+  };
+  __device__ __forceinline__ TailPre tail_prefetch(int row, int M, int N, int col0, int ncols) const {
+    TailPre t{nullptr, nullptr};
+    if (gate != nullptr) t.grow = gate + (size_t)gsel(row, M) * gate_ld;
+    if (no.g != nullptr) {
+      const int b = row < M ? row / S : 0;
+      t.crow = no.cvec + (no.c_stride ? (long)__ldg(no.slot + b) * no.c_stride : 0);
+    }
+    for (int c = col0; c < col0 + ncols && c < N; c += 64) {
+      if (t.grow != nullptr) l1_prefetch(t.grow + c);
+      if (t.crow != nullptr) l1_prefetch(t.crow + c);
+    }
+    return t;
+  }
+  template <class Acc>
+  __device__ __forceinline__ void tail_box(const Acc& acc, int acc_col, int r, int row, int col, int M,
+                                           uint8_t* hbox, uint8_t* gbox, const TailPre& pre) const {
+    uint32_t raw[2][32];
+    ACE_TCLK(16);
+    acc.load32_nowait(acc_col, raw[0]);
+    acc.load32_nowait(acc_col + 32, raw[1]);
+    const uint4* gp = reinterpret_cast<const uint4*>(pre.grow + col);
+    const uint4* cp = reinterpret_cast<const uint4*>(pre.crow + col);
+    uint4 gv[8], cv[8];
+    if (gate != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gv[q] = __ldg(gp + q);
+    }
+    if (no.g != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cv[q] = __ldg(cp + q);
+    }
+    ACE_TCLK(17);
+    tmem_ld_wait();
+    ACE_TCLK(18);
+    float ss = 0.f;
+    const uint32_t rowoff = (uint32_t)r * 128u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t off = rowoff + (uint32_t)((q ^ (r & 7)) << 4);
+      uint4* hs = reinterpret_cast<uint4*>(hbox + off);
+      uint4 res = *hs;
+      const uint32_t* a = &raw[q >> 2][(q & 3) * 8];
+      uint4 pv;
+      pv.x = pack_bf16x2(__uint_as_float(a[0]), __uint_as_float(a[1]));
+      pv.y = pack_bf16x2(__uint_as_float(a[2]), __uint_as_float(a[3]));
+      pv.z = pack_bf16x2(__uint_as_float(a[4]), __uint_as_float(a[5]));
+      pv.w = pack_bf16x2(__uint_as_float(a[6]), __uint_as_float(a[7]));
+      if (gate != nullptr) {
+        pv.x = bmul2(pv.x, gv[q].x); pv.y = bmul2(pv.y, gv[q].y);
+        pv.z = bmul2(pv.z, gv[q].z); pv.w = bmul2(pv.w, gv[q].w);
+      }
+      res.x = badd2(res.x, pv.x); res.y = badd2(res.y, pv.y);
+      res.z = badd2(res.z, pv.z); res.w = badd2(res.w, pv.w);
+      *hs = res;
+      if (no.ssp != nullptr) {
+        float x0, x1;
+        unpack_bf16x2(res.x, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(res.y, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(res.z, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+        unpack_bf16x2(res.w, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+      }
+      if (no.g != nullptr) {
+        uint4 gq;
+        gq.x = bmul2(res.x, cv[q].x); gq.y = bmul2(res.y, cv[q].y);
+        gq.z = bmul2(res.z, cv[q].z); gq.w = bmul2(res.w, cv[q].w);
+        *reinterpret_cast<uint4*>(gbox + off) = gq;
+      }
+    }
+    ACE_TCLK(19);
+    if (no.ssp != nullptr && row < M) no.ssp[(size_t)row * no.nss + (col >> 6)] = ss;
+  }
   __device__ __forceinline__ int gsel(int row, int M) const {
     const int b = row < M ? row / S : 0;
     return slot != nullptr ? __ldg(slot + b) : b;
@@ -493,7 +608,7 @@ struct EpiGatedResid {
         }
       }
       stg.store_rows(lane, ncols, addr);
-      if (no.g != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
+      if (no.ssp != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
       if (has_next) stg.commit_rows(lane, nxt);
     }
   }
@@ -503,6 +618,7 @@ struct EpiGatedResid {
 // matching up features; out[row, f0 + i] = bf16(bf16(silu(g)) * u).   (Qwen3MLP.forward)
 struct EpiSwiGLU {
   static constexpr bool kHalfTile = false;
+  static constexpr bool kTmaTail = false;
   bf16* out;
   long ldo;
   NormIn ni = {};  // deferred AdaLN of the MLP norm (see NormIn)
@@ -547,6 +663,7 @@ struct EpiSwiGLU {
 // vt[b, 2*s + k, o]; frames >= T (the odd-length pad) are cropped.  (turbo modeling :1284-1294,1498)
 struct EpiProjOut {
   static constexpr bool kHalfTile = false;
+  static constexpr bool kTmaTail = false;
   bf16* vt;  // [Bc, T, 64]
   const bf16* bias;  // [64]
   int S, T;
@@ -606,6 +723,7 @@ __device__ __forceinline__ float snake_f(float x, float a, float ib) {
 // on the whole decode (round-1 A/B measurement; the raw log was not kept — the kernel-level ncu rows of that build are in profiles/r1_v3_ncu_full_summary.txt), the 16-byte-per-thread stores merge in L2.
 struct EpiConv {
   static constexpr bool kHalfTile = true;  // run<64> on a 64-column half tile is valid
+  static constexpr bool kTmaTail = false;
   bf16* out_main;        // may be null
   bf16* out_snake;       // may be null
   const bf16* resid;     // may be null; same indexing as out

@@ -123,6 +123,10 @@ struct AccTmem {
   __device__ __forceinline__ void load32(int col, float (&v)[32]) const {
     tmem_ld_32x32(taddr + (uint32_t)col, v);
   }
+  // issue only; the caller runs tmem_ld_wait() once after several of these
+  __device__ __forceinline__ void load32_nowait(int col, uint32_t (&r)[32]) const {
+    tmem_ld_32x32_nowait(taddr + (uint32_t)col, r);
+  }
 };
 struct AccSmem {
   const float* p;  // &reduced[row_in_slice * BN + first column of this warp]
@@ -426,7 +430,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 template <int BN, int STAGES, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                const GemmShape shp, const Epi epi) {
+                const GemmShape shp, const __grid_constant__ Epi epi) {
   // BN = 256, or 192 for epilogues that accept 64-column sub-tiles: 256 x 192 pair tiles turn the
   // 48-tile N = 2048 problems of the DiT (48 of 74 clusters busy) into 66 tiles (66 of 74).
   static_assert(BN == 256 || (BN == 192 && Epi::kHalfTile), "pair tile width");
@@ -444,6 +448,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* resid_bar = bars + 2 * STAGES + 6;  // [4]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -466,6 +471,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&resid_bar[i], 1);  // tail path: one per 64-column residual box
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -485,6 +491,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int total_kb = shp.ntaps * shp.kblocks_per_tap;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  // Tail path (Epi::kTmaTail with its tensor maps set): the last tile of this cluster ends in tail_box() — see the
+  // producer's residual loads below and the epilogue's tail branch.
+  bool tma_tail = false;
+  if constexpr (Epi::kTmaTail) tma_tail = epi.use_tma != 0;
+  constexpr int NBOX = BN / 64;
+  const int my_tiles = cluster_id < num_tiles ? (num_tiles - 1 - cluster_id) / num_clusters + 1 : 0;
+  const int last_tile = cluster_id + (my_tiles - 1) * num_clusters;
 
   if (warp == 0) {
     // ---------------- TMA producer (both CTAs; warp-uniform loop, one elected lane issues) --------
@@ -516,6 +529,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
+        }
+      }
+    }
+    if constexpr (Epi::kTmaTail) {
+      // Residual boxes of the last tile: they ride the operand ring as NBOX extra "k-blocks" that nobody feeds to
+      // the tensor core — box i lands in the A part of the next ring slot as soon as the MMAs that read it have
+      // retired (5 k-blocks before the main loop ends), i.e. it is in shared memory before the accumulator is.
+      if (tma_tail && my_tiles > 0) {
+        const int m0 = (last_tile % m_tiles) * 256 + (int)rank * 128;
+        const int n0 = (last_tile / m_tiles) * BN;
+        for (int i = 0; i < NBOX; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elected && n0 + 64 * i < shp.N) {
+            mbar_arrive_expect_tx(&resid_bar[i], L::A_BYTES);
+            tma_load_2d(sA + stage * L::A_BYTES, &epi.tm_h, &resid_bar[i], n0 + 64 * i, m0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -588,6 +621,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
       const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
+      if constexpr (Epi::kTmaTail) {
+        if (tma_tail && tile == last_tile) {
+          // ---- tail path: residual already in shared memory (TMA), update in place, h / g leave by TMA ----
+          const int grp = (warp - 4) >> 2;                 // column group: boxes [2 grp, 2 grp + 2) of the tile
+          const int r = quarter * 32 + lane;               // row inside this CTA's 128-row tile
+          const int ring0 = (int)(((long)my_tiles * total_kb) % STAGES);  // ring slot of residual box 0
+          const int tile_n0 = (tile / m_tiles) * BN;
+          const auto tpre = epi.tail_prefetch(m0 + r, shp.M, shp.N, tile_n0 + 128 * grp, 128);
+          mbar_wait(&tfull_bar[as], aphase);
+          if (threadIdx.x == 128) ACE_STAMP(5);
+          tcgen05_fence_after();
+          __syncwarp();
+          AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN)};
+#pragma unroll 1
+          for (int bi = 2 * grp; bi < 2 * grp + 2 && bi < NBOX; ++bi) {
+            const int col = tile_n0 + 64 * bi;
+            if (col >= shp.N) break;  // group-uniform
+            uint8_t* hbox = sA + ((ring0 + bi) % STAGES) * L::A_BYTES;
+            uint8_t* gbox = sB + bi * L::A_BYTES;  // the B ring is idle by now (all MMAs retired)
+            ACE_TCLK(4 * (bi & 1) + 0);
+            mbar_wait(&resid_bar[bi], 0);
+            ACE_TCLK(4 * (bi & 1) + 1);
+            epi.tail_box(acc, 64 * bi, r, m0 + r, col, shp.M, hbox, gbox, tpre);
+            ACE_TCLK(4 * (bi & 1) + 2);
+            fence_proxy_async_smem();  // this thread's smem writes -> visible to the TMA store
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (quarter == 0 && elect_one()) {
+              tma_store_2d(&epi.tm_h, hbox, col, m0);
+              if (epi.no.g != nullptr) tma_store_2d(&epi.tm_g, gbox, col, m0);
+              tma_store_commit();
+            }
+            ACE_TCLK(4 * (bi & 1) + 3);
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+          ACE_TCLK(8);
+          if (quarter == 0) tma_store_wait_all();  // (only the lane that issued has pending groups)
+          ACE_TCLK(9);
+          if (threadIdx.x == 128) ACE_STAMP(6);
+          continue;
+        }
+      }
       float pre = 0.f;
       if (live) pre = epi.prefetch(m0 + quarter * 32 + lane, n0, shp.M, shp.N, stg);
       mbar_wait(&tfull_bar[as], aphase);

@@ -498,9 +498,39 @@ int ace_vae_decode(AceVae* v, const uint16_t* d_z, int frames, float* d_wav, voi
   return ACE_OK;
 }
 
+// Shared body of ace_vae_encode / ace_vae_encode_moments: d_z (posterior sample or mean) and / or d_moments.
+static int vae_encode_impl(AceVae* v, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z,
+                           uint16_t* d_moments, void* ws, size_t ws_bytes, void* stream);
+
 int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z, void* ws,
                    size_t ws_bytes, void* stream) {
-  ACE_REQUIRE(v && d_wav && d_z && ws, "ace_vae_encode: null argument");
+  ACE_REQUIRE(d_z, "ace_vae_encode: null argument");
+  return vae_encode_impl(v, d_wav, samples, d_eps, d_z, nullptr, ws, ws_bytes, stream);
+}
+
+int ace_vae_encode_moments(AceVae* v, const float* d_wav, int samples, uint16_t* d_moments, void* ws, size_t ws_bytes,
+                           void* stream) {
+  ACE_REQUIRE(d_moments, "ace_vae_encode_moments: null argument");
+  return vae_encode_impl(v, d_wav, samples, nullptr, nullptr, d_moments, ws, ws_bytes, stream);
+}
+
+int ace_vae_posterior_sample(const AceVae* v, const uint16_t* d_moments, const uint16_t* d_eps, uint16_t* d_z,
+                             int frames, void* stream) {
+  ACE_REQUIRE(v && d_moments && d_z && frames >= 1, "ace_vae_posterior_sample: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cz = v->cfg.latent_channels;
+  const long tot = (long)frames * Cz;
+  prof_begin(PROF_ELEM, 0.0, (double)tot * 8, st);
+  posterior_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const bf16*)d_moments, (const bf16*)d_eps, (bf16*)d_z,
+                                                                    frames, Cz);
+  prof_end(st);
+  ACE_CUDA_CHECK(cudaGetLastError());
+  return ACE_OK;
+}
+
+static int vae_encode_impl(AceVae* v, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z,
+                           uint16_t* d_moments, void* ws, size_t ws_bytes, void* stream) {
+  ACE_REQUIRE(v && d_wav && ws, "ace_vae_encode: null argument");
   ACE_REQUIRE(samples >= v->hop && samples % v->hop == 0, "samples %d must be a positive multiple of hop %d",
               samples, v->hop);
   ACE_REQUIRE(((uintptr_t)ws & 255) == 0, "unaligned workspace");
@@ -546,14 +576,18 @@ int ace_vae_encode(AceVae* v, const float* d_wav, int samples, const uint16_t* d
   {
     const int Cin = v->enc[n - 1].cout;
     const int sh3[3] = {-1, 0, 1};
-    EpiConv e{hs, nullptr, nullptr, v->enc_conv2.bias, nullptr, nullptr, (long)H, 0, L * H, H};
+    ACE_REQUIRE(H == 2 * v->cfg.latent_channels, "encoder_hidden %d != 2 x latent_channels %d", H, v->cfg.latent_channels);
+    bf16* mom = d_moments != nullptr ? (bf16*)d_moments : hs;  // [L, 2 Cz]: mean | scale
+    EpiConv e{mom, nullptr, nullptr, v->enc_conv2.bias, nullptr, nullptr, (long)H, 0, L * H, H};
     ACE_PROPAGATE(conv_gemm(xs, L, Cin, Cin, v->enc_conv2, H, L, 3, sh3, e, st));
-    const int Cz = v->cfg.latent_channels;
-    const long tot = L * Cz;
-    prof_begin(PROF_ELEM, 0.0, (double)tot * 8, st);
-    posterior_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(hs, (const bf16*)d_eps, (bf16*)d_z, L, Cz);
-    prof_end(st);
-    ACE_CUDA_CHECK(cudaGetLastError());
+    if (d_z != nullptr) {
+      const int Cz = v->cfg.latent_channels;
+      const long tot = L * Cz;
+      prof_begin(PROF_ELEM, 0.0, (double)tot * 8, st);
+      posterior_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(mom, (const bf16*)d_eps, (bf16*)d_z, L, Cz);
+      prof_end(st);
+      ACE_CUDA_CHECK(cudaGetLastError());
+    }
   }
   return ACE_OK;
 }

@@ -171,7 +171,10 @@ def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> 
             torch.cat([g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"),
                        g(p + "self_attn.v_proj.weight")], dim=0),
             g(p + "self_attn.q_norm.weight"), g(p + "self_attn.k_norm.weight"), g(p + "self_attn.o_proj.weight"),
-            g(p + "cross_attn.q_proj.weight"),
+            # the cross-attention RMSNorm has no AdaLN modulation, so its weight vector is folded into the q
+            # projection (x_hat * w) @ Wq^T = x_hat @ (Wq * w)^T: the q GEMM then reads the residual stream itself
+            # and only applies rstd in its epilogue (csrc/epilogues.cuh NormIn, csrc/dit.cu)
+            g(p + "cross_attn.q_proj.weight").float() * g(p + "cross_attn_norm.weight").float()[None, :],
             torch.cat([g(p + "cross_attn.k_proj.weight"), g(p + "cross_attn.v_proj.weight")], dim=0),
             g(p + "cross_attn.q_norm.weight"), g(p + "cross_attn.k_norm.weight"), g(p + "cross_attn.o_proj.weight"),
             gate_up, g(p + "mlp.down_proj.weight"),

@@ -149,6 +149,78 @@ class B200Vae:
                                                ws.data_ptr(), ws.numel(), _lib.stream_handle(self.device)), "ace_vae_encode", self.lib)
         return z
 
+    # ------------------------------------------------------------------
+    # Posterior-moments path: the encoder output (mean | scale per frame) is a deterministic function of the audio,
+    # only the noise of `latent_dist.sample()` is fresh per call.  Callers that encode the same reference / source
+    # audio over and over (handler/conditioning_embed.py:18-69 re-encodes every reference of every request) keep the
+    # moments and re-draw the sample: same distribution and same RNG consumption as encoding again.
+    def encode_moments(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [2, N] fp32 (N % hop == 0) -> moments [N/hop, 128] bf16 (mean | scale)."""
+        N = wav.shape[1]
+        wav = wav.to(device=self.device, dtype=torch.float32).contiguous()
+        T = N // self.shape.hop
+        mom = torch.empty(T, 2 * self.shape.decoder_input_channels, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            need = self.lib.ace_vae_encode_workspace_bytes(self.handle, N)
+            ws = self._workspace(need)
+            _lib.check(self.lib.ace_vae_encode_moments(self.handle, wav.data_ptr(), N, mom.data_ptr(), ws.data_ptr(),
+                                                       ws.numel(), _lib.stream_handle(self.device)),
+                       "ace_vae_encode_moments", self.lib)
+        return mom
+
+    def posterior_sample(self, moments: torch.Tensor, eps_tc: Optional[torch.Tensor]) -> torch.Tensor:
+        """moments [T, 128], eps_tc [T, 64] or None (the mean) -> z [T, 64] bf16; bit-identical to encode_samples."""
+        T = moments.shape[0]
+        z = torch.empty(T, self.shape.decoder_input_channels, dtype=torch.bfloat16, device=self.device)
+        if eps_tc is not None:
+            eps_tc = eps_tc.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ace_vae_posterior_sample(self.handle, moments.data_ptr(), _lib.ptr(eps_tc), z.data_ptr(),
+                                                         T, _lib.stream_handle(self.device)),
+                       "ace_vae_posterior_sample", self.lib)
+        return z
+
+    MOMENT_CACHE_ENTRIES = 16
+
+    @staticmethod
+    def _fingerprint(a: torch.Tensor):
+        """128-bit content fingerprint computed on the device (two wrapping 64-bit sums over the raw fp32 words, the
+        second position-weighted) + the shape.  A cache key, not a cryptographic hash: a collision needs two audio
+        clips of identical length whose word sums and index-weighted word sums both agree modulo 2^64."""
+        w = a.contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+        idx = torch.arange(1, w.numel() + 1, device=w.device, dtype=torch.int64)
+        both = torch.stack([w.sum(), (w * idx).sum()]).tolist()
+        return (tuple(a.shape), both[0], both[1])
+
+    def encode_cached(self, audio: torch.Tensor, sample: bool = True, generator: Optional[torch.Generator] = None):
+        """encode() with a device-resident cache of posterior moments keyed by audio content: a repeated clip skips
+        the encoder (5-6 ms per 30 s reference on B200) and only re-draws the posterior sample.  Same returns as
+        encode(): [B, 64, N // hop] bf16."""
+        if audio.dim() == 2:
+            audio = audio.unsqueeze(0)
+        hop = self.shape.hop
+        if not hasattr(self, "_moments"):
+            self._moments, self.moment_cache_hits, self.moment_cache_misses = {}, 0, 0
+        outs = []
+        for b in range(audio.shape[0]):
+            T = audio.shape[2] // hop
+            if T < 1:
+                raise ValueError(f"audio of {audio.shape[2]} samples is shorter than one hop ({hop})")
+            a = audio[b, :, : T * hop].to(device=self.device, dtype=torch.float32)
+            key = self._fingerprint(a)
+            mom = self._moments.pop(key, None)
+            if mom is None:
+                self.moment_cache_misses += 1
+                mom = self.encode_moments(a)
+                while len(self._moments) >= self.MOMENT_CACHE_ENTRIES:
+                    self._moments.pop(next(iter(self._moments)))  # least recently used
+            else:
+                self.moment_cache_hits += 1
+            self._moments[key] = mom  # most recently used last
+            eps = torch.randn(T, 64, device=self.device, dtype=torch.bfloat16, generator=generator) if sample else None
+            outs.append(self.posterior_sample(mom, eps).transpose(0, 1))
+        return torch.stack(outs, dim=0)
+
     def encode(self, audio: torch.Tensor, sample: bool = True, generator: Optional[torch.Generator] = None):
         """audio [B, 2, N] -> latents [B, 64, N // hop] (bf16); `sample` draws the posterior noise
         with torch's RNG on the device like latent_dist.sample()."""

@@ -175,6 +175,16 @@ int ace_vae_decode(AceVae* vae, const uint16_t* d_z, int frames, float* d_wav, v
  * NULL: return the mean) -> d_z [samples/hop, 64] bf16 = mean + (softplus(scale) + 1e-4) * eps. */
 int ace_vae_encode(AceVae* vae, const float* d_wav, int samples, const uint16_t* d_eps, uint16_t* d_z,
                    void* d_workspace, size_t workspace_bytes, void* stream);
+/* The two halves of ace_vae_encode, for callers that encode the SAME audio repeatedly (reference / source audio of
+ * successive requests: handler/conditioning_embed.py:18-69): the encoder's posterior moments are a deterministic
+ * function of the audio, only the noise is fresh per call (`latent_dist.sample()`).
+ *   ace_vae_encode_moments  : d_wav -> d_moments [samples/hop, 128] bf16 (mean | scale per frame)
+ *   ace_vae_posterior_sample: d_moments, d_eps [frames, 64] (NULL: the mean) -> d_z [frames, 64], bit-identical to
+ *                             what ace_vae_encode returns for the same audio and noise. */
+int ace_vae_encode_moments(AceVae* vae, const float* d_wav, int samples, uint16_t* d_moments, void* d_workspace,
+                           size_t workspace_bytes, void* stream);
+int ace_vae_posterior_sample(const AceVae* vae, const uint16_t* d_moments, const uint16_t* d_eps, uint16_t* d_z,
+                             int frames, void* stream);
 
 /* Device addresses of the handle's static I/O slots inside the bound workspace (xt [bc,t,64],
  * ctx [bc,t,128], vt [bc,t,64]).  Passing these to ace_dit_step skips the staging copies, so a

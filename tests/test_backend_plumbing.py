@@ -93,6 +93,8 @@ class StubVae:
     def encode(self, audio, sample=True):
         return torch.full((audio.shape[0], 64, audio.shape[2] // 1920), 0.25)
 
+    encode_cached = encode  # the encode seam goes through the posterior-moments cache
+
 
 def _payload(b=2, t=20):
     z = torch.zeros(1)
@@ -665,6 +667,8 @@ def test_real_reference_audio_callers_reach_the_b200_encoder():
         def encode(self, audio, sample=True):
             self.encodes.append(tuple(audio.shape))
             return torch.full((audio.shape[0], 64, audio.shape[2] // 1920), float(len(self.encodes)))
+
+        encode_cached = encode  # the seam's entry point (posterior-moments cache in the real engine)
 
     class Host(ConditioningEmbedMixin, ConditioningTargetMixin, BatchPrepMixin, FakeHandler):
         def __init__(self):

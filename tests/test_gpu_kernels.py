@@ -174,6 +174,41 @@ def test_dit_forward_mid_size(lib):
     assert rel_l2(vt.cpu().float(), want) <= 2e-2
 
 
+@pytest.mark.parametrize("hidden,T", [(512, 601), (2048, 1500)])
+def test_gemm_tail_path_matches_slab_path(lib, probe, hidden, T):
+    """The residual GEMMs' tail path (residual tile by TMA into the freed operand ring, in-place update in shared
+    memory, h and g out by TMA stores: gemm.cuh / EpiGatedResid::tail_box) rounds exactly like the slab path it
+    replaces on a CTA's last tile, so a forward must be bit-identical with it switched off (probe build,
+    ACE_NO_TMA_TAIL=1) — also against the release library."""
+    import os
+
+    layers = 4 if hidden == 512 else 2
+    cfg = DiTConfig(hidden_size=hidden, intermediate_size=2 * hidden, num_hidden_layers=layers,
+                    num_attention_heads=hidden // 128, num_key_value_heads=max(1, hidden // 256), sliding_window=128)
+    w = bf16_round_(make_dit_weights(cfg, seed=11))
+    g = torch.Generator().manual_seed(12)
+    B, E = 2, 70
+    xt = torch.randn(B, T, 64, generator=g).to(torch.bfloat16).to(DEV)
+    ctx = torch.randn(B, T, 128, generator=g).to(torch.bfloat16).to(DEV)
+    enc = torch.randn(B, E, cfg.hidden_size, generator=g).to(torch.bfloat16).to(DEV)
+    outs = []
+    for use, env in ((probe, "1"), (probe, None), (lib, None)):
+        if env is not None:
+            os.environ["ACE_NO_TMA_TAIL"] = env
+        try:
+            dit = B200DiT(w, DiTShape.from_config(cfg), DEV, lib=use)
+            dit.bind(B, T, E)
+        finally:
+            os.environ.pop("ACE_NO_TMA_TAIL", None)
+        dit.set_condition(enc)
+        outs.append(dit.step(xt, ctx, [0.5, 0.5]).clone())
+        torch.cuda.synchronize()
+        dit.close()
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1]), max_abs(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2]), max_abs(outs[0], outs[2])
+
+
 def _bf16_floor(fn_fp32, fn_bf16):
     """Spread between an all-bf16 torch run and the fp32 run of the same oracle op."""
     return rel_l2(fn_bf16().float(), fn_fp32())
