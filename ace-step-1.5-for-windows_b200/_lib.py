@@ -83,6 +83,7 @@ SIGNATURES = {
     "ace_enc_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "ace_enc_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "ace_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "ace_fsq": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int), C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "ace_launch_count": (C.c_uint64, []),
     "ace_profile_start": (None, []),
     "ace_profile_stop": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -26,6 +26,7 @@ from .cond import B200ConditionEncoder, CondShape
 from .dit import B200DiT, DiTShape
 from .pack import UnsupportedAdapterError, effective_decoder_state
 from .sampler import B200Sampler
+from .tokenizer import B200AudioTokenizer, TokShape
 from .vae import B200Vae, VaeShape
 
 
@@ -36,6 +37,7 @@ class B200BackendMixin:
     use_b200_vae: bool = False
     use_b200_cond: bool = False
     b200_cond: Optional[B200ConditionEncoder] = None
+    b200_tok: Optional[B200AudioTokenizer] = None
     b200_dit: Optional[B200DiT] = None
     b200_sampler: Optional[B200Sampler] = None
     b200_vae: Optional[B200Vae] = None
@@ -69,6 +71,13 @@ class B200BackendMixin:
                                                       CondShape.from_config(self.model.config), device)
                 self.use_b200_cond = True
                 dit_status = "Active (B200 tcgen05, condition encoder included)"
+                # the cover-song branch of prepare_condition: audio tokenizer -> FSQ -> detokenizer
+                if getattr(self.model, "tokenizer", None) is not None and getattr(self.model, "detokenizer", None) is not None:
+                    if self.b200_tok is not None:
+                        self.b200_tok.close()
+                    tsd = {"tokenizer." + k: v for k, v in self.model.tokenizer.state_dict().items()}
+                    tsd.update({"detokenizer." + k: v for k, v in self.model.detokenizer.state_dict().items()})
+                    self.b200_tok = B200AudioTokenizer(tsd, TokShape.from_config(self.model.config), device)
         if vae:
             if self.b200_vae is not None:
                 self.b200_vae.close()
@@ -156,10 +165,11 @@ class B200BackendMixin:
                                 refer_audio_order_mask, hidden_states, attention_mask, silence_latent, src_latents,
                                 chunk_masks, is_covers, precomputed_lm_hints_25Hz=None, audio_codes=None):
         """`model.prepare_condition` (modeling_acestep_v15_turbo.py:1604-1649) with the condition encoder
-        (`self.encoder(...)`, :1621-1628) on the B200 kernels; same keywords, same 3-tuple.  The LM-hint
-        branch (tokenizer / FSQ / detokenizer, only consumed where is_covers > 0) stays on the stock
-        modules and is skipped entirely for plain text2music / repaint batches, whose hints the
-        reference computes and then discards (:1649)."""
+        (`self.encoder(...)`, :1621-1628) and the LM-hint branch (audio tokenizer -> residual FSQ -> detokenizer,
+        :1630-1646) on the B200 kernels; same keywords, same 3-tuple.  The LM-hint branch is only consumed where
+        is_covers > 0, so it is skipped entirely for plain text2music / repaint batches, whose hints the reference
+        computes and then discards (:1646).  `audio_codes` (indices -> codes without the tokenizer) stays on the
+        stock quantizer: the reference's own line for it (:1638, `self.tokenize.quantizer`) raises AttributeError."""
         dtype = hidden_states.dtype
         enc, enc_mask = self.b200_cond(
             text_hidden_states=text_hidden_states, text_attention_mask=text_attention_mask,
@@ -172,9 +182,13 @@ class B200BackendMixin:
             else:
                 if audio_codes is not None:
                     hints5 = self.model.tokenizer.quantizer.get_output_from_indices(audio_codes)
+                    hints = self.model.detokenize(hints5)[:, : src_latents.shape[1], :]
+                elif getattr(self, "b200_tok", None) is not None:
+                    hints = self.b200_tok.lm_hints(hidden_states, silence_latent, attention_mask,
+                                                   src_latents.shape[1]).to(src_latents.dtype)
                 else:
                     hints5, _, _ = self.model.tokenize(hidden_states, silence_latent, attention_mask)
-                hints = self.model.detokenize(hints5)[:, : src_latents.shape[1], :]
+                    hints = self.model.detokenize(hints5)[:, : src_latents.shape[1], :]
             src_latents = torch.where(is_covers.unsqueeze(-1).unsqueeze(-1) > 0, hints, src_latents)
         context_latents = torch.cat([src_latents, chunk_masks.to(dtype)], dim=-1)
         return enc.to(dtype), enc_mask, context_latents
@@ -404,6 +418,7 @@ def install(target):
         setattr(target, "_ref_" + name, bind(original))
         setattr(target, name, bind(_make_attention_caller(name)))
     for flag, val in (("use_b200_dit", False), ("use_b200_vae", False), ("use_b200_cond", False), ("b200_dit", None),
+                      ("b200_tok", None),
                       ("_b200_dit_wanted", False),
                       ("b200_sampler", None), ("b200_vae", None), ("b200_cond", None)):
         if not hasattr(target, flag):

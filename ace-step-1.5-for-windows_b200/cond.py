@@ -54,7 +54,7 @@ class _EncoderStack:
         for i in range(n_layers):  # configuration_acestep_v15.py:251-254: even layers slide, odd are full
             cfg.layer_is_sliding[i] = 1 if (i + 1) % 2 else 0
         cfg.rope_theta, cfg.rms_eps = float(shape.rope_theta), float(shape.rms_norm_eps)
-        blob = pack_encoder(sd, n_layers, prefix)
+        blob = pack_encoder(sd, n_layers, prefix, embed=in_dim != 0)  # in_dim 0: tokens arrive already embedded
         expect = lib.ace_enc_packed_elems(C.byref(cfg))
         if blob.numel() != expect:
             raise _lib.B200Error(f"packed {prefix} blob has {blob.numel()} elements, library expects {expect}")

@@ -12,6 +12,11 @@
 //   rmsnorm -> [gate|up GEMM + SwiGLU] -> [down GEMM + residual]
 // text_projector (:1518) is a bias-free Linear: ace_linear.  pack_sequences / unpack_timbre_embeddings
 // are index plumbing and stay in the PyTorch host code (acestep_b200/cond.py).
+//
+// The audio tokenizer's AttentionPooler (:730-856) and the AudioTokenDetokenizer (:859-990) are the same stack with
+// the special token(s) joined AFTER embed_tokens, so they use a handle with in_dim = 0: the input is already
+// [batch, seq, hidden] (acestep_b200/tokenizer.py builds it), sequences are pool_window_size (+1) tokens long.
+// ace_fsq is the quantizer between them (ResidualFSQ of the third-party vector_quantize_pytorch, restated).
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,6 +55,72 @@ masked_rows_uniform_kernel(const bf16* __restrict__ v, long ldv, bf16* __restric
   for (int i = first; i < S; ++i) o[((long)b * S + i) * ldo + (long)h * 128 + d] = __float2bfloat16_rn(val);
 }
 
+// Residual FSQ (vector_quantize_pytorch ResidualFSQ / FSQ, restated — see oracle/tokenizer.py): one CTA per token.
+//   y = bf16(W_in x + b_in)  [C <= 8 values];  per quantizer q, in fp32 (the library forces fp32 for the FSQ math):
+//   z = residual / scale_q,  bounded = tanh(z + shift) * half_l - offset,  r = round-half-even(bounded),
+//   code = bf16(r / (L // 2)) * scale_q,  index_q = sum_c (r_c + L_c // 2) * basis_c;  out = bf16(W_out sum_q code + b_out).
+struct FsqLevels {
+  int v[8];
+};
+__global__ void __launch_bounds__(256)
+fsq_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w_in, const bf16* __restrict__ b_in, FsqLevels lv,
+           int C, int nq, const bf16* __restrict__ w_out, const bf16* __restrict__ b_out, bf16* __restrict__ q_out,
+           int* __restrict__ idx_out, int D) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float y[8];
+  __shared__ float code_sum[8];
+  __shared__ int idx_part[8][8];  // [quantizer][channel]
+  const int m = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* xr = x + (size_t)m * D;
+  for (int c = warp; c < C; c += 8) {
+    float acc = 0.f;
+    for (int k = lane * 2; k < D; k += 64) {
+      float x0, x1, w0, w1;
+      unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + k), x0, x1);
+      unpack_bf16x2(*reinterpret_cast<const uint32_t*>(w_in + (size_t)c * D + k), w0, w1);
+      acc = fmaf(x0, w0, acc);
+      acc = fmaf(x1, w1, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[c] = bf16_round(acc + __bfloat162float(b_in[c]));
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const int L = lv.v[c];
+    const float half_l = (float)(L - 1) * (1.0f + 1e-3f) / 2.0f;
+    const float offset = (L % 2 == 0) ? 0.5f : 0.0f;
+    const float shift = atanhf(offset / half_l);
+    const float half_w = (float)(L / 2);
+    int basis = 1;
+    for (int i = 0; i < c; ++i) basis *= lv.v[i];
+    float residual = y[c], out = 0.f;
+    for (int qi = 0; qi < nq; ++qi) {
+      const float scale = qi == 0 ? 1.0f : powf((float)(L - 1), -(float)qi);
+      const float bounded = tanhf(residual / scale + shift) * half_l - offset;
+      const float r = rintf(bounded);  // round half to even, like torch.round
+      const float code = bf16_round(r / half_w) * scale;
+      residual -= code;
+      out += code;
+      idx_part[qi][c] = ((int)r + L / 2) * basis;
+    }
+    code_sum[c] = bf16_round(out);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nq) {
+    int s = 0;
+    for (int c = 0; c < C; ++c) s += idx_part[threadIdx.x][c];
+    idx_out[(size_t)m * nq + threadIdx.x] = s;
+  }
+  for (int d = threadIdx.x; d < D; d += 256) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(code_sum[c], __bfloat162float(w_out[(size_t)d * C + c]), acc);
+    q_out[(size_t)m * D + d] = __float2bfloat16_rn(acc + __bfloat162float(b_out[d]));
+  }
+}
+
 }  // namespace
 }  // namespace ace
 
@@ -71,7 +142,7 @@ size_t ace_enc_packed_elems(const AceEncConfig* c) {
   const size_t D = c->hidden_size, I = c->intermediate_size, L = c->num_layers, IN = c->in_dim;
   const size_t NQ = (size_t)c->num_heads * c->head_dim, NKV = (size_t)c->num_kv_heads * c->head_dim;
   const size_t per = 2 * D + (NQ + 2 * NKV) * D + 256 + D * NQ + 2 * I * D + D * I;
-  return D * IN + D + D + L * per;
+  return D * IN + (IN ? D : 0) + D + L * per;  // in_dim 0: no embed_tokens in the blob
 }
 
 int ace_enc_create(AceEnc** out, const AceEncConfig* cfg, const uint16_t* weights, size_t n_elems) {
@@ -118,7 +189,7 @@ int ace_enc_create(AceEnc** out, const AceEncConfig* cfg, const uint16_t* weight
     return r;
   };
   e->embed_w = take(D * e->IN);
-  e->embed_b = take(D);
+  e->embed_b = take(e->IN ? D : 0);
   e->final_norm = take(D);
   e->lw.resize(e->L);
   for (EncLayerW& w : e->lw) {
@@ -178,9 +249,13 @@ int ace_enc_forward(AceEnc* e, const uint16_t* d_in, const int* d_kv_len, uint16
   const int group = e->cfg.num_heads / e->cfg.num_kv_heads;
 
   ACE_PROPAGATE(launch_rope_tables(rope_cos, rope_sin, S, e->cfg.rope_theta, st));
-  GemmPlan pe;
-  ACE_PROPAGATE(make_gemm_plan(&pe, (const bf16*)d_in, M, e->IN, e->IN, e->embed_w, D, e->IN, M, 1, nullptr, 0));
-  ACE_PROPAGATE(launch_gemm(pe, EpiBias{h, (long)D, e->embed_b}, st));
+  if (e->IN == 0) {  // pre-embedded input
+    ACE_CUDA_CHECK(cudaMemcpyAsync(h, d_in, (size_t)M * D * 2, cudaMemcpyDeviceToDevice, st));
+  } else {
+    GemmPlan pe;
+    ACE_PROPAGATE(make_gemm_plan(&pe, (const bf16*)d_in, M, e->IN, e->IN, e->embed_w, D, e->IN, M, 1, nullptr, 0));
+    ACE_PROPAGATE(launch_gemm(pe, EpiBias{h, (long)D, e->embed_b}, st));
+  }
   for (int l = 0; l < e->L; ++l) {
     const EncLayerW& w = e->lw[l];
     const int window = e->cfg.layer_is_sliding[l] ? e->cfg.sliding_window : -1;
@@ -210,6 +285,30 @@ int ace_enc_forward(AceEnc* e, const uint16_t* d_in, const int* d_kv_len, uint16
     ACE_PROPAGATE(launch_gemm(pd, EpiGatedResid{h, (long)D, nullptr, 0, S}, st));
   }
   ACE_PROPAGATE(launch_adaln_rmsnorm(h, e->final_norm, nullptr, nullptr, 0, (bf16*)d_out, M, D, S, eps, st));
+  return ACE_OK;
+}
+
+int ace_fsq(const uint16_t* d_x, const uint16_t* d_w_in, const uint16_t* d_b_in, const int* levels, int n_levels,
+            int num_quantizers, const uint16_t* d_w_out, const uint16_t* d_b_out, uint16_t* d_q, int* d_indices, int m,
+            int dim, void* stream) {
+  ACE_REQUIRE(d_x && d_w_in && d_b_in && levels && d_w_out && d_b_out && d_q && d_indices, "ace_fsq: null argument");
+  ACE_REQUIRE(n_levels >= 1 && n_levels <= 8 && num_quantizers >= 1 && num_quantizers <= 8,
+              "ace_fsq: %d levels / %d quantizers out of range [1, 8]", n_levels, num_quantizers);
+  ACE_REQUIRE(m >= 1 && dim >= 64 && dim % 64 == 0, "ace_fsq: bad shape m=%d dim=%d", m, dim);
+  FsqLevels lv;
+  long codes = 1;
+  for (int i = 0; i < 8; ++i) {
+    lv.v[i] = i < n_levels ? levels[i] : 1;
+    ACE_REQUIRE(lv.v[i] >= 1 && lv.v[i] <= 1024, "ace_fsq: level %d out of range", lv.v[i]);
+    codes *= lv.v[i];
+  }
+  ACE_REQUIRE(codes < (1L << 31), "ace_fsq: codebook of %ld entries does not fit int32 indices", codes);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(PROF_ELEM, 4.0 * m * dim * n_levels, 4.0 * m * dim, st);
+  ACE_CUDA_CHECK(launch_kernel(fsq_kernel, dim3(m), dim3(256), (size_t)0, st, (const bf16*)d_x, (const bf16*)d_w_in,
+                               (const bf16*)d_b_in, lv, n_levels, num_quantizers, (const bf16*)d_w_out,
+                               (const bf16*)d_b_out, (bf16*)d_q, d_indices, dim));
+  prof_end(st);
   return ACE_OK;
 }
 

@@ -185,13 +185,15 @@ def pack_dit(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str = "") -> 
 # --------------------------------------------------------------------------------------------
 # Condition encoders
 # --------------------------------------------------------------------------------------------
-def pack_encoder(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str) -> torch.Tensor:
+def pack_encoder(sd: Dict[str, torch.Tensor], num_layers: int, prefix: str, embed: bool = True) -> torch.Tensor:
     """One encoder stack (`prefix` = "lyric_encoder." / "timbre_encoder." inside
     AceStepConditionEncoder.state_dict(), modeling_acestep_v15_turbo.py:574-598, 994-1018) as the 1-D
     bf16 blob ace_enc_create walks: embed_tokens, final norm, then per layer the two norms, fused qkv,
     q/k norms, o_proj, gate/up interleaved in 64-row blocks (like pack_dit), down_proj."""
     g = lambda k: _get(sd, prefix + k)
-    parts: List[torch.Tensor] = [g("embed_tokens.weight"), g("embed_tokens.bias"), g("norm.weight")]
+    # embed=False (AceEncConfig.in_dim = 0): the caller feeds already-embedded tokens (audio tokenizer pooler /
+    # detokenizer, whose special tokens join after embed_tokens) and applies embed_tokens itself
+    parts: List[torch.Tensor] = ([g("embed_tokens.weight"), g("embed_tokens.bias")] if embed else []) + [g("norm.weight")]
     for l in range(num_layers):
         p = f"layers.{l}."
         gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")

@@ -228,6 +228,15 @@ int ace_enc_forward(AceEnc* enc, const uint16_t* d_in, const int* d_kv_len, uint
 int ace_linear(const uint16_t* d_a, const uint16_t* d_w, const uint16_t* d_bias, uint16_t* d_out, int m, int n,
                int k, void* stream);
 
+/* Residual finite-scalar quantizer of the audio tokenizer (AceStepAudioTokenizer.quantizer, turbo :1190-1194; the
+ * class is the third-party vector_quantize_pytorch.ResidualFSQ, restated in oracle/tokenizer.py):
+ *   d_x [m, dim] bf16 -> project_in (d_w_in [n_levels, dim], d_b_in [n_levels]) -> num_quantizers FSQ rounds in fp32
+ *   with `levels` (host ints) -> project_out (d_w_out [dim, n_levels], d_b_out [dim]) -> d_q [m, dim] bf16,
+ *   d_indices [m, num_quantizers] int32 (codebook index per round). */
+int ace_fsq(const uint16_t* d_x, const uint16_t* d_w_in, const uint16_t* d_b_in, const int* levels, int n_levels,
+            int num_quantizers, const uint16_t* d_w_out, const uint16_t* d_b_out, uint16_t* d_q, int* d_indices, int m,
+            int dim, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Measurement hooks (bench.py): launch counter and per-launch CUDA-event profiling              */
 /* ------------------------------------------------------------------------------------------ */
