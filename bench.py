@@ -414,7 +414,7 @@ def run_b200(args, wl):
 
     from acestep_b200 import _lib
     from acestep_b200.dit import DiTShape
-    from acestep_b200.multi_gpu import generate_sharded
+    from acestep_b200.multi_gpu import GatherPipeline, generate_sharded
     from acestep_b200.pipeline import B200Pipeline
     from acestep_b200.synthetic import random_dit_state, random_vae_state
     from acestep_b200.vae import VaeShape
@@ -437,7 +437,7 @@ def run_b200(args, wl):
         rank i, asynchronous waveform gather to rank 0 that overlaps the next song, drained inside the region).
         e2e: the same through the public API with pinned HOST inputs and a HOST waveform (wall clock)."""
         lengths = [r.n_samples] * world
-        pending, keep = [], {}
+        pipe_g, keep = GatherPipeline(depth=1), {}
         counter = [0]
 
         def step_device():
@@ -449,14 +449,12 @@ def run_b200(args, wl):
             def one(_song_index):
                 keep["out"] = r.song_device(i)
                 return keep["out"]["audio"][0]
-            pending.append(generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True))
+            # at most one gather in flight: the previous song's gather (finished long ago) is retired here, which
+            # hands its buffers back to the allocator before this song's successor needs memory
+            pipe_g.submit(generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True))
 
         def drain():
-            res = None
-            for p in pending:
-                res = p.wait()
-            pending.clear()
-            return res
+            return pipe_g.drain()
 
         # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop;
         # the clock sampler attaches BEFORE the warm-up and the warm-up runs back to back into the timed region

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from acestep_b200.multi_gpu import gather_waveforms, generate_sharded, shard_indices
+from acestep_b200.multi_gpu import GatherPipeline, gather_waveforms, generate_sharded, shard_indices
 
 
 def _free_port():
@@ -30,7 +30,10 @@ def _worker(rank, world, port, n_items, q):
         pend = generate_sharded(_song, n_items, dst=0, lengths=lens, async_op=True)
         # one equal-length song per rank (the benchmark's shape): zero-copy send buffer
         pend1 = generate_sharded(lambda i: _song(0) + i, world, dst=0, lengths=[_song(0).shape[-1]] * world, async_op=True)
-        out2, out3 = pend.wait(), pend1.wait()
+        gp = GatherPipeline(depth=1)
+        assert gp.submit(pend) is None          # one in flight: nothing retired yet
+        out2 = gp.submit(pend1)                  # second submit retires (waits for) the first
+        out3 = gp.drain()
         if rank == 0:
             ok = len(out) == n_items and all(torch.equal(out[i], _song(i)) for i in range(n_items))
             ok = ok and len(out2) == n_items and all(torch.equal(out2[i], _song(i)) for i in range(n_items))
