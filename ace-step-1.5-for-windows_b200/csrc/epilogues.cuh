@@ -569,12 +569,18 @@ struct EpiGatedResid {
                                       float) const {
     const int lane = threadIdx.x & 31, row0 = row - lane;
     const int b = gate != nullptr ? gsel(row, M) : 0;
+    const bf16* crow = nullptr;  // this row's c vector (the next norm's g = h * c), resolved once
+    if (no.g != nullptr)
+      crow = no.cvec + (no.c_stride ? (long)__ldg(no.slot + (row < M ? row / S : 0)) * no.c_stride : 0);
     uint4 nxt[8];
 #pragma unroll 1
     for (int s = 0; s < BN; s += 64) {
       if (n0 + s >= N) break;  // warp-uniform
       const int ncols = N - (n0 + s) < 64 ? N - (n0 + s) : 64;
       auto addr = [&](int r) -> bf16* { return row0 + r < M ? h + (size_t)(row0 + r) * ldh + n0 + s : nullptr; };
+      // NormOut: the sum of squares comes straight from the registers that hold the new h; g = h * c is made in
+      // place in the slab once h's copy has left it (holding g in registers instead spilled: 168-register budget)
+      float ss = 0.f;
       const bool has_next = s + 64 < BN && n0 + s + 64 < N;
       if (has_next) {  // next residual slab: global -> registers while this slab is processed
         const int nn = N - (n0 + s + 64) < 64 ? N - (n0 + s + 64) : 64;
@@ -605,10 +611,29 @@ struct EpiGatedResid {
           r.x = badd2(r.x, pv.x); r.y = badd2(r.y, pv.y);
           r.z = badd2(r.z, pv.z); r.w = badd2(r.w, pv.w);
           *slot = r;
+          if (no.ssp != nullptr) {
+            float x0, x1;
+            unpack_bf16x2(r.x, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+            unpack_bf16x2(r.y, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+            unpack_bf16x2(r.z, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+            unpack_bf16x2(r.w, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
+          }
         }
       }
       stg.store_rows(lane, ncols, addr);
-      if (no.ssp != nullptr) no.emit(stg, lane, row, row0, n0 + s, ncols, M);
+      if (no.ssp != nullptr && row < M) no.ssp[(size_t)row * no.nss + ((n0 + s) >> 6)] = ss;
+      if (no.g != nullptr) {
+        const uint4* cp = reinterpret_cast<const uint4*>(crow + n0 + s);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4* sl = stg.at(lane, q);
+          const uint4 r = *sl, c = __ldg(cp + q);
+          *sl = make_uint4(bmul2(r.x, c.x), bmul2(r.y, c.y), bmul2(r.z, c.z), bmul2(r.w, c.w));
+        }
+        stg.store_rows(lane, ncols, [&](int r) -> bf16* {
+          return row0 + r < M ? no.g + (size_t)(row0 + r) * no.ldg + n0 + s : nullptr;
+        });
+      }
       if (has_next) stg.commit_rows(lane, nxt);
     }
   }

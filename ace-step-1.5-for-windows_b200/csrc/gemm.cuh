@@ -93,7 +93,12 @@ int encode_tmap_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
 int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld, const bf16* b,
                    int n, long b_ld, int m, int ntaps, const int* shifts, int bn);
 
-// Split-K for problems with few output tiles (M <= a few hundred rows).  `scratch_bytes(works)` of
+// Split-K for problems with few output tiles (M <= a few hundred rows).  SINGLE-STREAM REQUIREMENT: the split-K tail
+// spin-waits across CTAs and relies on all `works <= #SMs` CTAs of the launch being co-resident, which holds when the
+// handle's kernels run one after another on one stream of an otherwise idle GPU (the DiT step, ace_enc_forward).
+// Two split-K GEMMs issued concurrently from different streams / handles / MPS clients could each hold part of the
+// SMs while spinning; the bounded wait (ACE_HANG_GUARD) then traps after ~2 s instead of hanging.  Callers that need
+// concurrency across handles must serialise small-M (T < ~20 s) steps themselves.  `scratch_bytes(works)` of
 // device memory hold the partial tiles followed by the per-tile counters (zero-initialised once by the
 // caller; the kernel re-arms them).  gemm_plan_enable_splitk decides from the shape (cost model in
 // runtime.cu), may switch a pair-tile plan to single-CTA 128-wide tiles, and leaves the plan untouched
@@ -180,7 +185,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  pdl_trigger();
   if (warp == 3) gemm_prefetch_next(shp, lane);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -205,6 +209,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Dependents are released only AFTER this CTA owns its tensor memory: a dependent CTA that became resident on
+  // this SM first could take the TMEM columns and then sit in griddepcontrol.wait for a grid that can never finish.
+  pdl_trigger();
   pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
@@ -456,7 +463,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const bool leader = rank == 0;
   if (threadIdx.x == 0) ACE_STAMP(0);
 
-  pdl_trigger();
   if (warp == 3) gemm_prefetch_next(shp, lane);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -482,6 +488,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after the TMEM allocation, see gemm_tc_kernel
   pdl_wait();
   if (threadIdx.x == 0) ACE_STAMP(1);
 

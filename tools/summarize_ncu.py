@@ -1,6 +1,12 @@
 #!/usr/bin/env python
 """One line per captured launch of `ncu --set full` reports: duration, DRAM bytes and bandwidth, L2 and
-tensor-pipe percentages, registers.  Usage: python tools/summarize_ncu.py a.ncu-rep [b.ncu-rep ...]"""
+tensor-pipe percentages, registers.  Usage: python tools/summarize_ncu.py a.ncu-rep [b.ncu-rep ...]
+
+umma_pct is the tcgen05 tensor-pipe utilisation: sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off
+.avg.pct_of_peak_sustained_elapsed = bf16 UTCHMMA operations executed / (8192 per SM per elapsed cycle).  (The generic
+sm__pipe_tensor_cycles_active_realtime counter, tensor_rt_pct, does not count the tcgen05 path properly: it reads
+17 % for a 1300 TFLOP/s launch.)  umma_tflops = the same counter's op count / duration: executed FLOPs including the
+zero rows of partial M tiles, so it is >= the algorithmic figure."""
 import csv
 import re
 import subprocess
@@ -13,6 +19,8 @@ KEYS = {
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "tensor_rt_pct": "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "umma_pct": "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "umma_ops": "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum",
     "xu_pct": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "issue_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "regs": "launch__registers_per_thread",
@@ -42,4 +50,5 @@ for rep in sys.argv[1:]:
         by = (float(g("rd")) * SCALE.get(units[col["rd"]], 1.0) + float(g("wr")) * SCALE.get(units[col["wr"]], 1.0))
         print(f"{short(r[hdr.index('Kernel Name')]):52s} grid={g('grid'):>6s} dur_us={dur_us:9.1f} dram_MB={by / 1e6:9.1f} "
               f"dram_GBs={by / dur_us / 1e3:7.1f} dram_pct={g('dram_pct')[:5]:>5s} lts_pct={g('lts_pct')[:5]:>5s} "
+              f"umma_pct={g('umma_pct')[:5]:>5s} umma_tflops={(float(g('umma_ops')) / dur_us / 1e6) if g('umma_ops') != '?' else 0:7.1f} "
               f"tensor_rt_pct={g('tensor_rt_pct')[:5]:>5s} xu_pct={g('xu_pct')[:5]:>5s} issue_pct={g('issue_pct')[:5]:>5s} regs={g('regs')}")
