@@ -62,7 +62,7 @@ __global__ void concat_patches_kernel(const bf16* __restrict__ ctx, const bf16* 
 // ---------------------------------------------------------------------------------------------
 // RMSNorm (+ AdaLN modulation): out = bf16(bf16(bf16(w * x_hat) * scale1p[b]) + shift[b]) where
 // scale1p = bf16(1 + bf16(table + tproj)) and shift = bf16(table + tproj) are precombined once per
-// step by mod_table_kernel (same roundings as the reference's bf16 expression, :490-496).
+// step by the caller (same roundings as the reference's bf16 expression, :490-496).
 // Generic fallback: one 256-thread block per row, any D % 8 == 0.
 __global__ void __launch_bounds__(256)
 adaln_rmsnorm_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w,
@@ -164,34 +164,6 @@ adaln_rmsnorm_warp_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w
     }
     *reinterpret_cast<uint4*>(out + (long)row * D + (lane + 32 * j) * 8) = o;
   }
-}
-
-// mods[l][b][i][:] = bf16(table[l][i] + tvec[b][i])  (i in scale_mask: bf16(1 + that)), i < n.
-// Layers: n = 6 (shift, scale, gate, c_shift, c_scale, c_gate; mask 0b010010); output norm: n = 2
-// with the same temb for both entries (t_i_stride = 0; mask 0b10).
-__global__ void mod_table_kernel(const bf16* __restrict__ tables, const bf16* __restrict__ tvec, long t_b_stride,
-                                 long t_i_stride, bf16* __restrict__ out, int L, int B, int n, int D,
-                                 unsigned scale_mask) {
-  pdl_trigger();
-  pdl_wait();
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // over L*B*n*(D/8)
-  const int nchunk = D >> 3;
-  const long total = (long)L * B * n * nchunk;
-  if (idx >= total) return;
-  const int c = idx % nchunk;
-  const int i = (idx / nchunk) % n;
-  const int b = (idx / ((long)n * nchunk)) % B;
-  const int l = idx / ((long)n * nchunk * B);
-  float a[8], t[8];
-  ld8(tables + ((long)l * n + i) * D + c * 8, a);
-  ld8(tvec + (long)b * t_b_stride + (long)i * t_i_stride + c * 8, t);
-  const bool one_plus = (scale_mask >> i) & 1u;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    a[k] = bf16_round(a[k] + t[k]);
-    if (one_plus) a[k] = 1.0f + a[k];
-  }
-  st8(out + (((long)l * B + b) * n + i) * D + c * 8, a);
 }
 
 // Timestep-cache tables (dit.cu): everything of the DiT's modulation that depends on the timestep only, for `nb`
@@ -646,16 +618,6 @@ int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift, const 
       ELEM(bytes, adaln_rmsnorm_kernel, rows, 256, h, w, shift, scale1p, mod_ld, out, D, rows_per_batch, eps);
   }
 #undef ADALN_WARP
-  ACE_CUDA_CHECK(cudaGetLastError());
-  return ACE_OK;
-}
-
-int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long t_i_stride, bf16* out, int L,
-                     int B, int n, int D, unsigned scale_mask, cudaStream_t stream) {
-  const long total = (long)L * B * n * (D / 8);
-  if (total == 0) return ACE_OK;
-  ELEM(total * 48, mod_table_kernel, (unsigned)((total + 255) / 256), 256, tables, tvec, t_b_stride, t_i_stride,
-       out, L, B, n, D, scale_mask);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;
 }

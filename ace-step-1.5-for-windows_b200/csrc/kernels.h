@@ -42,13 +42,10 @@ int launch_concat_patches(const bf16* ctx, const bf16* xt, bf16* out, int B, int
 
 // out[r, :] = bf16( rmsnorm(h[r, :]) * w ) [* scale1p[b] + shift[b]]  (AdaLN, :490-496, 1488-1493)
 //   shift / scale1p point at this op's rows of the per-step modulation table built by
-//   launch_mod_table (batch stride mod_ld); scale1p == null -> plain RMSNorm.
+//   the caller (batch stride mod_ld); scale1p == null -> plain RMSNorm.  (Used by the condition encoders: the DiT
+//   step itself has no stand-alone norm kernel any more, see epilogues.cuh NormOut / NormIn.)
 int launch_adaln_rmsnorm(const bf16* h, const bf16* w, const bf16* shift, const bf16* scale1p, long mod_ld,
                          bf16* out, int rows, int D, int rows_per_batch, float eps, cudaStream_t stream);
-
-// mods[l][b][i][:] = bf16(tables[l][i] + tvec[b*t_b_stride + i*t_i_stride]) (+1 where scale_mask bit i)
-int launch_mod_table(const bf16* tables, const bf16* tvec, long t_b_stride, long t_i_stride, bf16* out, int L,
-                     int B, int n, int D, unsigned scale_mask, cudaStream_t stream);
 
 // Timestep-cache tables for `nb` consecutive entries starting at `entries` (see tcache_tables_kernel).
 struct TCacheTablesArgs {
