@@ -544,3 +544,52 @@ def test_cross_attention_probabilities_ragged_mid_size(lib):
     assert (p.sum(-1) - 1).abs().max() <= 1e-2
     for l in range(2):
         assert rel_l2(p[l], want[l]) <= 3e-2 and max_abs(p[l], want[l]) <= 2e-2, l
+
+
+def test_timestep_cache_eviction_and_mixed_batches(lib):
+    """The per-handle timestep cache (dit.cu: 96 entries, ring eviction, entries computed on first sight or by
+    ace_dit_prepare_timesteps): more distinct timesteps than entries, batches whose items sit at DIFFERENT
+    timesteps (one cached, one new — including the case where the new entry's slot range would evict the cached
+    one), duplicates inside a batch, and a prepared schedule.  Every result must equal, bit for bit, what a fresh
+    handle computes for the same inputs, and the fp32 oracle within the forward tolerance."""
+    cfg, w = _tiny_dit()
+    g = torch.Generator().manual_seed(77)
+    B, T, E = 2, 33, 9
+    xt = torch.randn(B, T, 64, generator=g).to(torch.bfloat16).to(DEV)
+    ctx = torch.randn(B, T, 128, generator=g).to(torch.bfloat16).to(DEV)
+    enc = torch.randn(B, E, cfg.hidden_size, generator=g).to(torch.bfloat16).to(DEV)
+
+    def fresh(ts):
+        d = B200DiT(w, DiTShape.from_config(cfg), DEV)
+        d.bind(B, T, E)
+        d.set_condition(enc)
+        out = d.step(xt, ctx, ts).clone()
+        torch.cuda.synchronize()
+        d.close()
+        return out
+
+    dit = B200DiT(w, DiTShape.from_config(cfg), DEV)
+    dit.bind(B, T, E)
+    dit.set_condition(enc)
+    bf = lambda x: float(torch.tensor(x, dtype=torch.bfloat16))
+    ts = sorted({bf(i / 257.0) for i in range(1, 257)})[:130]  # 130 distinct bf16 timesteps > 96 entries
+    assert len(ts) == 130
+    first = dit.step(xt, ctx, [ts[0], ts[0]]).clone()
+    mixed = {}
+    for i in range(1, len(ts)):
+        out = dit.step(xt, ctx, [ts[i], ts[i - 1]])  # item 1 cached by the previous step, item 0 new
+        if i in (1, 95, 96, 97, 129):
+            mixed[i] = out.clone()
+    again = dit.step(xt, ctx, [ts[0], ts[0]])  # ts[0] was evicted long ago: recomputed
+    dit.prepare_timesteps(ts[:64] + ts[:8])    # batched fill with duplicates and cached values
+    prepared = dit.step(xt, ctx, [ts[5], ts[60]]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(first, again)
+    assert torch.equal(first, fresh([ts[0], ts[0]]))
+    for i, out in mixed.items():
+        assert torch.equal(out, fresh([ts[i], ts[i - 1]])), i
+    assert torch.equal(prepared, fresh([ts[5], ts[60]]))
+    want = dit_forward(w, cfg, xt.cpu().float(), torch.tensor([ts[5], ts[60]]), ctx.cpu().float(), enc.cpu().float(),
+                       bf16_time=True)
+    assert rel_l2(prepared.cpu().float(), want) <= 2e-2
+    dit.close()
