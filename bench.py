@@ -284,6 +284,37 @@ def time_torch_gpu(wl, dev, dshape, vshape, dit_state, vae_state, cond, null_emb
             "outputs_finite": finite}
 
 
+def cublas_gemm_ab(shapes, dev, reps=20):
+    """cuBLAS (torch.matmul, bf16, fp32 accumulate) on the DiT's GEMM problem shapes, timed like bench.py's own
+    per-launch profile: one CUDA event pair per launch, eager, mean of `reps` — a PLAIN GEMM (no fused epilogue, bf16
+    output), so it bounds what the library path would cost before its separate norm / RoPE / SwiGLU / residual kernels."""
+    import torch
+
+    out = []
+    for sh in shapes:
+        m, n, k = sh["m"], sh["n"], sh["k"]
+        if m > 100000:  # codec shapes: not a library GEMM (tap-shifted convolution)
+            continue
+        a = torch.randn(m, k, device=dev, dtype=torch.bfloat16)
+        b = torch.randn(n, k, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(a, b.t())
+        torch.cuda.synchronize(dev)
+        tot = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b.t())
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        us = tot / reps * 1e3
+        out.append({"m": m, "n": n, "k": k, "cublas_us": round(us, 2), "cublas_tflops": 2.0 * m * n * k / (us * 1e-6) / 1e12,
+                    "this_repo_us": round(sh["ms_total"] / sh["launches"] * 1e3, 2) if sh["launches"] else None,
+                    "this_repo_tflops": sh["tflops"]})
+    return out
+
+
 def run_torch_gpu(args, wl):
     """--impl torch-gpu: the reference's GPU path (see torch_gpu_arm) as a stand-alone arm, rank 0 only."""
     import torch
@@ -628,6 +659,7 @@ def run_b200(args, wl):
         try:
             gb = time_torch_gpu(wl, dev, dshape, vshape, dit_state, vae_state, main.dev_in, main.dev_in["null_emb"])
             gb["speedup_of_this_repo"] = line["value"] / gb["value"]
+            gb["cublas_vs_this_repo_by_gemm_shape"] = cublas_gemm_ab(line["roofline"]["by_shape"], dev)
             line["gpu_baseline"] = gb
         except Exception as exc:
             line["gpu_baseline"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}

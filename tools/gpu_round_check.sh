@@ -3,7 +3,7 @@
 # timings, the ncu launch list of one step and --set full captures.  Everything lands in gpurun_out/.
 #   bash tools/gpu_round_check.sh <tag>        AB=1: also bench c2/c3 with P through shared memory (attention A/B)
 #                                              ATTN=1: also capture the attention kernel with --set full
-V=${1:-v6}
+V=${1:-v5}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -q -x > gpurun_out/gputests.log 2>&1; tail -2 gpurun_out/gputests.log
 timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
@@ -17,15 +17,15 @@ ACE_B200_LIB=$PWD/ace-step-1.5-for-windows_b200/libacestep_b200_probe.so ACE_ATT
 fi
 timeout 120 python tools/profile_output.py > gpurun_out/output_path_timing.log 2>&1; cat gpurun_out/output_path_timing.log
 timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-  --log-file gpurun_out/r1_${V}_launches.csv python tools/profile_step.py > gpurun_out/prof.log 2>&1
+  --log-file gpurun_out/r2_${V}_launches.csv python tools/profile_step.py > gpurun_out/prof.log 2>&1
 timeout 200 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  --kernel-name regex:"abs_peak_kernel|peak_scale_kernel|latent_guard_kernel|cross_probs_kernel" -f -o gpurun_out/r1_${V}_output \
+  --kernel-name regex:"abs_peak_kernel|peak_scale_kernel|latent_guard_kernel|cross_probs_kernel" -f -o gpurun_out/r2_${V}_output \
   python tools/profile_output.py >> gpurun_out/prof.log 2>&1
 if [ -n "$ATTN" ]; then
 PROF_VAE=0 timeout 200 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  --kernel-name regex:attention_tc_kernel --launch-count 4 -f -o gpurun_out/r1_${V}_attn python tools/profile_step.py >> gpurun_out/prof.log 2>&1
+  --kernel-name regex:attention_tc_kernel --launch-count 4 -f -o gpurun_out/r2_${V}_attn python tools/profile_step.py >> gpurun_out/prof.log 2>&1
 PROF_VAE=0 PROF_T=6000 timeout 200 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  --kernel-name regex:attention_tc_kernel --launch-skip 2 --launch-count 1 -f -o gpurun_out/r1_${V}_attn_c3 python tools/profile_step.py >> gpurun_out/prof.log 2>&1
+  --kernel-name regex:attention_tc_kernel --launch-skip 2 --launch-count 1 -f -o gpurun_out/r2_${V}_attn_c3 python tools/profile_step.py >> gpurun_out/prof.log 2>&1
 fi
 for f in gpurun_out/bench_c2.json gpurun_out/bench_c3.json gpurun_out/bench_c1.json gpurun_out/bench_c5.json; do python - "$f" <<'PY'
 import json,sys
