@@ -160,6 +160,7 @@ def test_oracle_device_invariance(full):
     ("c3", 2, 6000, 512),     # configs[2] as benchmarked
     ("c3_e2305", 1, 6000, 2305),  # longest condition sequence once
     ("c2_odd", 2, 1499, 511),  # odd frame count (pad + crop path) and odd E at full width
+    ("max_600s", 2, 15000, 512),  # the reference's maximum duration (600 s, gpu_config.py:294-297): S = 7500 tokens
 ])
 def test_dit_forward_benchmark_shapes(full, name, B, T, E):
     cfg, _, wd, dit = full
@@ -297,3 +298,22 @@ def test_vae_encode_two_minutes_vs_tiled_reference(gain):
         assert err <= max(1.1 * floor, 2e-2), (err, floor)
     else:
         assert err <= max(1.5 * floor, 1e-2), (err, floor)
+
+
+def test_vae_decode_beyond_one_pass_matches_single_pass():
+    """Songs longer than B200Vae.MAX_FRAMES_PER_PASS (8192 frames = 5.5 min; the reference allows 10 min) are decoded
+    in windows with HALO_FRAMES = 16 of overlap-discard.  The codec's receptive field is < 10 latent frames per side
+    (SURVEY §7), and every output sample is computed by the same arithmetic in either schedule, so the windowed decode
+    must equal the single-pass decode of the same latents BIT FOR BIT (shipped architecture, 9000 frames = 6 min)."""
+    sd = make_vae_weights(ovae.VaeConfig(), seed=4, gain=0.5)
+    vae = B200Vae(sd, VaeShape(), DEV)
+    g = torch.Generator().manual_seed(63)
+    frames = 9000
+    z = torch.randn(frames, 64, generator=g).to(torch.bfloat16).to(DEV)
+    assert frames > vae.MAX_FRAMES_PER_PASS
+    windowed = vae.decode(z.T[None])[0]
+    single = vae.decode_frames(z)
+    torch.cuda.synchronize()
+    assert windowed.shape == single.shape == (2, frames * 1920) and torch.isfinite(single).all()
+    assert torch.equal(windowed, single), max_abs(windowed, single)
+    vae.close()
