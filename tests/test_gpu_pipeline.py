@@ -141,3 +141,92 @@ def test_encode_seam_keeps_latents_on_device_and_caches_posterior_moments():
     fresh = h.b200_vae.encode(ref_a.unsqueeze(0), sample=True)[0].transpose(0, 1)  # uncached path, same seed
     assert torch.equal(z1, fresh)
     h.b200_vae.close()
+
+
+def test_init_backends_and_cover_branch_of_prepare_condition_through_the_seam():
+    """`_init_b200_backends` on a handler-shaped host whose model exposes decoder / encoder / tokenizer /
+    detokenizer `state_dict()`s (the weight source the reference's MLX converters use too), then
+    `_b200_prepare_condition` with a mixed is_covers batch: item 0's source latents are replaced by the LM hints
+    (audio tokenizer -> FSQ -> detokenizer on the device, turbo :1630-1646), item 1 keeps its own; the context is
+    [src | chunk_mask].  Checked against the oracle chain (oracle.cond + oracle.tokenizer) on bf16-rounded weights;
+    bounds as in test_gpu_tokenizer.py / test_gpu_kernels.py (FSQ codes may flip next to a rounding boundary, so
+    the hint rows are compared per 5-frame token and >= 80 % of the tokens must agree within 4e-2)."""
+    import types
+
+    from acestep_b200.backend import install
+    from oracle import cond as ocond
+    from oracle import tokenizer as otok
+    from oracle.weights import bf16_round_ as r16
+
+    tcfg = otok.TokConfig.tiny()
+    ccfg = ocond.CondConfig.tiny()
+    dcfg = DiTConfig.tiny()
+    w_dit = r16(make_dit_weights(dcfg, seed=0))
+    w_cond = r16(ocond.make_cond_weights(ccfg, seed=5))
+    w_tok = r16(otok.make_tokenizer_weights(tcfg, seed=9))
+
+    class _SD(torch.nn.Module):            # a module whose state_dict() is the oracle's weight dict
+        def __init__(self, d):
+            super().__init__()
+            self._d = d
+
+        def state_dict(self, *a, **k):
+            return self._d
+
+    sd = _SD
+    strip = lambda p: {k[len(p):]: v for k, v in w_tok.items() if k.startswith(p)}
+    cfg = types.SimpleNamespace(**{**vars(tcfg), **vars(ccfg), **vars(dcfg), "is_turbo": False})
+    cfg.layer_types = dcfg.layer_types
+
+    class Host:
+        device, dtype = DEV, torch.bfloat16
+
+        def _execute_service_generate_diffusion(self, *a, **k):
+            raise AssertionError("not used")
+
+        def tiled_decode(self, *a, **k):
+            raise AssertionError("not used")
+
+        def tiled_encode(self, *a, **k):
+            raise AssertionError("not used")
+
+    h = install(Host())
+    h.model = types.SimpleNamespace(decoder=sd(w_dit), encoder=sd(w_cond), tokenizer=sd(strip("tokenizer.")),
+                                    detokenizer=sd(strip("detokenizer.")), config=cfg,
+                                    null_condition_emb=make_null_condition_emb(dcfg))
+    h.config = cfg
+    dit_status, vae_status = h._init_b200_backends(dit=True, vae=False, cond=True)
+    assert "condition encoder" in dit_status and vae_status == "Disabled"
+    assert h.use_b200_dit and h.use_b200_cond and h.b200_tok is not None
+
+    g = torch.Generator().manual_seed(91)
+    B, T = 2, 23
+    text = torch.randn(B, 6, ccfg.text_hidden_dim, generator=g).to(torch.bfloat16)
+    lyric = torch.randn(B, 12, ccfg.text_hidden_dim, generator=g).to(torch.bfloat16)
+    refer = torch.randn(B, 10, ccfg.timbre_hidden_dim, generator=g).to(torch.bfloat16)
+    tm, lm = torch.ones(B, 6, dtype=torch.long), torch.ones(B, 12, dtype=torch.long)
+    order = torch.tensor([0, 1])
+    hidden = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    src = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    silence = torch.randn(1, 40, 64, generator=g).to(torch.bfloat16)
+    chunk = torch.ones(B, T, 64)
+    is_covers = torch.tensor([1, 0])
+    enc, enc_mask, ctx = h._b200_prepare_condition(
+        text_hidden_states=text.to(DEV), text_attention_mask=tm.to(DEV), lyric_hidden_states=lyric.to(DEV),
+        lyric_attention_mask=lm.to(DEV), refer_audio_acoustic_hidden_states_packed=refer.to(DEV),
+        refer_audio_order_mask=order.to(DEV), hidden_states=hidden.to(DEV), attention_mask=torch.ones(B, T, device=DEV),
+        silence_latent=silence.to(DEV), src_latents=src.to(DEV), chunk_masks=chunk.to(DEV), is_covers=is_covers.to(DEV))
+    torch.cuda.synchronize()
+    assert ctx.shape == (B, T, 128) and enc.dtype == torch.bfloat16
+    want_enc, want_mask = ocond.condition_encoder(w_cond, ccfg, text.float(), tm, lyric.float(), lm, refer.float(), order)
+    assert torch.equal(enc_mask.cpu(), want_mask)
+    assert rel_l2(enc.cpu().float(), want_enc) <= 3e-2
+    want_src = otok.lm_hints(w_tok, tcfg, hidden.float(), silence.float(), torch.ones(B, T), src.float(), is_covers)
+    got_src = ctx[..., :64].cpu().float()
+    assert torch.equal(ctx[..., 64:].cpu().float(), chunk)
+    assert torch.equal(got_src[1], src[1].float())               # not a cover: untouched
+    assert not torch.equal(got_src[0], src[0].float())           # cover: replaced by the hints
+    tok_err = [rel_l2(got_src[0, 5 * k: 5 * k + 5], want_src[0, 5 * k: 5 * k + 5]) for k in range(4)]
+    assert sum(e <= 4e-2 for e in tok_err) >= 3, tok_err
+    for eng in (h.b200_dit, h.b200_cond, h.b200_tok):
+        eng.close()
