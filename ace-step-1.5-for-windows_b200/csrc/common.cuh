@@ -243,6 +243,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// the stores of this thread's committed groups have finished READING shared memory (the source may be reused)
+__device__ __forceinline__ void tma_store_wait_read_all() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
                                             int c0, int c1, int c2) {
   asm volatile(

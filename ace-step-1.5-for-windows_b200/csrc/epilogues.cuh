@@ -485,7 +485,9 @@ struct EpiGatedResid {
     }
     return t;
   }
-  template <class Acc>
+  // WITH_G = false: h (and the sum of squares) only; g is then made in place by tail_g() once h's store has read
+  // the box (the every-tile variant of the pair kernel has no second box to put it in).
+  template <bool WITH_G = true, class Acc>
   __device__ __forceinline__ void tail_box(const Acc& acc, int acc_col, int r, int row, int col, int M,
                                            uint8_t* hbox, uint8_t* gbox, const TailPre& pre) const {
     uint32_t raw[2][32];
@@ -499,7 +501,7 @@ struct EpiGatedResid {
 #pragma unroll
       for (int q = 0; q < 8; ++q) gv[q] = __ldg(gp + q);
     }
-    if (no.g != nullptr) {
+    if (WITH_G && no.g != nullptr) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) cv[q] = __ldg(cp + q);
     }
@@ -533,7 +535,7 @@ struct EpiGatedResid {
         unpack_bf16x2(res.z, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
         unpack_bf16x2(res.w, x0, x1); ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss);
       }
-      if (no.g != nullptr) {
+      if (WITH_G && no.g != nullptr) {
         uint4 gq;
         gq.x = bmul2(res.x, cv[q].x); gq.y = bmul2(res.y, cv[q].y);
         gq.z = bmul2(res.z, cv[q].z); gq.w = bmul2(res.w, cv[q].w);
@@ -542,6 +544,17 @@ struct EpiGatedResid {
     }
     ACE_TCLK(19);
     if (no.ssp != nullptr && row < M) no.ssp[(size_t)row * no.nss + (col >> 6)] = ss;
+  }
+  // g = h * c in place over a box that holds the NEW h (same products as tail_box / run make)
+  __device__ __forceinline__ void tail_g(int r, int col, uint8_t* hbox, const TailPre& pre) const {
+    const uint4* cp = reinterpret_cast<const uint4*>(pre.crow + col);
+    const uint32_t rowoff = (uint32_t)r * 128u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4* hs = reinterpret_cast<uint4*>(hbox + rowoff + (uint32_t)((q ^ (r & 7)) << 4));
+      const uint4 v = *hs, c = __ldg(cp + q);
+      *hs = make_uint4(bmul2(v.x, c.x), bmul2(v.y, c.y), bmul2(v.z, c.z), bmul2(v.w, c.w));
+    }
   }
   __device__ __forceinline__ int gsel(int row, int M) const {
     const int b = row < M ? row / S : 0;

@@ -434,28 +434,38 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define ACE_STAMP(i) do { } while (0)
 #endif
 
-template <int BN, int STAGES, class Epi>
+// ALLTAIL (multi-wave problems of a kTmaTail epilogue): EVERY tile ends in the tail path.  The residual boxes get
+// their own shared memory (NBOX x 16 KB after the ring, in place of the per-warp staging slabs; the 256-wide tile
+// gives up one ring stage for it), warp 3 loads the next tile's boxes as soon as the epilogue has handed the
+// previous ones back (resid_empty), h is updated in place and stored by TMA, then g = h * c is made in place in the
+// same box once that store has read it.  The slab path it replaces spent about as long per 256-wide tile as the
+// main loop (per-row global loads of the residual, two staged store passes).
+template <int BN, int STAGES, class Epi, bool ALLTAIL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const GemmShape shp, const __grid_constant__ Epi epi) {
   // BN = 256, or 192 for epilogues that accept 64-column sub-tiles: 256 x 192 pair tiles turn the
   // 48-tile N = 2048 problems of the DiT (48 of 74 clusters busy) into 66 tiles (66 of 74).
   static_assert(BN == 256 || (BN == 192 && Epi::kHalfTile), "pair tile width");
+  static_assert(!ALLTAIL || Epi::kTmaTail, "ALLTAIL needs a tail-path epilogue");
   constexpr int HALF = BN / 2;       // B rows staged by each CTA of the pair
   using L = GemmSmem<HALF, STAGES>;  // per-CTA stage: 128 A rows + HALF B rows
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr int BOX_BYTES = ALLTAIL ? (BN / 64) * L::A_BYTES : 0;  // dedicated residual boxes (ALLTAIL)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * L::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint8_t* boxes = smem + STAGES * L::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + BOX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint64_t* resid_bar = bars + 2 * STAGES + 6;  // [4]
+  uint64_t* resid_bar = bars + 2 * STAGES + 6;     // [4] residual box i has landed
+  uint64_t* resid_empty = bars + 2 * STAGES + 10;  // [2] ALLTAIL: column group g's boxes may be reloaded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -478,6 +488,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
     }
     for (int i = 0; i < 4; ++i) mbar_init(&resid_bar[i], 1);  // tail path: one per 64-column residual box
+    for (int i = 0; i < 2; ++i) mbar_init(&resid_empty[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -539,7 +550,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
       }
     }
-    if constexpr (Epi::kTmaTail) {
+    if constexpr (Epi::kTmaTail && !ALLTAIL) {
       // Residual boxes of the last tile: they ride the operand ring as NBOX extra "k-blocks" that nobody feeds to
       // the tensor core — box i lands in the A part of the next ring slot as soon as the MMAs that read it have
       // retired (5 k-blocks before the main loop ends), i.e. it is in shared memory before the accumulator is.
@@ -613,6 +624,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
 #endif
     }
+  } else if (warp == 3) {
+    if constexpr (ALLTAIL) {
+      // ---------------- residual loader (both CTAs): tile i+1's boxes as soon as tile i's are handed back -------
+      const bool elected = elect_one();
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
+        const int tile_n0 = (tile / m_tiles) * BN;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&resid_empty[g], (uint32_t)((it & 1) ^ 1));
+          if (elected) {
+            for (int bi = 2 * g; bi < 2 * g + 2 && bi < NBOX; ++bi) {
+              if (tile_n0 + 64 * bi >= shp.N) break;
+              mbar_arrive_expect_tx(&resid_bar[bi], L::A_BYTES);
+              tma_load_2d(boxes + bi * L::A_BYTES, &epi.tm_h, &resid_bar[bi], tile_n0 + 64 * bi, m0);
+            }
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ---------------- epilogue (both CTAs, each on its own 128 accumulator rows) ----------------
     // warps 4-7 take tile columns [0,128), warps 8-11 columns [128,256); warp w reads TMEM lanes
@@ -621,6 +652,66 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int quarter = (warp - 4) & 3;
     const int sub = ((warp - 4) >> 2) * 128;
     int it = 0;
+    if constexpr (ALLTAIL) {
+      const int grp = (warp - 4) >> 2;    // column group: boxes [2 grp, 2 grp + 2) of the tile
+      const int r = quarter * 32 + lane;  // row inside this CTA's 128-row tile
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
+        const int tile_n0 = (tile / m_tiles) * BN;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const auto tpre = epi.tail_prefetch(m0 + r, shp.M, shp.N, tile_n0 + 128 * grp, 128);
+        mbar_wait(&tfull_bar[as], aphase);
+        if (threadIdx.x == 128) ACE_STAMP(5);
+        tcgen05_fence_after();
+        __syncwarp();
+        AccTmem acc{tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN)};
+#pragma unroll 1
+        for (int bi = 2 * grp; bi < 2 * grp + 2 && bi < NBOX; ++bi) {
+          const int col = tile_n0 + 64 * bi;
+          if (col >= shp.N) break;  // group-uniform
+          uint8_t* hbox = boxes + bi * L::A_BYTES;
+          mbar_wait(&resid_bar[bi], (uint32_t)(it & 1));
+          epi.template tail_box<false>(acc, 64 * bi, r, m0 + r, col, shp.M, hbox, nullptr, tpre);
+          fence_proxy_async_smem();  // this thread's smem writes -> visible to the TMA store
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (quarter == 0 && elect_one()) {
+            tma_store_2d(&epi.tm_h, hbox, col, m0);
+            tma_store_commit();
+          }
+        }
+        tcgen05_fence_before();  // the accumulator is free: the next tile's MMAs may overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+        if (epi.no.g != nullptr) {
+          if (quarter == 0) tma_store_wait_read_all();  // h's stores have read the boxes
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll 1
+          for (int bi = 2 * grp; bi < 2 * grp + 2 && bi < NBOX; ++bi) {
+            const int col = tile_n0 + 64 * bi;
+            if (col >= shp.N) break;
+            epi.tail_g(r, col, boxes + bi * L::A_BYTES, tpre);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (quarter == 0 && elect_one()) {
+            for (int bi = 2 * grp; bi < 2 * grp + 2 && bi < NBOX; ++bi) {
+              const int col = tile_n0 + 64 * bi;
+              if (col >= shp.N) break;
+              tma_store_2d(&epi.tm_g, boxes + bi * L::A_BYTES, col, m0);
+            }
+            tma_store_commit();
+          }
+        }
+        if (quarter == 0) {
+          tma_store_wait_read_all();  // (only the lane that issued has pending groups)
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&resid_empty[grp]);
+        }
+        if (threadIdx.x == 128) ACE_STAMP(6);
+      }
+      if (quarter == 0) tma_store_wait_all();
+    } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
       const int n0 = (tile / m_tiles) * BN + sub;
@@ -628,7 +719,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
       const WarpStage stg{smem + L::OFF_EPI + (warp - 4) * 4096};
-      if constexpr (Epi::kTmaTail) {
+      if constexpr (Epi::kTmaTail && !ALLTAIL) {
         if (tma_tail && tile == last_tile) {
           // ---- tail path: residual already in shared memory (TMA), update in place, h / g leave by TMA ----
           const int grp = (warp - 4) >> 2;                 // column group: boxes [2 grp, 2 grp + 2) of the tile
@@ -773,6 +864,24 @@ int launch_gemm_bn(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   return ACE_OK;
 }
 
+// every-tile tail variant: BN = 256 runs a 5-stage ring (5 x 32 KB + 4 boxes x 16 KB), BN = 192 keeps 6 stages
+template <int BN, class Epi>
+int launch_gemm_pair_alltail(const GemmPlan& p, const Epi& epi, int grid, cudaStream_t stream) {
+  constexpr int STAGES = BN == 256 ? 5 : 6;
+  using L = GemmSmem<BN / 2, STAGES>;
+  constexpr size_t SMEM = (size_t)STAGES * L::STAGE_BYTES + (BN / 64) * L::A_BYTES + L::BAR_BYTES + 1024;
+  static_assert(SMEM <= 232448, "ALLTAIL shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ACE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, Epi, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<BN, STAGES, Epi, true>, dim3(grid), dim3(GEMM2_THREADS), SMEM, stream,
+                               p.tma_a, p.tma_b, p.shp, epi));
+  return ACE_OK;
+}
+
 template <int BN, int STAGES, class Epi>
 int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   using L = GemmSmem<BN / 2, STAGES>;
@@ -788,12 +897,27 @@ int launch_gemm_pair(const GemmPlan& p, const Epi& epi, cudaStream_t stream) {
   if (const char* e = getenv("ACE_GEMM_MAX_CLUSTERS")) max_clusters = atoi(e);  // probe builds only
 #endif
   const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
+  bool alltail = false;
+  if constexpr (Epi::kTmaTail) {
+    static const bool off = probe_env("ACE_NO_ALLTAIL") != nullptr;  // probe builds: A/B against the slab path
+    static const int kb_max = probe_env("ACE_ALLTAIL_KB") ? atoi(probe_env("ACE_ALLTAIL_KB")) : 1 << 30;
+    alltail = epi.use_tma != 0 && tiles > max_clusters && !off &&
+              (BN == 192 || p.shp.ntaps * p.shp.kblocks_per_tap <= kb_max);
+  }
   const double ktot = (double)p.shp.ntaps * p.shp.kblocks_per_tap * GEMM_BK;
   prof_tag_gemm(p.shp.M, p.shp.N, (int)ktot);
   prof_begin(PROF_GEMM, 2.0 * p.shp.M * p.shp.N * ktot,
              2.0 * ((double)p.shp.M * p.shp.kblocks_per_tap * GEMM_BK + (double)p.shp.N * ktot +
                     (double)p.shp.M * p.shp.N),
              stream);
+  if constexpr (Epi::kTmaTail) {
+    if (alltail) {
+      ACE_PROPAGATE((launch_gemm_pair_alltail<BN, Epi>(p, epi, grid, stream)));
+      prof_end(stream);
+      ACE_CUDA_CHECK(cudaGetLastError());
+      return ACE_OK;
+    }
+  }
   ACE_CUDA_CHECK(launch_kernel(gemm_tc2_kernel<BN, STAGES, Epi>, dim3(grid), dim3(GEMM2_THREADS),
                                (size_t)L::TOTAL, stream, p.tma_a, p.tma_b, p.shp, epi));
   prof_end(stream);

@@ -9,8 +9,8 @@
 #include "../ace-step-1.5-for-windows_b200/csrc/gemm.cuh"
 using namespace ace;
 
-int main() {
-  const int M = 1500, S = 750;
+int main(int argc, char** argv) {
+  const int M = argc > 1 ? atoi(argv[1]) : 1500, S = M / 2;  // M = 6000: multi-wave (the every-tile tail variant)
   const int shapes[4][2] = {{2048, 2048}, {4096, 2048}, {12288, 2048}, {2048, 6144}};
   char* flush;
   cudaMalloc(&flush, 256u << 20);
