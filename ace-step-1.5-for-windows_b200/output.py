@@ -52,8 +52,8 @@ def peak_normalize_(wav: torch.Tensor, peak: Optional[torch.Tensor] = None,
     return peak
 
 
-def latent_flags(lat: torch.Tensor) -> Tuple[bool, bool]:
-    """(any NaN/Inf, any non-zero) of a CUDA bf16 tensor — one kernel, one 8-byte device->host read."""
+def latent_flags_enqueue(lat: torch.Tensor) -> torch.Tensor:
+    """Queue the guard kernel; returns its int32[2] device result (any NaN/Inf, any non-zero) without reading it."""
     if not lat.is_cuda:
         raise _lib.B200Error("latent_flags: the B200 output path needs a CUDA tensor (no CPU fallback)")
     if lat.dtype != torch.bfloat16:
@@ -63,15 +63,25 @@ def latent_flags(lat: torch.Tensor) -> Tuple[bool, bool]:
     with torch.cuda.device(lat.device):
         _lib.check(_lib.load().ace_latent_guard(lat.data_ptr(), lat.numel(), flags.data_ptr(),
                                                 _lib.stream_handle(lat.device)), "ace_latent_guard")
-    bad, nonzero = flags.tolist()
+    return flags
+
+
+def latent_flags(lat: torch.Tensor) -> Tuple[bool, bool]:
+    """(any NaN/Inf, any non-zero) of a CUDA bf16 tensor — one kernel, one 8-byte device->host read."""
+    bad, nonzero = latent_flags_enqueue(lat).tolist()
     return bool(bad), bool(nonzero)
 
 
-def check_latents(lat: torch.Tensor) -> None:
+def raise_on_flags(bad, nonzero, numel: int) -> None:
     """The reference's guard, same order and same leading sentence of each message: RuntimeError on NaN/Inf,
     then on all-zero latents (only when there is at least one element)."""
-    bad, nonzero = latent_flags(lat)
     if bad:
         raise RuntimeError(NAN_MESSAGE)
-    if lat.numel() > 0 and not nonzero:
+    if numel > 0 and not nonzero:
         raise RuntimeError(ZERO_MESSAGE)
+
+
+def check_latents(lat: torch.Tensor) -> None:
+    """Guard + host decision in one call (one host synchronisation)."""
+    bad, nonzero = latent_flags(lat)
+    raise_on_flags(bad, nonzero, lat.numel())

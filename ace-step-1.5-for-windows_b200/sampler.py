@@ -80,6 +80,26 @@ class B200Sampler:
         self.null_condition_emb = None
         if null_condition_emb is not None:
             self.null_condition_emb = null_condition_emb.detach().to(self.device, torch.bfloat16)
+        self._sched: Dict[Any, torch.Tensor] = {}  # (infer_steps, shift) -> bf16 schedule, host copy
+
+    def _base_schedule(self, infer_steps: int, shift: float, timesteps) -> torch.Tensor:
+        """The base / sft timestep schedule as a HOST bf16 tensor.  linspace and the shift formula run on the device
+        in the model dtype exactly like the reference (base :1895-1899) — once per (steps, shift); the host copy is
+        kept, so a steady-state request reads no device value back (each `.tolist()` on a device tensor is a host
+        synchronisation that drains the queue between two songs).  Explicit `timesteps` (sft :1866-1873) are a pure
+        dtype conversion, which rounds the same on either side."""
+        bf = torch.bfloat16
+        if timesteps is not None:
+            return torch.as_tensor(timesteps).detach().to("cpu").to(bf)
+        key = (int(infer_steps), float(shift))
+        t = self._sched.get(key)
+        if t is None:
+            t = torch.linspace(1.0, 0.0, infer_steps + 1, device=self.device, dtype=bf)
+            if shift != 1.0:
+                t = shift * t / (1 + (shift - 1) * t)
+            t = t.cpu()
+            self._sched[key] = t
+        return t
 
     # ------------------------------------------------------------------
     def _stream(self):
@@ -121,7 +141,9 @@ class B200Sampler:
                        audio_cover_strength: float = 1.0, cover_noise_strength: float = 0.0,
                        encoder_hidden_states_non_cover=None, context_latents_non_cover=None,
                        noise: Optional[torch.Tensor] = None, sde_noise: Optional[Sequence[torch.Tensor]] = None,
-                       ) -> Dict[str, Any]:
+                       sync: bool = True) -> Dict[str, Any]:
+        """`sync=False`: return as soon as the loop is enqueued (no host synchronisation anywhere in the call; the
+        time costs are then enqueue times) — for callers that queue the decode right behind it."""
         self._validate(encoder_hidden_states, context_latents, src_latents, infer_method, timesteps,
                        encoder_hidden_states_non_cover, context_latents_non_cover)
         t0 = time.time()
@@ -139,7 +161,7 @@ class B200Sampler:
             sched = sched[sched.index(nearest):]
         else:
             xt = noise.clone()
-        t_sched = torch.tensor(sched, device=self.device, dtype=torch.bfloat16).tolist()
+        t_sched = torch.tensor(sched, dtype=torch.bfloat16).tolist()  # the model-dtype rounding of the table (host)
         n = len(t_sched)
         cover_steps = int(n * audio_cover_strength)
         self.dit.bind(B, T, enc.shape[1])
@@ -176,9 +198,10 @@ class B200Sampler:
             else:
                 self._euler(xt, vt, _bf16(t_cur - t_next))
         xt = xt.clone()  # the slots are reused by the next request
-        torch.cuda.synchronize(self.device)
+        if sync:
+            torch.cuda.synchronize(self.device)
         t1 = time.time()
-        return {"target_latents": xt,
+        return {"target_latents": xt, "steps": n,
                 "time_costs": {"diffusion_time_cost": t1 - t0, "diffusion_per_step_time_cost": (t1 - t0) / max(n, 1),
                                "total_time_cost": t1 - t0}}
 
@@ -190,7 +213,8 @@ class B200Sampler:
                       cover_noise_strength: float = 0.0, encoder_hidden_states_non_cover=None,
                       context_latents_non_cover=None, null_condition_emb: Optional[torch.Tensor] = None,
                       noise: Optional[torch.Tensor] = None, sde_noise: Optional[Sequence[torch.Tensor]] = None,
-                      ) -> Dict[str, Any]:
+                      sync: bool = True) -> Dict[str, Any]:
+        """`sync=False`: see generate_turbo."""
         self._validate(encoder_hidden_states, context_latents, src_latents, infer_method, timesteps,
                        encoder_hidden_states_non_cover, context_latents_non_cover)
         t0 = time.time()
@@ -198,12 +222,7 @@ class B200Sampler:
         enc, ctx, src = self._to(encoder_hidden_states), self._to(context_latents), self._to(src_latents)
         enc_nc, ctx_nc = self._to(encoder_hidden_states_non_cover), self._to(context_latents_non_cover)
         B, T, _ = ctx.shape
-        if timesteps is not None:  # sft variant: explicit schedule including the trailing 0
-            t = torch.as_tensor(timesteps).to(device=dev, dtype=bf)
-        else:
-            t = torch.linspace(1.0, 0.0, infer_steps + 1, device=dev, dtype=bf)
-            if shift != 1.0:
-                t = shift * t / (1 + (shift - 1) * t)
+        t = self._base_schedule(infer_steps, shift, timesteps)  # host bf16; sft: explicit schedule incl. the trailing 0
         if noise is None:
             noise = prepare_noise((B, T, ctx.shape[-1] // 2), seed, dev)
         noise = self._to(noise)
@@ -288,8 +307,9 @@ class B200Sampler:
             else:
                 self._euler(xt, v, dts[i], dup)
         xt = xt.clone()  # the slots are reused by the next request
-        torch.cuda.synchronize(dev)
+        if sync:
+            torch.cuda.synchronize(dev)
         t1 = time.time()
-        return {"target_latents": xt,
+        return {"target_latents": xt, "steps": n,
                 "time_costs": {"diffusion_time_cost": t1 - t0, "diffusion_per_step_time_cost": (t1 - t0) / max(n, 1),
                                "total_time_cost": t1 - t0}}

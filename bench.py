@@ -370,20 +370,23 @@ class Runner:
 
     # the starting noise is drawn INSIDE the song (seeded torch generator on the device), like the reference's
     # generate_audio -> prepare_noise (turbo :1917, base :1899)
+    # Both closures only ENQUEUE the song (B200Pipeline.generate_async / repaint_async -> PendingSong); the loops
+    # below keep one song in flight behind the one being waited for (SongPipeline(depth=1)), which is how a serving
+    # loop calls the product API.
     def song_device(self, i):
         if self.rp:
-            return self.pipe.repaint(self.dev_in["enc"], self.audio_d, self.rp[0], self.rp[1], self.sil_d,
-                                     [self.seed0 + i], posterior_eps=self.eps_d, to_host=False, **self.skw)
-        return self.pipe.generate(self.dev_in["enc"], self.dev_in["ctx"], self.dev_in["src"], [self.seed0 + i],
-                                  to_host=False, **self.skw)
+            return self.pipe.repaint_async(self.dev_in["enc"], self.audio_d, self.rp[0], self.rp[1], self.sil_d,
+                                           [self.seed0 + i], posterior_eps=self.eps_d, to_host=False, **self.skw)
+        return self.pipe.generate_async(self.dev_in["enc"], self.dev_in["ctx"], self.dev_in["src"], [self.seed0 + i],
+                                        to_host=False, **self.skw)
 
     def song_host(self, i):
         if self.rp:
-            return self.pipe.repaint(self.host["enc"], self.audio_h, self.rp[0], self.rp[1], self.sil_h,
-                                     [self.seed0 + i], posterior_eps=self.eps_h, to_host=True, reuse_host_buffer=True,
-                                     **self.skw)
-        return self.pipe.generate(self.host["enc"], self.host["ctx"], self.host["src"], [self.seed0 + i],
-                                  to_host=True, reuse_host_buffer=True, **self.skw)
+            return self.pipe.repaint_async(self.host["enc"], self.audio_h, self.rp[0], self.rp[1], self.sil_h,
+                                           [self.seed0 + i], posterior_eps=self.eps_h, to_host=True,
+                                           reuse_host_buffer=True, **self.skw)
+        return self.pipe.generate_async(self.host["enc"], self.host["ctx"], self.host["src"], [self.seed0 + i],
+                                        to_host=True, reuse_host_buffer=True, **self.skw)
 
     def h2d_bytes(self):
         if self.rp:
@@ -446,7 +449,7 @@ def run_b200(args, wl):
     from acestep_b200 import _lib
     from acestep_b200.dit import DiTShape
     from acestep_b200.multi_gpu import GatherPipeline, generate_sharded
-    from acestep_b200.pipeline import B200Pipeline
+    from acestep_b200.pipeline import B200Pipeline, SongPipeline
     from acestep_b200.synthetic import random_dit_state, random_vae_state
     from acestep_b200.vae import VaeShape
 
@@ -468,23 +471,30 @@ def run_b200(args, wl):
         rank i, asynchronous waveform gather to rank 0 that overlaps the next song, drained inside the region).
         e2e: the same through the public API with pinned HOST inputs and a HOST waveform (wall clock)."""
         lengths = [r.n_samples] * world
-        pipe_g, keep = GatherPipeline(depth=1), {}
+        pipe_g, pipe_s, keep = GatherPipeline(depth=1), SongPipeline(depth=1), {}
         counter = [0]
+
+        def retire(out):
+            if out is not None:
+                keep["out"] = out
 
         def step_device():
             i = counter[0]
             counter[0] += 1
             if world == 1:
-                keep["out"] = r.song_device(i)
+                retire(pipe_s.submit(r.song_device(i)))  # song i enqueued; song i - 1 waited for and guard-checked
                 return
             def one(_song_index):
-                keep["out"] = r.song_device(i)
-                return keep["out"]["audio"][0]
+                pend = r.song_device(i)
+                wav = pend._res["audio"][0]  # device tensor, stream-ordered: the gather is queued behind the song
+                retire(pipe_s.submit(pend))
+                return wav
             # at most one gather in flight: the previous song's gather (finished long ago) is retired here, which
             # hands its buffers back to the allocator before this song's successor needs memory
             pipe_g.submit(generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True))
 
         def drain():
+            retire(pipe_s.drain())
             return pipe_g.drain()
 
         # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop;
@@ -494,7 +504,7 @@ def run_b200(args, wl):
         if verify and world > 1:
             # once, through the RAGGED mode of the product API (length exchange + padded gather) and checked
             def one(_i):
-                keep["out"] = r.song_device(0)
+                keep["out"] = r.song_device(0).wait()
                 return keep["out"]["audio"][0]
             songs = generate_sharded(one, world, dst=0, device=dev)
             if rank == 0:
@@ -520,12 +530,14 @@ def run_b200(args, wl):
         if gathered is not None:
             finite = finite and all(bool(torch.isfinite(s).all()) for s in gathered)
         # ---- e2e
-        r.song_host(0)
+        r.song_host(0).wait()
         barrier()
         barrier()
         t0 = time.perf_counter()
+        pipe_h, oh = SongPipeline(depth=1), None
         for i in range(steps):
-            oh = r.song_host(10 + i)
+            oh = pipe_h.submit(r.song_host(10 + i)) or oh  # host waveform of song i - 1 (pinned, two buffers alternate)
+        oh = pipe_h.drain() or oh
         barrier()
         t1 = time.perf_counter()
         res = {"ms": ms, "launches": int(launches), "finite": finite, "e2e_s": t1 - t0,
@@ -555,7 +567,7 @@ def run_b200(args, wl):
         import ctypes as C
 
         lib.ace_profile_start()
-        main.song_device(0)  # rank-local: no collective here, the other ranks are already past the timed region
+        main.song_device(0).wait()  # rank-local: no collective here, the other ranks are already past the timed region
         pms, pfl, pby, pln = (C.c_float * 4)(), (C.c_double * 4)(), (C.c_double * 4)(), (C.c_int * 4)()
         _lib.check(lib.ace_profile_stop(pms, pfl, pby, pln))
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))

@@ -230,3 +230,51 @@ def test_init_backends_and_cover_branch_of_prepare_condition_through_the_seam():
     assert sum(e <= 4e-2 for e in tok_err) >= 3, tok_err
     for eng in (h.b200_dit, h.b200_cond, h.b200_tok):
         eng.close()
+
+
+def test_async_pipeline_matches_blocking_calls_and_defers_the_latent_guard():
+    """`generate_async` + `SongPipeline(depth=1)` (no host synchronisation inside a song; the next song is enqueued
+    while the previous one runs) must hand out exactly what the blocking `generate` returns for the same seeds — the
+    static I/O slots, the timestep cache and the two alternating pinned buffers are reused in stream order — and the
+    reference's latent guard (generate_music_decode.py:66-77) must still fire, at `wait()`, before any audio is
+    handed out."""
+    from acestep_b200.output import NAN_MESSAGE
+    from acestep_b200.pipeline import SongPipeline
+
+    cfg, vcfg = DiTConfig.tiny(), ovae.VaeConfig.tiny()
+    w = bf16_round_(make_dit_weights(cfg, seed=0))
+    vsd = make_vae_weights(vcfg, seed=3)
+    null = make_null_condition_emb(cfg).to(torch.bfloat16)
+    vshape = VaeShape(encoder_hidden_size=vcfg.encoder_hidden_size, downsampling_ratios=vcfg.downsampling_ratios,
+                      channel_multiples=vcfg.channel_multiples, decoder_channels=vcfg.decoder_channels)
+    pipe = B200Pipeline(w, vsd, DiTShape.from_config(cfg), vshape, null, DEV, turbo=False)
+    g = torch.Generator().manual_seed(21)
+    T, E = 40, 12
+    enc = torch.randn(1, E, cfg.hidden_size, generator=g).to(torch.bfloat16).pin_memory()
+    src = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    ctx = torch.cat([src, torch.ones(1, T, 64, dtype=torch.bfloat16)], -1).pin_memory()
+    kw = dict(infer_steps=4, diffusion_guidance_sale=4.0, shift=3.0)
+    want = [pipe.generate(enc, ctx, src, [s], **kw) for s in (5, 6, 7)]
+    want = [{k: o[k].clone() for k in ("audio", "target_latents", "peak")} for o in want]
+    q, got = SongPipeline(depth=1), []
+    for s in (5, 6, 7):
+        out = q.submit(pipe.generate_async(enc, ctx, src, [s], reuse_host_buffer=True, **kw))
+        if out is not None:
+            got.append({k: out[k].clone() for k in ("audio", "target_latents", "peak")})
+    out = q.drain()
+    got.append({k: out[k].clone() for k in ("audio", "target_latents", "peak")})
+    assert len(got) == 3
+    for a, b in zip(got, want):
+        for k in a:
+            assert torch.equal(a[k].cpu(), b[k].cpu()), k
+    assert not torch.equal(got[0]["audio"], got[1]["audio"])  # different seeds: different songs
+    for k in ("diffusion_time_cost", "diffusion_per_step_time_cost", "vae_decode_time_cost", "total_time_cost"):
+        assert out["time_costs"][k] > 0.0
+
+    bad = enc.clone()
+    bad[0, 0, 0] = float("nan")
+    pending = pipe.generate_async(bad, ctx, src, [5], **kw)   # enqueues fine
+    with pytest.raises(RuntimeError, match=NAN_MESSAGE[:20]):
+        pending.wait()
+    assert torch.isfinite(pipe.generate(enc, ctx, src, [5], **kw)["audio"]).all()  # the engine is still usable
+    pipe.close()
