@@ -51,6 +51,10 @@ struct GemmShape {
   int splits;
   float* part;
   unsigned* sync;
+  // Tile order of the CTA-pair kernel: 0 = m fastest (consecutive clusters share a B tile; B is streamed from HBM
+  // once, A is re-read once per wave), 1 = n fastest (consecutive clusters share an A row block; A is streamed
+  // once and B — the smaller operand — stays in L2).  make_gemm_plan sets it to "A is the larger operand".
+  int raster_n;
 };
 
 #ifdef __CUDACC__
@@ -506,6 +510,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int m_tiles = (shp.M + 255) / 256;
   const int n_tiles = (shp.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
+  const bool nfast = shp.raster_n != 0;
+  auto tile_m = [&](int t) { return nfast ? t / n_tiles : t % m_tiles; };
+  auto tile_n = [&](int t) { return nfast ? t % n_tiles : t / m_tiles; };
   const int total_kb = shp.ntaps * shp.kblocks_per_tap;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
@@ -523,8 +530,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-      const int n0 = (tile / m_tiles) * BN + (int)rank * HALF;
+      const int m0 = tile_m(tile) * 256 + (int)rank * 128;
+      const int n0 = tile_n(tile) * BN + (int)rank * HALF;
       int tap = 0, kk = 0;
       int a_row = m0 + shp.shift[0];  // refreshed after the loads of a tap's last block (off the issue path)
       for (int kb = 0; kb < total_kb; ++kb) {
@@ -555,8 +562,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       // the tensor core — box i lands in the A part of the next ring slot as soon as the MMAs that read it have
       // retired (5 k-blocks before the main loop ends), i.e. it is in shared memory before the accumulator is.
       if (tma_tail && my_tiles > 0) {
-        const int m0 = (last_tile % m_tiles) * 256 + (int)rank * 128;
-        const int n0 = (last_tile / m_tiles) * BN;
+        const int m0 = tile_m(last_tile) * 256 + (int)rank * 128;
+        const int n0 = tile_n(last_tile) * BN;
         for (int i = 0; i < NBOX; ++i) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elected && n0 + 64 * i < shp.N) {
@@ -627,11 +634,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp == 3) {
     if constexpr (ALLTAIL) {
       // ---------------- residual loader (both CTAs): tile i+1's boxes as soon as tile i's are handed back -------
+      // (resid_bar[i] only flips on tiles that HAVE box i — the last column tile of N = 2048 at 192-wide tiles has
+      // two — so its parity is counted per box on both sides, not derived from the tile counter)
       const bool elected = elect_one();
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-        const int tile_n0 = (tile / m_tiles) * BN;
+        const int m0 = tile_m(tile) * 256 + (int)rank * 128;
+        const int tile_n0 = tile_n(tile) * BN;
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&resid_empty[g], (uint32_t)((it & 1) ^ 1));
           if (elected) {
@@ -655,9 +664,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if constexpr (ALLTAIL) {
       const int grp = (warp - 4) >> 2;    // column group: boxes [2 grp, 2 grp + 2) of the tile
       const int r = quarter * 32 + lane;  // row inside this CTA's 128-row tile
+      uint32_t box_parity = 0;            // bit i: parity of resid_bar[i]'s next completion
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-        const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-        const int tile_n0 = (tile / m_tiles) * BN;
+        const int m0 = tile_m(tile) * 256 + (int)rank * 128;
+        const int tile_n0 = tile_n(tile) * BN;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const auto tpre = epi.tail_prefetch(m0 + r, shp.M, shp.N, tile_n0 + 128 * grp, 128);
@@ -671,7 +681,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const int col = tile_n0 + 64 * bi;
           if (col >= shp.N) break;  // group-uniform
           uint8_t* hbox = boxes + bi * L::A_BYTES;
-          mbar_wait(&resid_bar[bi], (uint32_t)(it & 1));
+          mbar_wait(&resid_bar[bi], (box_parity >> bi) & 1u);
+          box_parity ^= 1u << bi;
           epi.template tail_box<false>(acc, 64 * bi, r, m0 + r, col, shp.M, hbox, nullptr, tpre);
           fence_proxy_async_smem();  // this thread's smem writes -> visible to the TMA store
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -713,8 +724,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       if (quarter == 0) tma_store_wait_all();
     } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int m0 = (tile % m_tiles) * 256 + (int)rank * 128;
-      const int n0 = (tile / m_tiles) * BN + sub;
+      const int m0 = tile_m(tile) * 256 + (int)rank * 128;
+      const int n0 = tile_n(tile) * BN + sub;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool live = n0 < shp.N;
@@ -725,7 +736,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const int grp = (warp - 4) >> 2;                 // column group: boxes [2 grp, 2 grp + 2) of the tile
           const int r = quarter * 32 + lane;               // row inside this CTA's 128-row tile
           const int ring0 = (int)(((long)my_tiles * total_kb) % STAGES);  // ring slot of residual box 0
-          const int tile_n0 = (tile / m_tiles) * BN;
+          const int tile_n0 = tile_n(tile) * BN;
           const auto tpre = epi.tail_prefetch(m0 + r, shp.M, shp.N, tile_n0 + 128 * grp, 128);
           mbar_wait(&tfull_bar[as], aphase);
           if (threadIdx.x == 128) ACE_STAMP(5);

@@ -268,6 +268,19 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
   plan->b_ptr = b;
   plan->b_ld = b_ld;
   plan->bn = bn;
+  {
+    // stream the larger operand once, keep the smaller one in L2 (see GemmShape::raster_n)
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = probe_env("ACE_GEMM_RASTER");
+      forced = e ? atoi(e) : 2;
+    }
+    // measured rule (tools/time_step.py A/B): only where the m-fastest order demonstrably re-reads A from HBM once
+    // per wave — a plain GEMM whose A exceeds what L2 keeps next to B (down_proj at M = 6000: 74 MB, ncu 308 MB of
+    // DRAM traffic for 172 MB of operands); the codec's tap-shifted convolutions stay m-fastest
+    const double a_bytes = 2.0 * m * kc, b_bytes = 2.0 * n * kc * ntaps;
+    plan->shp.raster_n = forced != 2 ? forced : (ntaps == 1 && a_bytes > 48e6 && a_bytes > b_bytes ? 1 : 0);
+  }
   if (m <= 0 || n <= 0) return ACE_OK;
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_a, a, (uint64_t)kc, (uint64_t)a_rows,
                                (uint64_t)a_ld * sizeof(bf16), GEMM_BM));

@@ -174,14 +174,17 @@ def test_dit_forward_mid_size(lib):
     assert rel_l2(vt.cpu().float(), want) <= 2e-2
 
 
-@pytest.mark.parametrize("hidden,T", [(512, 601), (2048, 1500), (512, 6403), (2048, 3000), (2048, 6001)])
+@pytest.mark.parametrize("hidden,T", [(512, 601), (2048, 1500), (512, 6403), (2048, 3000), (2048, 6001), (2048, 7001)])
 def test_gemm_tail_path_matches_slab_path(lib, probe, hidden, T):
     """The residual GEMMs' tail path (residual tile by TMA into the freed operand ring, in-place update in shared
     memory, h and g out by TMA stores: gemm.cuh / EpiGatedResid::tail_box) rounds exactly like the slab path it
     replaces on a CTA's last tile, so a forward must be bit-identical with it switched off (probe build,
     ACE_NO_TMA_TAIL=1) — also against the release library.  The long cases are multi-wave problems (more pair
     tiles than CTA pairs: 192-wide tiles at M = 3000 / 6402, 256-wide at M = 6002 with a ragged last row tile), which
-    run the every-tile variant (ALLTAIL: dedicated residual boxes, loader warp, g made in place)."""
+    run the every-tile variant (ALLTAIL: dedicated residual boxes, loader warp, g made in place).  T = 7001 (M = 7002)
+    is the shape where down_proj runs 192-wide tiles in n-fastest order (A = 57 MB: GemmShape::raster_n), so a CTA pair
+    meets the two-box last column tile BEFORE other tiles — the per-box barrier parity must not follow the tile
+    counter (a bug this case caught)."""
     import os
 
     layers = 4 if hidden == 512 else 2
