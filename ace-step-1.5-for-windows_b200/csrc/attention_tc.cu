@@ -90,9 +90,17 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[3
 #ifdef ACE_ATTN_TIMING
 // probe builds only (tools/attn_timing.cu): cycles CTA 0 / warp 4 / lane 0 spends per phase of the KV loop
 __device__ long long g_attn_cycles[8];
+__device__ unsigned long long g_attn_stamp[8];  // globaltimer (ns) of CTA (0,0,0): entry, setup done, S_0 seen, loop end, last PV, stores done, exit
+__device__ __forceinline__ unsigned long long att_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_STAMP(i, cond) do { if ((cond) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_attn_stamp[i] = att_gtimer(); } while (0)
 #define ATT_T(i) do { if (stamp) { const long long now_ = clock64(); g_attn_cycles[i] += now_ - tprev; tprev = now_; } } while (0)
 #else
 #define ATT_T(i) do { } while (0)
+#define ATT_STAMP(i, cond) do { } while (0)
 #endif
 
 __device__ __forceinline__ void tmem_st_32x32_u32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -117,7 +125,8 @@ __device__ __forceinline__ void tmem_st_32x32_u32(uint32_t taddr, const uint32_t
 template <int NSW, bool PT>
 __global__ void __launch_bounds__(128 + 32 * NSW, NSW == 4 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                    const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                    const AttnParams p) {
   // No static __shared__ in this kernel, so the dynamic window starts 1024-byte aligned (needed by
   // SWIZZLE_128B); checked rather than padded so that two CTAs fit on one SM.
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,6 +142,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int q0 = blockIdx.x * BQ;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / p.group;
+  ATT_STAMP(0, threadIdx.x == 0);
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
@@ -165,6 +175,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 128u;
   pdl_wait();
+  ATT_STAMP(1, threadIdx.x == 0);
 
   // keys visited by this query tile; `skv` = this sample's valid (non-padding) keys
   int skv = p.Skv;
@@ -303,6 +314,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t ph = (j >> 1) & 1;
       const int jb0 = j_lo + j * BKV;
       mbar_wait(&bar[S_FULL + s], ph);
+      if (j == 0) ATT_STAMP(2, threadIdx.x == 128);
       ATT_T(0);  // wait for S_j
       tcgen05_fence_after();
       __syncwarp();
@@ -452,33 +464,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
 
     // O is complete once the last PV has retired
+    ATT_STAMP(3, threadIdx.x == 128);
     mbar_wait(&bar[P_EMPTY], (uint32_t)((nblk - 1) & 1));
+    ATT_STAMP(4, threadIdx.x == 128);
     tcgen05_fence_after();
     __syncwarp();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    bf16* op = p.o + ((long)b * p.Sq + qi) * p.ldo + (long)h * HD + hsel * 64;
+    // The output tile leaves through the Q tile's shared memory (idle: every S MMA has retired) and two TMA stores
+    // — thread-per-row 16-byte global stores hit 32 different lines per instruction and took 1.3-2.7 us of a
+    // 8-19 us CTA (tools/attn_timing.cu).  Same [128 rows x 64 cols] 128-byte-swizzled boxes TMA loaded Q into;
+    // rows past the end of the batch item are clipped by the tensor map.
 #pragma unroll 1
     for (int c = 0; c < OCH; ++c) {
       float o[32];
       tmem_ld_32x32(tmem_o + lane_base + (uint32_t)(hsel * 64 + c * 32), o);
-      if (qi < p.Sq) {
+      const int col0 = hsel * 64 + c * 32;
+      uint8_t* rowp = sQ + (col0 >> 6) * Q_HALF + r * 128;
+      const int ch0 = (col0 & 63) >> 3;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
-          w.y = pack_bf16x2(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
-          w.z = pack_bf16x2(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
-          w.w = pack_bf16x2(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
-          *reinterpret_cast<uint4*>(op + c * 32 + q * 8) = w;
-        }
+      for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = pack_bf16x2(o[8 * q + 0] * inv, o[8 * q + 1] * inv);
+        w.y = pack_bf16x2(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+        w.z = pack_bf16x2(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+        w.w = pack_bf16x2(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+        *reinterpret_cast<uint4*>(rowp + (((ch0 + q) ^ (r & 7)) << 4)) = w;
       }
     }
+    fence_proxy_async_smem();  // this thread's smem writes -> visible to the TMA store
+    asm volatile("bar.sync 6, %0;" ::"n"(32 * NSW) : "memory");
+    if (warp == 4 && elect_one()) {
+      tma_store_3d(&tm_o, sQ, h * HD, q0, b);
+      tma_store_3d(&tm_o, sQ + Q_HALF, h * HD + 64, q0, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+    ATT_STAMP(5, threadIdx.x == 128);
   }
 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 256);
+  ATT_STAMP(6, threadIdx.x == 64);
 }
 
 }  // namespace
@@ -499,6 +527,8 @@ int make_attn_plan(AttnPlan* plan, const AttnParams& p, int heads, int batch) {
                                (uint64_t)p.ldk * 2, (uint64_t)p.Skv * p.ldk * 2, BKV));
   ACE_PROPAGATE(encode_tmap_3d(&plan->tm_v, p.v, (uint64_t)kvh * HD, (uint64_t)p.Skv, (uint64_t)batch,
                                (uint64_t)p.ldv * 2, (uint64_t)p.Skv * p.ldv * 2, BKV));
+  ACE_PROPAGATE(encode_tmap_3d(&plan->tm_o, p.o, (uint64_t)heads * HD, (uint64_t)p.Sq, (uint64_t)batch,
+                               (uint64_t)p.ldo * 2, (uint64_t)p.Sq * p.ldo * 2, BQ));
   return ACE_OK;
 }
 
@@ -511,7 +541,7 @@ static int launch_attention_tc_n(const AttnPlan& plan, dim3 grid, cudaStream_t s
     attr = true;
   }
   ACE_CUDA_CHECK(launch_kernel(attention_tc_kernel<NSW, PT>, grid, dim3(128 + 32 * NSW), (size_t)smem_bytes<NSW>(),
-                               stream, plan.tm_q, plan.tm_k, plan.tm_v, plan.p));
+                               stream, plan.tm_q, plan.tm_k, plan.tm_v, plan.tm_o, plan.p));
   return ACE_OK;
 }
 

@@ -25,7 +25,7 @@ int launch_cross_probs(const bf16* q, long ldq, const bf16* k, long ldk, bf16* o
 
 // tcgen05 / TMEM kernel (attention_tc.cu): tensor maps are encoded once per bound shape
 struct AttnPlan {
-  CUtensorMap tm_q, tm_k, tm_v;
+  CUtensorMap tm_q, tm_k, tm_v, tm_o;  // tm_o: the output, stored by TMA from the (then idle) Q tile
   AttnParams p;
   int heads, batch;
 };

@@ -42,5 +42,31 @@ int main() {
            (double)c[2] / nblk, (double)c[3] / nblk, (double)c[4] / nblk, (double)c[5] / nblk,
            (double)(c[0] + c[1] + c[2] + c[3] + c[4] + c[5]) / nblk);
   }
+  // C2 shapes (750 tokens, batch 2): the fixed cost of a launch.  globaltimer stamps of CTA (0,0,0).
+  {
+    const int S2 = 750, E2 = 512;
+    struct { const char* name; int skv, window; } cases[3] = {{"self full", S2, -1}, {"self window", S2, 128}, {"cross", E2, -1}};
+    for (auto& cs : cases) {
+      AttnParams p{q, k, v, o, H * 128L, HK * 128L, HK * 128L, H * 128L, S2, cs.skv, cs.window, H / HK,
+                   (1.0f / sqrtf(128.0f)) * 1.4426950408889634f, nullptr};
+      AttnPlan plan;
+      if (make_attn_plan(&plan, p, H, B) != ACE_OK) { printf("plan: %s\n", get_error()); return 1; }
+      for (int rep = 0; rep < 3; ++rep) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        launch_attention_tc(plan, 0);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        unsigned long long st[8];
+        cudaMemcpyFromSymbol(st, g_attn_stamp, sizeof(st));
+        if (rep == 2)
+          printf("%-12s %.1f us by events | CTA 0 (ns): setup %llu | Q,K0 load + S_0 %llu | KV loop %llu | last PV %llu | O readout + stores %llu | "
+                 "teardown %llu | entry->exit %llu\n", cs.name, ms * 1e3, st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3],
+                 st[5] - st[4], st[6] - st[5], st[6] - st[0]);
+      }
+    }
+  }
   return 0;
 }
