@@ -497,7 +497,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tma_store_3d(&tm_o, sQ, h * HD, q0, b);
       tma_store_3d(&tm_o, sQ + Q_HALF, h * HD + 64, q0, b);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read_all();
     }
     ATT_STAMP(5, threadIdx.x == 128);
   }

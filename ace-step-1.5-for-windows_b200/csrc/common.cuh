@@ -249,7 +249,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// the stores of this thread's committed groups have finished READING shared memory (the source may be reused)
+// the stores of this thread's committed groups have finished READING shared memory (the source may be reused, the
+// CTA may exit: the writes themselves complete with the grid, like any store still in flight at exit)
 __device__ __forceinline__ void tma_store_wait_read_all() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }

@@ -721,7 +721,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         if (threadIdx.x == 128) ACE_STAMP(6);
       }
-      if (quarter == 0) tma_store_wait_all();
+      if (quarter == 0) tma_store_wait_read_all();
     } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m0 = tile_m(tile) * 256 + (int)rank * 128;
@@ -767,7 +767,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
           ACE_TCLK(8);
-          if (quarter == 0) tma_store_wait_all();  // (only the lane that issued has pending groups)
+          if (quarter == 0) tma_store_wait_read_all();  // (only the lane that issued has pending groups)
           ACE_TCLK(9);
           if (threadIdx.x == 128) ACE_STAMP(6);
           continue;
