@@ -125,9 +125,16 @@ def gather_waveforms(local: Sequence[torch.Tensor], n_items: int, dst: int = 0, 
 
 def generate_sharded(generate_one: Callable[[int], torch.Tensor], n_items: int, dst: int = 0, group=None,
                      device: Optional[torch.device] = None, lengths: Optional[Sequence[int]] = None,
-                     async_op: bool = False):
+                     async_op: bool = False, gather_stream=None):
     """Run `generate_one(i) -> waveform [C, N]` for this rank's songs, then gather on `dst`
-    (see gather_waveforms for `lengths` / `async_op`)."""
+    (see gather_waveforms for `lengths` / `async_op`).  `gather_stream`: the CUDA stream the waveforms are produced
+    on when that is not the current one (B200Pipeline.codec_stream): the collective is queued behind it, so the
+    caller's stream — and the next song's denoising loop — does not wait for this song's decode."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     local = [generate_one(i) for i in shard_indices(n_items, rank, world)]
-    return gather_waveforms(local, n_items, dst=dst, group=group, device=device, lengths=lengths, async_op=async_op)
+    if gather_stream is None:
+        return gather_waveforms(local, n_items, dst=dst, group=group, device=device, lengths=lengths,
+                                async_op=async_op)
+    with torch.cuda.stream(gather_stream):
+        return gather_waveforms(local, n_items, dst=dst, group=group, device=device, lengths=lengths,
+                                async_op=async_op)

@@ -26,6 +26,7 @@ class PendingSong:
         self._res, self._ev, self._flags, self._numel = res, events, host_flags, numel
         self._t0, self._decoded, self._steps = t0, decoded, max(1, int(steps))
         self._extra_time: Dict[str, float] = {}
+        self.stream = None  # the CUDA stream the waveform is produced on
 
     def done(self) -> bool:
         return self._ev[2].query()
@@ -71,15 +72,31 @@ class SongPipeline:
 class B200Pipeline:
     def __init__(self, dit_state: Dict[str, torch.Tensor], vae_state: Dict[str, torch.Tensor],
                  dit_shape: Optional[DiTShape] = None, vae_shape: Optional[VaeShape] = None,
-                 null_condition_emb: Optional[torch.Tensor] = None, device="cuda:0", turbo: bool = False):
+                 null_condition_emb: Optional[torch.Tensor] = None, device="cuda:0", turbo: bool = False,
+                 overlap_codec: bool = False):
+        """`overlap_codec=True`: the denoising loop runs on a high-priority stream and everything the codec does
+        (decode, peak normalisation, the D2H copy; the encode of a repaint) on a second, normal-priority stream, so with
+        songs queued back to back (SongPipeline) the decode of song i runs under song i + 1's steps instead of
+        standing between two loops.  OFF by default: measured on B200 (bench.py, C2, 10 songs) it is slower —
+        386.3 vs 393.7 audio-s/s — the codec's CTAs (a whole SM each, like the GEMMs') delay the step's dependent
+        GEMM chain by more than the idle SM time they fill, and the device is power-capped either way.
+        False: one stream (the caller's current one)."""
         self.device = torch.device(device)
         self.turbo = turbo
+        self.overlap_codec = bool(overlap_codec)
+        self._loop_stream = torch.cuda.Stream(self.device, priority=-1) if overlap_codec else None
+        self._codec_stream = torch.cuda.Stream(self.device, priority=0) if overlap_codec else None
         self.dit = B200DiT(dit_state, dit_shape or DiTShape(), self.device)
         self.vae = B200Vae(vae_state, vae_shape or VaeShape(), self.device)
         self.sampler = B200Sampler(self.dit, null_condition_emb)
         self.sample_rate = 48000
         self._pinned_wav = [None, None]
         self._pinned_i = 0
+
+    @property
+    def codec_stream(self):
+        """The stream decode / normalisation / D2H run on (None: the caller's current stream)."""
+        return self._codec_stream
 
     def close(self):
         self.dit.close()
@@ -112,49 +129,57 @@ class B200Pipeline:
         raised before any audio is handed out) and returns generate()'s dict.  A serving loop that submits song i + 1
         before waiting for song i keeps the GPU busy across the song boundary (the host-side preparation of a song —
         conditioning copies, K/V projection launches, the graph launches of the first steps — is a few hundred
-        microseconds during which the device would otherwise idle).  Everything runs on the current stream, so the
-        handle's static I/O slots are reused in stream order."""
+        microseconds during which the device would otherwise idle).  The loop runs on one stream (the handle's static
+        I/O slots are reused in stream order) and the codec on another (see `overlap_codec`); `PendingSong.stream` is
+        the stream the waveform was produced on, for callers that queue device work behind it without waiting."""
         t0 = time.time()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        with torch.cuda.device(self.device):
+        cur = torch.cuda.current_stream(self.device)
+        loop_s = self._loop_stream if self.overlap_codec else cur
+        codec_s = self._codec_stream if self.overlap_codec else cur
+        loop_s.wait_stream(cur)  # inputs the caller produced on its own stream
+        with torch.cuda.stream(loop_s):
             ev[0].record()
-        enc, ctx = self._dev(encoder_hidden_states), self._dev(context_latents)
-        src = self._dev(src_latents) if src_latents is not None else ctx[..., :64].contiguous()
-        noise = self._dev(noise)
-        fn = self.sampler.generate_turbo if self.turbo else self.sampler.generate_base
-        out = fn(enc, ctx, src, seed, noise=noise, sync=False, **sampler_kwargs)
-        lat = out["target_latents"]
-        # NaN / Inf / all-zero guard of _prepare_generate_music_decode_state (generate_music_decode.py:66-77): the
-        # kernel runs here, the host looks at its two flags in wait()
-        flags = latent_flags_enqueue(lat)
-        numel = lat.numel()
-        host_flags = torch.empty(2, dtype=torch.int32, pin_memory=True)
-        host_flags.copy_(flags, non_blocking=True)
-        if latent_shift != 0.0 or latent_rescale != 1.0:
-            lat = lat * latent_rescale + latent_shift
-        res: Dict[str, Any] = {"target_latents": lat, "time_costs": out["time_costs"]}
-        with torch.cuda.device(self.device):
+            enc, ctx = self._dev(encoder_hidden_states), self._dev(context_latents)
+            src = self._dev(src_latents) if src_latents is not None else ctx[..., :64].contiguous()
+            noise = self._dev(noise)
+            fn = self.sampler.generate_turbo if self.turbo else self.sampler.generate_base
+            out = fn(enc, ctx, src, seed, noise=noise, sync=False, **sampler_kwargs)
+            lat = out["target_latents"]
+            # NaN / Inf / all-zero guard of _prepare_generate_music_decode_state (generate_music_decode.py:66-77):
+            # the kernel runs here, the host looks at its two flags in wait()
+            flags = latent_flags_enqueue(lat)
+            numel = lat.numel()
+            host_flags = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            host_flags.copy_(flags, non_blocking=True)
+            if latent_shift != 0.0 or latent_rescale != 1.0:
+                lat = lat * latent_rescale + latent_shift
+            res: Dict[str, Any] = {"target_latents": lat, "time_costs": out["time_costs"]}
             ev[1].record()
-        if decode:
-            wav = torch.stack([self.vae.decode_frames(lat[b]) for b in range(lat.shape[0])], dim=0)
-            # per-sample peak normalisation (generate_music_decode.py:191-195), in place, no host decision
-            res["peak"] = peak_normalize_(wav, normalization_db=normalization_db)
-            if to_host:
-                if not reuse_host_buffer:
-                    host = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
-                else:  # two buffers: the one handed out by the previous call stays valid while this song runs
-                    self._pinned_i ^= 1
-                    host = self._pinned_wav[self._pinned_i]
-                    if host is None or host.shape != wav.shape:
+        codec_s.wait_event(ev[1])
+        with torch.cuda.stream(codec_s):
+            if decode:
+                lat.record_stream(codec_s)
+                wav = torch.stack([self.vae.decode_frames(lat[b]) for b in range(lat.shape[0])], dim=0)
+                # per-sample peak normalisation (generate_music_decode.py:191-195), in place, no host decision
+                res["peak"] = peak_normalize_(wav, normalization_db=normalization_db)
+                if to_host:
+                    if not reuse_host_buffer:
                         host = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
-                        self._pinned_wav[self._pinned_i] = host
-                host.copy_(wav, non_blocking=True)
-                res["_device_audio"] = wav  # keeps the source alive until the copy has run
-                wav = host
-            res["audio"] = wav
-        with torch.cuda.device(self.device):
+                    else:  # two buffers: the one handed out by the previous call stays valid while this song runs
+                        self._pinned_i ^= 1
+                        host = self._pinned_wav[self._pinned_i]
+                        if host is None or host.shape != wav.shape:
+                            host = torch.empty(wav.shape, dtype=torch.float32, pin_memory=True)
+                            self._pinned_wav[self._pinned_i] = host
+                    host.copy_(wav, non_blocking=True)
+                    res["_device_audio"] = wav  # keeps the source alive until the copy has run
+                    wav = host
+                res["audio"] = wav
             ev[2].record()
-        return PendingSong(res, ev, host_flags, numel, t0, decode, out.get("steps", 1))
+        pending = PendingSong(res, ev, host_flags, numel, t0, decode, out.get("steps", 1))
+        pending.stream = codec_s
+        return pending
 
     # ------------------------------------------------------------------
     def repaint(self, *args, **kwargs) -> Dict[str, Any]:
@@ -176,28 +201,38 @@ class B200Pipeline:
         latent_dist.sample()).  The PendingSong's result is generate()'s dict plus "src_latents"; like
         generate_async nothing here synchronises with the host."""
         t0 = time.time()
-        audio = src_audio.to(self.device, torch.float32, non_blocking=True)
-        if audio.dim() == 2:
-            audio = audio.unsqueeze(0)
-        B = audio.shape[0]
-        hop = self.vae.shape.hop
-        T = audio.shape[-1] // hop
-        lat = []
-        for b in range(B):
-            eps = None if posterior_eps is None else posterior_eps[b].to(self.device, torch.bfloat16)
-            if eps is None:
-                eps = torch.randn(T, 64, device=self.device, dtype=torch.bfloat16)
-            lat.append(self.vae.encode_samples(audio[b, :, : T * hop], eps))
-        target = torch.stack(lat, dim=0)  # [B, T, 64] bf16
-        t_enc = time.time() - t0
-        s0 = max(0, min(int(repaint_start_frame), T - 1))
-        s1 = max(s0 + 1, min(int(repaint_end_frame), T))
-        sil = self._dev(silence_latent)[:, :T, :].expand(B, -1, -1)
-        src = target.clone()
-        src[:, s0:s1] = sil[:, s0:s1]
-        mask = torch.zeros(B, T, 64, device=self.device, dtype=torch.bfloat16)
-        mask[:, s0:s1] = 1.0
-        ctx = torch.cat([src, mask], dim=-1)
+        cur = torch.cuda.current_stream(self.device)
+        codec_s = self._codec_stream if self.overlap_codec else cur
+        codec_s.wait_stream(cur)
+        # the encode shares the codec handle's workspace with the previous song's decode: same stream
+        with torch.cuda.stream(codec_s):
+            audio = src_audio.to(self.device, torch.float32, non_blocking=True)
+            if audio.dim() == 2:
+                audio = audio.unsqueeze(0)
+            B = audio.shape[0]
+            hop = self.vae.shape.hop
+            T = audio.shape[-1] // hop
+            lat = []
+            for b in range(B):
+                eps = None if posterior_eps is None else posterior_eps[b].to(self.device, torch.bfloat16)
+                if eps is None:
+                    eps = torch.randn(T, 64, device=self.device, dtype=torch.bfloat16)
+                lat.append(self.vae.encode_samples(audio[b, :, : T * hop], eps))
+            target = torch.stack(lat, dim=0)  # [B, T, 64] bf16
+            t_enc = time.time() - t0
+            s0 = max(0, min(int(repaint_start_frame), T - 1))
+            s1 = max(s0 + 1, min(int(repaint_end_frame), T))
+            sil = self._dev(silence_latent)[:, :T, :].expand(B, -1, -1)
+            src = target.clone()
+            src[:, s0:s1] = sil[:, s0:s1]
+            mask = torch.zeros(B, T, 64, device=self.device, dtype=torch.bfloat16)
+            mask[:, s0:s1] = 1.0
+            ctx = torch.cat([src, mask], dim=-1)
+        cur.wait_stream(codec_s)  # generate_async makes its loop stream wait for the caller's stream
+        for x in (ctx, src, target):
+            x.record_stream(cur)
+            if self.overlap_codec:
+                x.record_stream(self._loop_stream)
         pending = self.generate_async(encoder_hidden_states, ctx, src, seed, noise=noise, to_host=to_host,
                                       reuse_host_buffer=reuse_host_buffer, **sampler_kwargs)
         pending._res["src_latents"] = target

@@ -491,11 +491,15 @@ def run_b200(args, wl):
                 return wav
             # at most one gather in flight: the previous song's gather (finished long ago) is retired here, which
             # hands its buffers back to the allocator before this song's successor needs memory
-            pipe_g.submit(generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True))
+            pg = generate_sharded(one, world, dst=0, device=dev, lengths=lengths, async_op=True,
+                                  gather_stream=pipe.codec_stream)
+            with torch.cuda.stream(pipe.codec_stream):  # retiring the previous gather must not stall the loop stream
+                pipe_g.submit(pg)
 
         def drain():
             retire(pipe_s.drain())
-            return pipe_g.drain()
+            with torch.cuda.stream(pipe.codec_stream):
+                return pipe_g.drain()
 
         # Warm-up keeps the previous song's result alive while the next one runs, exactly like the timed loop;
         # the clock sampler attaches BEFORE the warm-up and the warm-up runs back to back into the timed region
@@ -506,7 +510,7 @@ def run_b200(args, wl):
             def one(_i):
                 keep["out"] = r.song_device(0).wait()
                 return keep["out"]["audio"][0]
-            songs = generate_sharded(one, world, dst=0, device=dev)
+            songs = generate_sharded(one, world, dst=0, device=dev)  # (the song was waited for: any stream will do)
             if rank == 0:
                 assert len(songs) == world and all(s.shape == (2, r.n_samples) for s in songs)
                 assert torch.equal(songs[0], keep["out"]["audio"][0]) and all(bool(torch.isfinite(s).all()) for s in songs)

@@ -278,3 +278,39 @@ def test_async_pipeline_matches_blocking_calls_and_defers_the_latent_guard():
         pending.wait()
     assert torch.isfinite(pipe.generate(enc, ctx, src, [5], **kw)["audio"]).all()  # the engine is still usable
     pipe.close()
+
+
+def test_two_stream_pipeline_matches_single_stream():
+    """`overlap_codec=True` (loop on a high-priority stream, codec + D2H on a second one; off by default, see
+    DESIGN.md) must return exactly what the single-stream pipeline returns, songs queued back to back."""
+    from acestep_b200.pipeline import SongPipeline
+
+    cfg, vcfg = DiTConfig.tiny(), ovae.VaeConfig.tiny()
+    w = bf16_round_(make_dit_weights(cfg, seed=0))
+    vsd = make_vae_weights(vcfg, seed=3)
+    null = make_null_condition_emb(cfg).to(torch.bfloat16)
+    vshape = VaeShape(encoder_hidden_size=vcfg.encoder_hidden_size, downsampling_ratios=vcfg.downsampling_ratios,
+                      channel_multiples=vcfg.channel_multiples, decoder_channels=vcfg.decoder_channels)
+    g = torch.Generator().manual_seed(31)
+    T, E = 56, 9
+    enc = torch.randn(1, E, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    src = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    ctx = torch.cat([src, torch.ones(1, T, 64, dtype=torch.bfloat16)], -1)
+    audio = torch.rand(1, 2, T * vcfg.hop, generator=g) - 0.5
+    eps = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    kw = dict(infer_steps=3, diffusion_guidance_sale=4.0, shift=3.0)
+    results = []
+    for overlap in (False, True):
+        pipe = B200Pipeline(w, vsd, DiTShape.from_config(cfg), vshape, null, DEV, turbo=False, overlap_codec=overlap)
+        q, outs = SongPipeline(depth=1), []
+        for s in (1, 2, 3):
+            o = q.submit(pipe.generate_async(enc, ctx, src, [s], **kw))
+            if o is not None:
+                outs.append(o["audio"].clone())
+        outs.append(q.drain()["audio"].clone())
+        o = pipe.repaint(enc, audio, 10, 30, src, [4], posterior_eps=eps, **kw)
+        outs += [o["audio"].clone(), o["src_latents"].cpu().float()]
+        results.append(outs)
+        pipe.close()
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
