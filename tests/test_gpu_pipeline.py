@@ -314,3 +314,108 @@ def test_two_stream_pipeline_matches_single_stream():
         pipe.close()
     for a, b in zip(*results):
         assert torch.equal(a, b)
+
+
+def test_wrapped_selection_sites_end_to_end_on_real_engines():
+    """The drop-in boundary exercised the way the reference calls it, with REAL engines on the device (the CPU
+    plumbing tests use stubs): `install()` on a handler-shaped host, `_init_b200_backends` from the modules'
+    state dicts, then
+      * `_execute_service_generate_diffusion(payload, generate_kwargs, seed_param, infer_method, shift,
+        audio_cover_strength)` (handler/service_generate_execute.py:107-196): condition encoder -> context ->
+        base sampler with CFG + APG -> (outputs, enc, enc_mask, ctx);
+      * `tiled_decode(latents)` (handler/vae_decode.py:16-48) and `tiled_encode(audio)` (vae_encode.py:15-43).
+    Checked against the oracle chain on bf16-rounded weights: condition encoder 3e-2, loop 3e-2 (started from the
+    CUDA path's own conditioning so the comparison isolates the loop), waveform 1e-1 (bounds of smoke())."""
+    import contextlib
+    import types
+
+    from acestep_b200.backend import install
+    from acestep_b200.sampler import prepare_noise
+    from oracle import cond as ocond
+
+    dcfg, ccfg, vcfg = DiTConfig.tiny(), ocond.CondConfig.tiny(), ovae.VaeConfig.tiny()
+    w_dit = bf16_round_(make_dit_weights(dcfg, seed=0))
+    w_cond = bf16_round_(ocond.make_cond_weights(ccfg, seed=5))
+    vsd = make_vae_weights(vcfg, seed=3)
+    wf = folded_vae_state(vsd)
+    null = make_null_condition_emb(dcfg).to(torch.bfloat16)
+
+    class _SD(torch.nn.Module):
+        def __init__(self, d, config=None):
+            super().__init__()
+            self._d, self.config = d, config
+
+        def state_dict(self, *a, **k):
+            return self._d
+
+    cfg = types.SimpleNamespace(**{**vars(ccfg), **vars(dcfg), "is_turbo": False})
+    cfg.layer_types = dcfg.layer_types
+
+    class Host:
+        device, dtype = DEV, torch.bfloat16
+
+        def _execute_service_generate_diffusion(self, *a, **k):
+            raise AssertionError("the reference path must not run while the B200 backend is active")
+
+        def tiled_decode(self, *a, **k):
+            raise AssertionError("the reference path must not run while the B200 backend is active")
+
+        def tiled_encode(self, *a, **k):
+            raise AssertionError("the reference path must not run while the B200 backend is active")
+
+        @contextlib.contextmanager
+        def _load_model_context(self, name):
+            yield
+
+    h = install(Host())
+    h.model = types.SimpleNamespace(decoder=_SD(w_dit), encoder=_SD(w_cond), config=cfg, null_condition_emb=null,
+                                    generate_audio=lambda **kw: None)  # plain base model: no `timesteps` parameter
+    h.config = cfg
+    h.vae = _SD(vsd, config=vcfg)
+    dit_status, vae_status = h._init_b200_backends()
+    assert dit_status.startswith("Active") and vae_status.startswith("Active")
+
+    g = torch.Generator().manual_seed(77)
+    B, T = 2, 36
+    text = torch.randn(B, 5, ccfg.text_hidden_dim, generator=g).to(torch.bfloat16)
+    lyric = torch.randn(B, 9, ccfg.text_hidden_dim, generator=g).to(torch.bfloat16)
+    refer = torch.randn(B, 8, ccfg.timbre_hidden_dim, generator=g).to(torch.bfloat16)
+    tm, lm = torch.ones(B, 5, dtype=torch.long), torch.ones(B, 9, dtype=torch.long)
+    order = torch.tensor([0, 1])
+    src = torch.randn(B, T, 64, generator=g).to(torch.bfloat16)
+    chunk = torch.ones(B, T, 64, dtype=torch.bfloat16)
+    h.silence_latent = torch.randn(1, 64, 64, generator=g).to(torch.bfloat16).to(DEV)
+    dv = lambda x: x.to(DEV)
+    payload = dict(src_latents=dv(src), text_hidden_states=dv(text), text_attention_mask=dv(tm),
+                   lyric_hidden_states=dv(lyric), lyric_attention_mask=dv(lm),
+                   refer_audio_acoustic_hidden_states_packed=dv(refer), refer_audio_order_mask=dv(order),
+                   chunk_mask=dv(chunk), is_covers=torch.zeros(B, dtype=torch.long, device=DEV),
+                   precomputed_lm_hints_25Hz=None, non_cover_text_hidden_states=None,
+                   non_cover_text_attention_masks=None)
+    gk = dict(infer_steps=4, diffusion_guidance_sale=5.0, cfg_interval_start=0.0, cfg_interval_end=1.0,
+              use_adg=False, cover_noise_strength=0.0, timesteps=[1.0, 0.5, 0.0])  # ignored by the plain base model
+    seeds = [11, 12]
+    outputs, enc, enc_mask, ctx = h._execute_service_generate_diffusion(payload, gk, seeds, "ode", 3.0, 1.0)
+    lat = outputs["target_latents"]
+    assert lat.shape == (B, T, 64) and lat.dtype == torch.bfloat16 and lat.device.type == "cuda"
+    assert "diffusion_time_cost" in outputs["time_costs"]
+    want_enc, want_mask = ocond.condition_encoder(w_cond, ccfg, text.float(), tm, lyric.float(), lm, refer.float(), order)
+    assert torch.equal(enc_mask.cpu(), want_mask)
+    assert rel_l2(enc.cpu().float(), want_enc) <= 3e-2
+    assert torch.equal(ctx.cpu(), torch.cat([src, chunk], -1))
+    noise = prepare_noise((B, T, 64), seeds, DEV).cpu().float()  # the same RNG calls the seam makes
+    vel = lambda xt, t, c, e, cache: dit_forward(w_dit, dcfg, xt, t, c, e, cache, bf16_time=True)
+    want = osamp.sample_base(vel, enc.cpu().float(), ctx.cpu().float(), src.float(), None, null_emb=null.float(),
+                             infer_steps=4, guidance_scale=5.0, shift=3.0, noise=noise, new_cache=CrossCache)
+    err = rel_l2(lat.cpu().float(), want)
+    assert err < 3e-2, err
+
+    wav = h.tiled_decode(lat.transpose(1, 2).contiguous())  # [B, 64, T] like the reference's caller
+    assert wav.shape == (B, 2, T * vcfg.hop) and wav.device.type == "cuda"
+    want_wav = ovae.decode(wf, vcfg, lat.cpu().float().transpose(1, 2))
+    peak = want_wav.abs().amax(dim=[1, 2], keepdim=True).clamp(min=1.0)
+    assert rel_l2(wav.cpu().float(), want_wav / peak) < 1e-1
+    z = h.tiled_encode(wav[0].float(), offload_latent_to_cpu=True)  # 2-D input -> 2-D result, stays on the device
+    assert z.shape == (64, T) and z.device.type == "cuda"
+    for eng in (h.b200_dit, h.b200_cond, h.b200_vae):
+        eng.close()
