@@ -18,7 +18,8 @@
 //               variant and ACE_ATTN_PTMEM=0 keep the swizzled-smem P buffer.)  O stays in TMEM across the
 //               whole KV loop; it is rescaled (tcgen05.ld/st) only when a row maximum grows by more
 //               than 2^8 (lazy rescale: P and the row sum keep using the stale maximum, which is
-//               exact because the final 1/l normalisation uses the same reference).
+//               exact because the final 1/l normalisation uses the same reference).  The normalised output
+//               tile is written as bf16 into the (by then idle) Q tile and leaves by two TMA stores.
 // Semantics = sdpa with the reference's masks (modeling_acestep_v15_turbo.py:286-368, 1405-1437):
 // full, +-window band (|i-j| <= W), or cross attention; softmax in fp32, P rounded to bf16.
 #include <stdlib.h>

@@ -450,7 +450,9 @@ struct EpiGatedResid {
   // The CTA-pair kernel runs the LAST tile of every CTA (every tile of a single-wave problem: M = 1500 at N = 2048)
   // through tail_box() instead of run(): the residual tile arrives by TMA in the operand ring's freed slots while
   // the main loop drains, the update happens in place in shared memory, and h (and g) leave by TMA stores — the
-  // epilogue warps only read TMEM and touch shared memory.  Needs the tensor maps below (use_tma).
+  // epilogue warps only read TMEM and touch shared memory.  Multi-wave problems (M = 3000 / 6000) run EVERY tile
+  // that way in the ALLTAIL variant of the kernel (dedicated residual boxes, tail_box<false> + tail_g: gemm.cuh).
+  // Needs the tensor maps below (use_tma); run() is the path without them (condition encoder, probe A/B).
   static constexpr bool kTmaTail = true;
   bf16* h;  // read-modify-write in place
   long ldh;
