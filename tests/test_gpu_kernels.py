@@ -632,3 +632,29 @@ def test_dit_forward_random_shapes_one_handle(lib):
     torch.cuda.synchronize()
     assert torch.equal(again, vt)
     dit.close()
+
+
+def test_vae_ragged_lengths_one_handle(lib):
+    """Decode and encode at lengths either side of the 128-row tile edge (1, 2, 17, 127, 128, 129, 260 latent
+    frames) through ONE codec handle, workspace regrown on demand; bound as in test_vae_decode_tiny."""
+    cfg, sd, shape = _tiny_vae()
+    wf = folded_vae_state(sd)
+    wb = {k: v.to(torch.bfloat16) for k, v in wf.items()}
+    vae = B200Vae(sd, shape, DEV)
+    g = torch.Generator().manual_seed(60)
+    for T in (129, 1, 260, 2, 128, 17, 127):
+        z = torch.randn(1, 64, T, generator=g).to(torch.bfloat16)
+        want = ovae.decode(wf, cfg, z.float())
+        got = vae.decode(z.to(DEV))
+        torch.cuda.synchronize()
+        assert got.shape == (1, 2, T * cfg.hop) and torch.isfinite(got).all(), T
+        floor = _bf16_floor(lambda: want, lambda: ovae.decode(wb, cfg, z))
+        assert rel_l2(got.cpu().float(), want) <= max(1.1 * floor, 2e-2), (T, floor)
+        audio = torch.rand(1, 2, T * cfg.hop, generator=g) - 0.5
+        mean, _ = ovae.encode_moments(wf, cfg, audio.to(torch.bfloat16).float())
+        got_mean = vae.encode_samples(audio[0].to(DEV), None)
+        torch.cuda.synchronize()
+        floor = _bf16_floor(lambda: mean, lambda: ovae.encode_moments(wb, cfg, audio.to(torch.bfloat16))[0])
+        assert got_mean.shape == (T, 64)
+        assert rel_l2(got_mean.cpu().float(), mean[0].T) <= max(1.1 * floor, 2e-2), (T, floor)
+    vae.close()
