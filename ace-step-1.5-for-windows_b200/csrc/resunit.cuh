@@ -11,17 +11,19 @@
 // 1x1 convolution's epilogue is latency-bound on its residual reads (2.9 TB/s, profiles/r1_v3_*).
 // Fused: 2.9 GB (read xs and x once, write x' and xs' once) and every global read goes through TMA.
 //
-// RU_CLUSTER > 1 makes clusters of CTAs share the conv7 weights (every 16 KB K block of W1 fetched
-// once per cluster, each CTA loading a slice and multicasting it; the CTAs then step through their K
-// blocks in lockstep, and a CTA whose tile index runs past the end computes on zero-filled rows).
-// Measured on B200 with 4-CTA clusters: bit-identical results but 18.7 ms instead of 12.6 ms for the
-// 60 s decode — a 4-deep ring cannot cover the cluster-wide release/refill round trip — so the
-// shipped configuration keeps private copies (RU_CLUSTER = 1).
+// Operand traffic into shared memory per 128-frame tile: the seven taps read ONE box of xs —
+// rows [m0 - 3 dil, m0 + 128 + 3 dil), fetched once per 64-channel half — through UMMA descriptors whose start
+// address is stepped by tap * dil rows (a K-major SWIZZLE_128B descriptor may start on any 128-byte row: the swizzle
+// follows the absolute shared-memory address, base-offset field zero; tools/desc_rowstep_probe.cu).  Seven shifted
+// [128 x 128] boxes were 224 KB per tile; the one box is 34-47 KB.  The weights (W1: 14 blocks of 16 KB, W2: 2) stream
+// through a 4-stage ring per tile: 303-335 KB per tile in all, against 480 KB before.  (Sharing the W1 stream
+// between the CTAs of a cluster by TMA multicast was measured twice — 4-CTA clusters: 18.7 vs 12.6 ms per 60 s
+// decode, 2-CTA: within 1 % — multicast saves L2 reads, not the bytes each SM has to take in; it is gone.)
 //
 // One CTA = one 128-frame tile at a time (persistent over tiles), warp-specialised:
-//   warp 0      TMA producer: per tile 14 K blocks of conv7 (7 taps x 2 halves of 64 channels; tap t
-//               reads rows m0 + (t-3)*dil, out-of-range rows are zero-filled = the conv's padding),
-//               plus the tile's residual rows x[m0:m0+128, :] (consumed two tiles later)
+//   warp 0      TMA producer: the xs box of tile it+1 (double-buffered; out-of-range rows are zero-filled = the
+//               conv's padding), the 14 W1 blocks of tile it with the 2 W2 blocks of tile it-1's conv1 slotted in
+//               after block RU_MMA2_AT, and the tile's residual rows x[m0:m0+128, :] (consumed two tiles later)
 //   warp 1      MMA issuer: conv7 -> D1[it & 1] (TMEM), conv1 of the PREVIOUS tile -> D2[(it-1) & 1]
 //               slotted in at K block 11 so the tensor pipe never waits for the Snake epilogue
 //   warp 2      TMEM allocator (512 columns: D1 x2, D2 x2)
@@ -41,23 +43,28 @@
 namespace ace {
 
 constexpr int RU_C = 128;       // channels (in = out)
-constexpr int RU_CLUSTER = 1;   // CTAs sharing each W1 K block through TMA multicast (1 = private copies, see below)
-constexpr int RU_STAGES = 4;    // conv7 operand ring
+constexpr int RU_STAGES = 4;    // weight ring (16 KB blocks)
 constexpr int RU_THREADS = 640;  // 4 control warps + 8 (epilogue 1) + 8 (epilogue 2)
 constexpr int RU_KB = 14;       // K blocks of 64 per tile: 7 taps x 2
 constexpr int RU_MMA2_AT = 11;  // K block of tile it+1 after which conv1 of tile it is issued
 constexpr int RU_LOADX_AT = 8;  // K block of tile it+1 after which the residual rows of tile it are fetched
+constexpr int RU_LOADA_AT = 3;  // K block of tile it after which the xs box of tile it+1 is fetched
+constexpr int RU_MAX_DIL = 9;
 
 struct RuSmem {
   static constexpr int A_BYTES = 128 * 64 * 2;  // [128 rows x 64 ch] bf16, SWIZZLE_128B
-  static constexpr int STAGE_BYTES = 2 * A_BYTES;
   static constexpr int TILE_BYTES = 2 * A_BYTES;  // a [128 x 128] bf16 tile = two 64-channel halves
-  static constexpr int OFF_W2 = RU_STAGES * STAGE_BYTES;
-  static constexpr int OFF_HS = OFF_W2 + TILE_BYTES;
+  static constexpr int XS_ROWS = (128 + 6 * RU_MAX_DIL + 7) / 8 * 8;  // 184: rows of the largest xs box, whole atoms
+  static constexpr int XS_HALF = XS_ROWS * 128;                        // one 64-channel half of the box
+  static constexpr int XS_BYTES = 2 * XS_HALF;
+  static constexpr int OFF_W = 2 * XS_BYTES;                           // after the two xs boxes
+  static constexpr int OFF_HS = OFF_W + RU_STAGES * A_BYTES;
   static constexpr int OFF_X = OFF_HS + TILE_BYTES;
   static constexpr int OFF_BAR = OFF_X + TILE_BYTES;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;  // +1024: manual alignment
 };
+static_assert(RuSmem::XS_HALF % 1024 == 0 && RuSmem::OFF_W % 1024 == 0 && RuSmem::OFF_HS % 1024 == 0, "swizzle atoms");
+static_assert(RuSmem::TOTAL <= 232448, "res_unit shared memory");
 
 struct RuParams {
   int L;    // frames (rows)
@@ -69,23 +76,34 @@ struct RuParams {
 
 #ifdef __CUDACC__
 
-enum RuBar {
-  RU_FULL = 0, RU_EMPTY = RU_STAGES, RU_W2 = 2 * RU_STAGES, RU_D1F, RU_D1F1, RU_D1E, RU_D1E1, RU_HSF, RU_HSE,
-  RU_D2F, RU_D2F1, RU_D2E, RU_D2E1, RU_XF, RU_XE, RU_NBAR
-};
+#ifdef ACE_RU_TIMING
+// probe builds (tools/ru_timing.cu): cycles the MMA warp of CTA 0 waits on each barrier class, and its total
+__device__ long long g_ru_wait[8];
+__device__ long long g_ru_pwait[8];
+__device__ long long g_ru_e2[8];     // epilogue 2, warp 12: wait D2F, wait XF, TMEM + math, x' store, xs' store, total
+__device__ long long g_ru_e1[8];     // epilogue 1, warp 4: wait D1F, wait HSE, TMEM + math + smem store, total
+#define RU_E2(i) do { if (e2_stamp) { const long long n_ = clock64(); ru_e[i] += n_ - e_prev; e_prev = n_; } } while (0)  // the producer warp: ring slot free, xs buffer free, x buffer free, total
+#define RU_WAIT(i, stmt) do { const long long t0_ = clock64(); stmt; if (blockIdx.x == 0) ru_w[i] += clock64() - t0_; } while (0)
+#else
+#define RU_WAIT(i, stmt) do { stmt; } while (0)
+#define RU_E2(i) do { } while (0)
+#endif
 
-__global__ void __cluster_dims__(RU_CLUSTER, 1, 1) __launch_bounds__(RU_THREADS, 1)
+enum RuBar {
+  RU_FULL = 0, RU_EMPTY = RU_STAGES, RU_AF = 2 * RU_STAGES, RU_AF1, RU_AE, RU_AE1, RU_D1F, RU_D1F1, RU_D1E, RU_D1E1,
+  RU_HSF, RU_HSE, RU_D2F, RU_D2F1, RU_D2E, RU_D2E1, RU_XF, RU_XE, RU_NBAR
+};
+static_assert(RU_NBAR <= 30, "barrier block");
+
+__global__ void __launch_bounds__(RU_THREADS, 1)
 res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_w1,
                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x,
                 const RuParams p) {
-  static_assert(128 % RU_CLUSTER == 0 && (128 / RU_CLUSTER) % 8 == 0, "W1 slices must be whole swizzle atoms");
-  constexpr int W1_ROWS = 128 / RU_CLUSTER;          // rows of each W1 K block this CTA fetches
-  constexpr uint16_t ALL = (1u << RU_CLUSTER) - 1;   // multicast mask: every CTA of the cluster
   using S = RuSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sW2 = smem + S::OFF_W2;
+  uint8_t* sW = smem + S::OFF_W;
   uint8_t* sHS = smem + S::OFF_HS;
   uint8_t* sX = smem + S::OFF_X;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
@@ -102,10 +120,11 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < RU_STAGES; ++i) {
       mbar_init(&bar[RU_FULL + i], 1);
-      mbar_init(&bar[RU_EMPTY + i], RU_CLUSTER);  // the slot is rewritten by every CTA's multicast
+      mbar_init(&bar[RU_EMPTY + i], 1);
     }
-    mbar_init(&bar[RU_W2], 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar[RU_AF + i], 1);
+      mbar_init(&bar[RU_AE + i], 1);
       mbar_init(&bar[RU_D1F + i], 1);
       mbar_init(&bar[RU_D1E + i], 8);
       mbar_init(&bar[RU_D2F + i], 1);
@@ -122,27 +141,25 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     tmem_relinquish();
   }
   tcgen05_fence_before();
-  cluster_sync_all();  // barriers of every CTA are initialised before any remote arrive / multicast
+  __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = cluster_ctarank();
 
-  // every CTA runs the same number of tile iterations (lockstep on the shared W1 stream); tiles past
-  // the end read zero-filled rows and store nothing
+  // every CTA runs the same number of tile iterations; tiles past the end read zero-filled rows and store nothing
   const int num_tiles = (p.L + 127) / 128;
   const int my_tiles = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int xs_rows = 128 + 6 * p.dil;  // rows of the xs box (= box height of tm_xs)
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     const bool elected = elect_one();
-    if (elected) {  // conv1 weights: constant, so they may be fetched before the dependency wait
-      mbar_arrive_expect_tx(&bar[RU_W2], S::TILE_BYTES);
-      tma_load_2d(sW2, &tm_w2, &bar[RU_W2], 0, 0);
-      tma_load_2d(sW2 + S::A_BYTES, &tm_w2, &bar[RU_W2], 64, 0);
-    }
     pdl_wait();
+#ifdef ACE_RU_TIMING
+    long long ru_w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long ru_t0 = clock64();
+#endif
     auto load_x = [&](int j) {  // residual rows of this CTA's j-th tile (single buffer)
-      mbar_wait(&bar[RU_XE], (uint32_t)((j & 1) ^ 1));
+      RU_WAIT(2, mbar_wait(&bar[RU_XE], (uint32_t)((j & 1) ^ 1)));
       if (elected) {
         const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * 128;
         mbar_arrive_expect_tx(&bar[RU_XF], S::TILE_BYTES);
@@ -150,90 +167,133 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
         tma_load_2d(sX + S::A_BYTES, &tm_x, &bar[RU_XF], 64, m0);
       }
     };
+    auto load_a = [&](int j) {  // xs box of this CTA's j-th tile: rows [m0 - 3 dil, m0 + 128 + 3 dil), both halves
+      const int buf = j & 1;
+      RU_WAIT(1, mbar_wait(&bar[RU_AE + buf], (uint32_t)(((j >> 1) & 1) ^ 1)));
+      if (elected) {
+        const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * 128;
+        uint8_t* dst = smem + buf * S::XS_BYTES;
+        mbar_arrive_expect_tx(&bar[RU_AF + buf], (uint32_t)(2 * xs_rows * 128));
+        tma_load_2d(dst, &tm_xs, &bar[RU_AF + buf], 0, m0 - 3 * p.dil);
+        tma_load_2d(dst + S::XS_HALF, &tm_xs, &bar[RU_AF + buf], 64, m0 - 3 * p.dil);
+      }
+    };
     int stage = 0;
     uint32_t phase = 0;
+    auto load_w = [&](const CUtensorMap* tm, int col) {  // one 16 KB weight block [128 out x 64 in] into the ring
+      RU_WAIT(0, mbar_wait(&bar[RU_EMPTY + stage], phase ^ 1));
+      if (elected) {
+        mbar_arrive_expect_tx(&bar[RU_FULL + stage], S::A_BYTES);
+        tma_load_2d(sW + stage * S::A_BYTES, tm, &bar[RU_FULL + stage], col, 0);
+      }
+      if (++stage == RU_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    if (my_tiles > 0) load_a(0);
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
       for (int kb = 0; kb < RU_KB; ++kb) {
-        const int tap = kb >> 1, kk = kb & 1;
-        mbar_wait(&bar[RU_EMPTY + stage], phase ^ 1);
-        if (elected) {
-          mbar_arrive_expect_tx(&bar[RU_FULL + stage], S::STAGE_BYTES);
-          tma_load_2d(smem + stage * S::STAGE_BYTES, &tm_xs, &bar[RU_FULL + stage], kk * 64,
-                      m0 + (tap - 3) * p.dil);
-          if (RU_CLUSTER == 1) {
-            tma_load_2d(smem + stage * S::STAGE_BYTES + S::A_BYTES, &tm_w1, &bar[RU_FULL + stage],
-                        tap * RU_C + kk * 64, 0);
-          } else {
-            tma_load_2d_mcast(smem + stage * S::STAGE_BYTES + S::A_BYTES + crank * (W1_ROWS * 128), &tm_w1,
-                              &bar[RU_FULL + stage], tap * RU_C + kk * 64, (int)crank * W1_ROWS, ALL);
-          }
-        }
-        if (++stage == RU_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        load_w(&tm_w1, (kb >> 1) * RU_C + (kb & 1) * 64);
+        // the next tile's xs box: its buffer was released when tile it-1's conv7 retired, i.e. before the MMA warp
+        // started on this tile, so this wait does not hold up the weight stream
+        if (kb == RU_LOADA_AT && it + 1 < my_tiles) load_a(it + 1);
         // the previous tile's residual rows are needed only after its conv1, which the MMA warp issues
         // at K block RU_MMA2_AT of this tile; by now epilogue 2 of the tile before that has long
         // released the buffer, so this wait never stalls the loads that feed the tensor core
         if (kb == RU_LOADX_AT && it > 0) load_x(it - 1);
+        if (kb == RU_MMA2_AT && it > 0) {  // W2 for conv1 of the previous tile, in the order the MMA warp consumes
+          load_w(&tm_w2, 0);
+          load_w(&tm_w2, 64);
+        }
       }
     }
-    if (my_tiles > 0) load_x(my_tiles - 1);
+    if (my_tiles > 0) {
+      load_w(&tm_w2, 0);
+      load_w(&tm_w2, 64);
+      load_x(my_tiles - 1);
+    }
+#ifdef ACE_RU_TIMING
+    if (blockIdx.x == 0 && elected) {
+      for (int i = 0; i < 3; ++i) g_ru_pwait[i] = ru_w[i];
+      g_ru_pwait[3] = clock64() - ru_t0;
+    }
+#endif
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_umma_idesc_bf16(128, RU_C);
     const bool elected = elect_one();
-    const uint32_t ring_lo = (smem_u32(smem) >> 4) & 0x3FFFu;
-    const uint32_t hs_lo = (smem_u32(sHS) >> 4) & 0x3FFFu, w2_lo = (smem_u32(sW2) >> 4) & 0x3FFFu;
-    auto mma2 = [&](int j) {  // x'_j accumulators: D2[j & 1] = hs_j . W2^T   (K = 128 = 2 halves x 4 slices)
-      const int b = j & 1;
-      mbar_wait(&bar[RU_HSF], (uint32_t)(j & 1));
-      mbar_wait(&bar[RU_D2E + b], (uint32_t)(((j >> 1) & 1) ^ 1));
-      tcgen05_fence_after();
-      if (elected) {
-        const uint32_t d = tmem_base + 256u + (uint32_t)(b * RU_C);
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss_lo(d, hs_lo + (uint32_t)(half * (S::A_BYTES >> 4) + 2 * k),
-                            w2_lo + (uint32_t)(half * (S::A_BYTES >> 4) + 2 * k), idesc, (half | k) != 0 ? 1u : 0u);
-        umma_commit(&bar[RU_HSE]);
-        umma_commit(&bar[RU_D2F + b]);
-      }
-    };
-    mbar_wait(&bar[RU_W2], 0);
+    const uint32_t xs_lo = (smem_u32(smem) >> 4) & 0x3FFFu, w_lo = (smem_u32(sW) >> 4) & 0x3FFFu;
+    const uint32_t hs_lo = (smem_u32(sHS) >> 4) & 0x3FFFu;
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = it & 1;
-      mbar_wait(&bar[RU_D1E + b], (uint32_t)(((it >> 1) & 1) ^ 1));
-      tcgen05_fence_after();
-      const uint32_t d1 = tmem_base + (uint32_t)(b * RU_C);
-      for (int kb = 0; kb < RU_KB; ++kb) {
-        mbar_wait(&bar[RU_FULL + stage], phase);
+    auto next_stage = [&]() {
+      if (++stage == RU_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+#ifdef ACE_RU_TIMING
+    long long ru_w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long ru_t0 = clock64();
+#endif
+    auto mma2 = [&](int j) {  // x'_j accumulators: D2[j & 1] = hs_j . W2^T   (K = 128 = 2 ring blocks x 4 slices)
+      const int b = j & 1;
+      RU_WAIT(3, mbar_wait(&bar[RU_HSF], (uint32_t)(j & 1)));
+      RU_WAIT(4, mbar_wait(&bar[RU_D2E + b], (uint32_t)(((j >> 1) & 1) ^ 1)));
+      const uint32_t d = tmem_base + 256u + (uint32_t)(b * RU_C);
+      for (int half = 0; half < 2; ++half) {
+        RU_WAIT(0, mbar_wait(&bar[RU_FULL + stage], phase));
         tcgen05_fence_after();
         if (elected) {
-          const uint32_t a_lo = ring_lo + (uint32_t)stage * (S::STAGE_BYTES >> 4);
-          const uint32_t b_lo = a_lo + (S::A_BYTES >> 4);
+          const uint32_t b_lo = w_lo + (uint32_t)stage * (S::A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss_lo(d, hs_lo + (uint32_t)(half * (S::A_BYTES >> 4) + 2 * k), b_lo + 2 * k, idesc,
+                            (half | k) != 0 ? 1u : 0u);
+          umma_commit(&bar[RU_EMPTY + stage]);
+          if (half == 1) {
+            umma_commit(&bar[RU_HSE]);
+            umma_commit(&bar[RU_D2F + b]);
+          }
+        }
+        next_stage();
+      }
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = it & 1;
+      RU_WAIT(2, mbar_wait(&bar[RU_D1E + b], (uint32_t)(((it >> 1) & 1) ^ 1)));
+      RU_WAIT(1, mbar_wait(&bar[RU_AF + b], (uint32_t)((it >> 1) & 1)));
+      tcgen05_fence_after();
+      const uint32_t d1 = tmem_base + (uint32_t)(b * RU_C);
+      const uint32_t box_lo = xs_lo + (uint32_t)b * (S::XS_BYTES >> 4);
+      for (int kb = 0; kb < RU_KB; ++kb) {
+        RU_WAIT(0, mbar_wait(&bar[RU_FULL + stage], phase));
+        tcgen05_fence_after();
+        if (elected) {
+          // tap kb >> 1 reads box rows [tap * dil, tap * dil + 128): + tap * dil * 128 B on the start address
+          const uint32_t a_lo = box_lo + (uint32_t)((kb & 1) * (S::XS_HALF >> 4) + (kb >> 1) * p.dil * 8);
+          const uint32_t b_lo = w_lo + (uint32_t)stage * (S::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss_lo(d1, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (RU_CLUSTER == 1) {
-            umma_commit(&bar[RU_EMPTY + stage]);
-          } else {
-            umma_commit_mcast(&bar[RU_EMPTY + stage], ALL);  // frees the slot in every CTA that multicasts into it
+          umma_commit(&bar[RU_EMPTY + stage]);
+          if (kb == RU_KB - 1) {
+            umma_commit(&bar[RU_D1F + b]);
+            umma_commit(&bar[RU_AE + b]);
           }
-          if (kb == RU_KB - 1) umma_commit(&bar[RU_D1F + b]);
         }
-        if (++stage == RU_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        next_stage();
         if (kb == RU_MMA2_AT && it > 0) mma2(it - 1);
       }
     }
     if (my_tiles > 0) mma2(my_tiles - 1);
+#ifdef ACE_RU_TIMING
+    if (blockIdx.x == 0 && elected) {
+      for (int i = 0; i < 5; ++i) g_ru_wait[i] = ru_w[i];
+      g_ru_wait[5] = clock64() - ru_t0;
+      g_ru_wait[6] = my_tiles;
+    }
+#endif
   } else if (warp >= 4 && warp < 12) {
     // ---------------- epilogue 1: D1 -> snake2 -> hs tile in smem (A operand of conv1) ----------------
     const int quarter = (warp - 4) & 3, r = quarter * 32 + lane;
@@ -284,27 +344,39 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     }
   } else if (warp >= 12) {
     // ---------------- epilogue 2: D2 + b2 + x -> x', snake_next(x') ----------------
+    // Each warp owns a [32 rows x 64 channels] slab of the residual tile in sX (its lane quarter's rows of its
+    // channel half): it turns the slab into x' IN PLACE, copies it out with 8 lanes per row (4 rows x 128 contiguous
+    // bytes per store instruction), then overwrites it with snake_next(x') and copies that out the same way.  Storing
+    // thread-per-row straight from registers made every 16-byte store of a warp hit 32 different lines: ncu had the
+    // LSU data pipe at 63 % and lg_throttle stalls on this kernel, 92 M store sectors for 2.9 M requests.
     const int quarter = (warp - 12) & 3, r = quarter * 32 + lane;
     const int c_lo = ((warp - 12) >> 2) * 64;  // this warp's 64 channels
-    const uint8_t* xrow = sX + r * 128;
+    const WarpStage slab{sX + (c_lo >> 6) * S::A_BYTES + quarter * 32 * 128};  // same XOR-by-row swizzle as TMA's
+#ifdef ACE_RU_TIMING
+    const bool e2_stamp = blockIdx.x == 0 && warp == 12;
+    long long ru_e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, e_prev = clock64();
+    const long long e_t0 = e_prev;
+#endif
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
-      const long row = ((long)blockIdx.x + (long)it * gridDim.x) * 128 + r;
+      const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * 128 + quarter * 32;
       mbar_wait(&bar[RU_D2F + b], (uint32_t)((it >> 1) & 1));
+      RU_E2(0);
       mbar_wait(&bar[RU_XF], (uint32_t)(it & 1));
+      RU_E2(1);
       tcgen05_fence_after();
       __syncwarp();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u + (uint32_t)(b * RU_C);
-      const bool ok = row < p.L;
-#pragma unroll 1
-      for (int c = c_lo; c < c_lo + 64; c += 32) {
+      uint32_t xs_packed[32];  // snake_next(x') of this thread's 64 channels, held until x' has left the slab
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = c_lo + half * 32;
         float v[32];
         tmem_ld_32x32(taddr + (uint32_t)c, v);
-        const uint8_t* half = xrow + (c >> 6) * S::A_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (((c & 32) >> 3) + q) ^ (r & 7);
-          const uint4 xq = *reinterpret_cast<const uint4*>(half + chunk * 16);
+          uint4* xp = slab.at(lane, half * 4 + q);
+          const uint4 xq = *xp;
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c) + 2 * q);
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c) + 2 * q + 1);
           // x' = bf16(bf16(acc + b2) + x): one pair-wise rounding, then a packed bf16 add (exactly rounded)
@@ -313,7 +385,7 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
           xn.y = badd2(pack_bf16x2(v[8 * q + 2] + b0.z, v[8 * q + 3] + b0.w), xq.y);
           xn.z = badd2(pack_bf16x2(v[8 * q + 4] + b1.x, v[8 * q + 5] + b1.y), xq.z);
           xn.w = badd2(pack_bf16x2(v[8 * q + 6] + b1.z, v[8 * q + 7] + b1.w), xq.w);
-          if (ok) reinterpret_cast<uint4*>(p.ox + row * RU_C + c)[q] = xn;
+          *xp = xn;
           unpack_bf16x2(xn.x, v[8 * q + 0], v[8 * q + 1]); unpack_bf16x2(xn.y, v[8 * q + 2], v[8 * q + 3]);
           unpack_bf16x2(xn.z, v[8 * q + 4], v[8 * q + 5]); unpack_bf16x2(xn.w, v[8 * q + 6], v[8 * q + 7]);
         }
@@ -321,24 +393,37 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
         for (int i = 0; i < 8; ++i) {
           const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.an + c) + i);
           const float4 i4 = __ldg(reinterpret_cast<const float4*>(p.ibn + c) + i);
-          v[4 * i + 0] = snake_f(v[4 * i + 0], a4.x, i4.x);
-          v[4 * i + 1] = snake_f(v[4 * i + 1], a4.y, i4.y);
-          v[4 * i + 2] = snake_f(v[4 * i + 2], a4.z, i4.z);
-          v[4 * i + 3] = snake_f(v[4 * i + 3], a4.w, i4.w);
+          xs_packed[half * 16 + 2 * i] = pack_bf16x2(snake_f(v[4 * i + 0], a4.x, i4.x), snake_f(v[4 * i + 1], a4.y, i4.y));
+          xs_packed[half * 16 + 2 * i + 1] = pack_bf16x2(snake_f(v[4 * i + 2], a4.z, i4.z), snake_f(v[4 * i + 3], a4.w, i4.w));
         }
-        if (ok) store_bf16x32(p.oxs + row * RU_C + c, v);
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar[RU_D2E + b]);
-        mbar_arrive(&bar[RU_XE]);
-      }
+      if (lane == 0) mbar_arrive(&bar[RU_D2E + b]);  // the accumulator is in registers / shared memory
+      RU_E2(2);
+      slab.store_rows(lane, 64, [&](int rr) -> bf16* {
+        return row0 + rr < p.L ? p.ox + (row0 + rr) * RU_C + c_lo : nullptr;
+      });
+      RU_E2(3);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *slab.at(lane, q) = make_uint4(xs_packed[4 * q], xs_packed[4 * q + 1], xs_packed[4 * q + 2], xs_packed[4 * q + 3]);
+      slab.store_rows(lane, 64, [&](int rr) -> bf16* {
+        return row0 + rr < p.L ? p.oxs + (row0 + rr) * RU_C + c_lo : nullptr;
+      });
+      if (lane == 0) mbar_arrive(&bar[RU_XE]);
+      RU_E2(4);
     }
+#ifdef ACE_RU_TIMING
+    if (e2_stamp && lane == 0) {
+      for (int i = 0; i < 5; ++i) g_ru_e2[i] = ru_e[i];
+      g_ru_e2[5] = clock64() - e_t0;
+    }
+#endif
   }
 
   tcgen05_fence_before();
-  cluster_sync_all();  // no CTA may exit while a sibling can still multicast into it
+  __syncthreads();
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
@@ -348,8 +433,12 @@ inline int launch_res_unit_fused(const bf16* xs, const bf16* x, const bf16* w1, 
                                  cudaStream_t stream) {
   if (p.L <= 0) return ACE_OK;
   CUtensorMap tm_xs, tm_w1, tm_w2, tm_x;
-  ACE_PROPAGATE(encode_tmap_2d(&tm_xs, xs, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 128));
-  ACE_PROPAGATE(encode_tmap_2d(&tm_w1, w1, 7 * RU_C, RU_C, 7 * RU_C * sizeof(bf16), 128 / RU_CLUSTER));
+  if (p.dil < 1 || p.dil > RU_MAX_DIL) {
+    set_error("res_unit: dilation %d outside [1, %d]", p.dil, RU_MAX_DIL);
+    return ACE_ERR_INVALID;
+  }
+  ACE_PROPAGATE(encode_tmap_2d(&tm_xs, xs, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 128 + 6 * p.dil));
+  ACE_PROPAGATE(encode_tmap_2d(&tm_w1, w1, 7 * RU_C, RU_C, 7 * RU_C * sizeof(bf16), 128));
   ACE_PROPAGATE(encode_tmap_2d(&tm_w2, w2, RU_C, RU_C, RU_C * sizeof(bf16), 128));
   ACE_PROPAGATE(encode_tmap_2d(&tm_x, x, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 128));
   static bool attr_set = false;
@@ -358,9 +447,7 @@ inline int launch_res_unit_fused(const bf16* xs, const bf16* x, const bf16* w1, 
     attr_set = true;
   }
   const int tiles = (p.L + 127) / 128;
-  const int max_grid = num_sms() / RU_CLUSTER * RU_CLUSTER;
-  int grid = (tiles + RU_CLUSTER - 1) / RU_CLUSTER * RU_CLUSTER;
-  if (grid > max_grid) grid = max_grid;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_tag_gemm(p.L, RU_C, 8 * RU_C);
   prof_begin(PROF_GEMM, 2.0 * p.L * RU_C * 8.0 * RU_C, 4.0 * p.L * RU_C * 2.0, stream);
   ACE_CUDA_CHECK(launch_kernel(res_unit_kernel, dim3(grid), dim3(RU_THREADS), (size_t)RuSmem::TOTAL, stream, tm_xs,

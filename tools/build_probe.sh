@@ -13,3 +13,4 @@ nvcc $FLAGS -o tools/_bin/tmem_probe tools/tmem_probe.cu $CS/runtime.cu
 nvcc $FLAGS -DACE_ATTN_TIMING -o tools/_bin/attn_timing tools/attn_timing.cu $CS/runtime.cu
 nvcc $FLAGS -o tools/_bin/gemm_multiwave tools/gemm_multiwave.cu $CS/runtime.cu
 nvcc  -o tools/_bin/desc_rowstep_probe tools/desc_rowstep_probe.cu $CS/runtime.cu
+nvcc $FLAGS -DACE_RU_TIMING -o tools/_bin/ru_timing tools/ru_timing.cu $CS/runtime.cu
