@@ -766,3 +766,32 @@ def test_real_get_lyric_score_runs_through_the_decoder_shim():
     assert isinstance(out["lm_score"], float) and isinstance(out["dit_score"], float)
     assert h.b200_dit.calls[-1] == ("attn", (2, T, 64), [1.0, 0.125], 4)
     assert isinstance(h.model.decoder, Dec)
+
+
+def test_song_pipeline_ordering_and_deferred_errors():
+    """SongPipeline is plain host logic: results come back one submit later, in order; a song whose latent guard
+    fired raises at ITS turn (from wait()), and the queue keeps serving the songs behind it."""
+    from acestep_b200.pipeline import SongPipeline
+
+    class Pending:
+        def __init__(self, value, fail=False):
+            self.value, self.fail, self.waited = value, fail, False
+
+        def wait(self):
+            self.waited = True
+            if self.fail:
+                raise RuntimeError("Generation produced NaN or Inf latents.")
+            return {"audio": self.value}
+
+    q = SongPipeline(depth=1)
+    a, b, c = Pending("a"), Pending("b", fail=True), Pending("c")
+    assert q.submit(a) is None and not a.waited           # one song stays in flight
+    assert q.submit(b)["audio"] == "a" and not b.waited   # a's result arrives when b is submitted
+    with pytest.raises(RuntimeError, match="NaN or Inf"):
+        q.submit(c)                                       # b's guard fires at b's turn
+    assert q.drain()["audio"] == "c" and q.drain() is None
+    q0 = SongPipeline(depth=0)                            # depth 0 = blocking
+    assert q0.submit(Pending("x"))["audio"] == "x"
+    q2 = SongPipeline(depth=2)
+    assert q2.submit(Pending(1)) is None and q2.submit(Pending(2)) is None and q2.submit(Pending(3))["audio"] == 1
+    assert q2.drain()["audio"] == 3
