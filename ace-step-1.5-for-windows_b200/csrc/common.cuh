@@ -194,6 +194,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// try_wait with a suspend-time hint: the warp may sleep in hardware until the phase completes (it is woken by the
+// completion) or the hint expires, instead of coming back to the scheduler after the default interval.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+// -DACE_WAIT_HINT_NS=<ns>: poll with that suspend-time hint in the slow path of mbar_wait (A/B builds)
+#ifdef ACE_WAIT_HINT_NS
+#define ACE_TRY_WAIT_SLOW(bar, parity) mbar_try_wait_hint(bar, parity, ACE_WAIT_HINT_NS)
+#else
+#define ACE_TRY_WAIT_SLOW(bar, parity) mbar_try_wait(bar, parity)
+#endif
 // Wait for the phase with the given parity to complete.  With ACE_HANG_GUARD the
 // wait is bounded (~2 s of SM clocks) and traps, so a protocol bug surfaces as a
 // launch failure instead of a wedged GPU.
@@ -201,7 +220,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;  // fast path: no clock read on the issue threads' critical path
 #if ACE_HANG_GUARD
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!ACE_TRY_WAIT_SLOW(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("ace: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
@@ -209,7 +228,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 #else
-  while (!mbar_try_wait(bar, parity)) {
+  while (!ACE_TRY_WAIT_SLOW(bar, parity)) {
   }
 #endif
 }
