@@ -55,6 +55,10 @@ struct GemmShape {
   // once, A is re-read once per wave), 1 = n fastest (consecutive clusters share an A row block; A is streamed
   // once and B — the smaller operand — stays in L2).  make_gemm_plan sets it to "A is the larger operand".
   int raster_n;
+  // probe builds (ACE_RACE_DELAY=1): column group 0 of the every-tile tail epilogue sleeps 30 us per tile, which puts
+  // group 1 a whole tile ahead of the loader warp — the schedule under which a hand-back protocol that counts
+  // arrivals per TILE instead of per tile-with-boxes deadlocks (tests/test_gpu_kernels.py)
+  int race_delay;
 };
 
 #ifdef __CUDACC__
@@ -634,15 +638,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   } else if (warp == 3) {
     if constexpr (ALLTAIL) {
       // ---------------- residual loader (both CTAs): tile i+1's boxes as soon as tile i's are handed back -------
-      // (resid_bar[i] only flips on tiles that HAVE box i — the last column tile of N = 2048 at 192-wide tiles has
-      // two — so its parity is counted per box on both sides, not derived from the tile counter)
+      // Barrier accounting is per box / per column group, never derived from the tile counter: the last column tile
+      // of N = 2048 at 192-wide tiles has two boxes, so group 1 has NOTHING to do there.  resid_bar[i] flips only on
+      // tiles that have box i, and resid_empty[g] is arrived (and waited for) only for tiles in which group g had
+      // boxes — a group that merely passes through a tile must not arrive, or it could complete two phases before
+      // this warp has looked at the first one (it then waits for a third that needs this warp's next load: a
+      // deadlock that the n-fastest tile order, where such tiles sit in the middle of a CTA's sequence, produced).
       const bool elected = elect_one();
-      int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      uint32_t in_use = 0, wait_parity = 0;  // bit g: group g's boxes hold a tile / parity of its next hand-back
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = tile_m(tile) * 256 + (int)rank * 128;
         const int tile_n0 = tile_n(tile) * BN;
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&resid_empty[g], (uint32_t)((it & 1) ^ 1));
+          if (2 * g >= NBOX || tile_n0 + 128 * g >= shp.N) continue;  // group g has no box in this tile
+          if (in_use & (1u << g)) {
+            mbar_wait(&resid_empty[g], (wait_parity >> g) & 1u);
+            wait_parity ^= 1u << g;
+          }
+          in_use |= 1u << g;
           if (elected) {
             for (int bi = 2 * g; bi < 2 * g + 2 && bi < NBOX; ++bi) {
               if (tile_n0 + 64 * bi >= shp.N) break;
@@ -692,6 +705,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
         }
         tcgen05_fence_before();  // the accumulator is free: the next tile's MMAs may overwrite it
+#ifdef ACE_PROBE
+        if (shp.race_delay && grp == 0) __nanosleep(30000);
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
         if (epi.no.g != nullptr) {
@@ -714,7 +730,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             tma_store_commit();
           }
         }
-        if (quarter == 0) {
+        if (quarter == 0 && 2 * grp < NBOX && tile_n0 + 128 * grp < shp.N) {  // this group had boxes in this tile
           tma_store_wait_read_all();  // (only the lane that issued has pending groups)
           __syncwarp();
           if (elect_one()) mbar_arrive(&resid_empty[grp]);

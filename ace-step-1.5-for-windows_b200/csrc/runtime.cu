@@ -281,6 +281,9 @@ int make_gemm_plan(GemmPlan* plan, const bf16* a, int a_rows, int kc, long a_ld,
     const double a_bytes = 2.0 * m * kc, b_bytes = 2.0 * n * kc * ntaps;
     plan->shp.raster_n = forced != 2 ? forced : (ntaps == 1 && a_bytes > 48e6 && a_bytes > b_bytes ? 1 : 0);
   }
+  {
+    plan->shp.race_delay = probe_env("ACE_RACE_DELAY") != nullptr;  // read per plan: a test flips it per handle
+  }
   if (m <= 0 || n <= 0) return ACE_OK;
   ACE_PROPAGATE(encode_tmap_2d(&plan->tma_a, a, (uint64_t)kc, (uint64_t)a_rows,
                                (uint64_t)a_ld * sizeof(bf16), GEMM_BM));

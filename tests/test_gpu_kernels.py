@@ -658,3 +658,44 @@ def test_vae_ragged_lengths_one_handle(lib):
         assert got_mean.shape == (T, 64)
         assert rel_l2(got_mean.cpu().float(), mean[0].T) <= max(1.1 * floor, 2e-2), (T, floor)
     vae.close()
+
+
+def test_multiwave_residual_gemms_hand_back_protocol_under_a_forced_race(lib, probe):
+    """M = 15000 (600 s, CFG): the residual GEMMs run 192-wide tiles in n-fastest order with the every-tile tail
+    variant, so a CTA pair meets the two-box last column tile — a tile in which column group 1 has nothing to load —
+    in the MIDDLE of its tile sequence.  A hand-back protocol that let the idle group arrive on `resid_empty` there
+    deadlocks when group 1 gets a tile ahead of the loader warp (it completes two phases before the loader looks at
+    the first): seen on some boxes only, caught by the 24-layer full-size test.  The probe build forces that schedule
+    (ACE_RACE_DELAY=1: group 0 sleeps 30 us per tile — with it the old protocol deadlocks on the first launch): the
+    forward must complete (the bounded barrier wait turns a deadlock into a launch failure) and equal the release
+    library's result bit for bit; then a few undisturbed replays on the release library."""
+    import os
+
+    from acestep_b200.synthetic import random_dit_state
+
+    shape = DiTShape(num_hidden_layers=2)
+    state = random_dit_state(shape, 0, DEV)
+    g = torch.Generator(device=DEV).manual_seed(15000)
+    T, E = 15000, 70
+    xt = torch.randn(2, T, 64, device=DEV, generator=g).bfloat16()
+    ctx = torch.randn(2, T, 128, device=DEV, generator=g).bfloat16()
+    enc = torch.randn(2, E, shape.hidden_size, device=DEV, generator=g).bfloat16()
+    outs = []
+    for use, env in ((probe, "1"), (lib, None)):
+        if env is not None:
+            os.environ["ACE_RACE_DELAY"] = env
+        try:
+            dit = B200DiT(state, shape, DEV, lib=use)
+            dit.bind(2, T, E)  # the plans (and the probe switch) are made here
+        finally:
+            os.environ.pop("ACE_RACE_DELAY", None)
+        dit.set_condition(enc)
+        outs.append(dit.step(xt, ctx, [0.5, 0.25]).clone())
+        torch.cuda.synchronize()
+        if use is lib:
+            for i in range(4):
+                assert torch.equal(dit.step(xt, ctx, [0.5, 0.25]), outs[-1]), i
+            torch.cuda.synchronize()
+        dit.close()
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1])
