@@ -31,6 +31,13 @@ class PendingSong:
     def done(self) -> bool:
         return self._ev[2].query()
 
+    @property
+    def device_audio(self):
+        """The waveform on the device ([B, 2, N] fp32), valid in stream order on `stream` (the caller's current stream
+        unless the pipeline overlaps the codec) WITHOUT waiting — for callers that queue device work behind the song,
+        e.g. the multi-GPU gather.  The latent guard has not been looked at yet: call wait() before handing it out."""
+        return self._res.get("_device_audio", self._res.get("audio"))
+
     def wait(self) -> Dict[str, Any]:
         self._ev[2].synchronize()
         bad, nonzero = self._flags.tolist()

@@ -486,7 +486,7 @@ def run_b200(args, wl):
                 return
             def one(_song_index):
                 pend = r.song_device(i)
-                wav = pend._res["audio"][0]  # device tensor, stream-ordered: the gather is queued behind the song
+                wav = pend.device_audio[0]  # device tensor, stream-ordered: the gather is queued behind the song
                 retire(pipe_s.submit(pend))
                 return wav
             # at most one gather in flight: the previous song's gather (finished long ago) is retired here, which
