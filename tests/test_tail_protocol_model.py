@@ -173,3 +173,87 @@ def test_the_device_case_in_the_model():
     with pytest.raises(ProtocolError):
         for _ in range(2000):
             simulate(seq, "arrive_every_tile", rng)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Single-wave tail path: the residual boxes of a CTA pair's LAST tile ride the operand ring as extra "k-blocks" that
+# the tensor-core warp never consumes (gemm.cuh, the `Epi::kTmaTail && !ALLTAIL` branch).
+# ---------------------------------------------------------------------------------------------------------------------
+def simulate_ring_ride(my_tiles, total_kb, nbox, stages, rng, max_steps=200000):
+    full = [Barrier() for _ in range(stages)]
+    empty = [Barrier() for _ in range(stages)]
+    resid = [Barrier() for _ in range(nbox)]
+    slot = [None] * stages            # ("op", tile, kb) / ("box", i)
+    last_mma_done = [False]
+
+    def producer():
+        stage, phase = 0, 0
+        for t in range(my_tiles):
+            for kb in range(total_kb):
+                yield ("wait", empty[stage], phase ^ 1)
+                slot[stage] = ("op", t, kb)
+                full[stage].arrive()
+                stage += 1
+                if stage == stages:
+                    stage, phase = 0, phase ^ 1
+                yield ("step",)
+        for i in range(nbox):
+            yield ("wait", empty[stage], phase ^ 1)
+            if slot[stage] is not None and slot[stage][0] == "box":
+                raise ProtocolError("a residual box overwrites another one")
+            slot[stage] = ("box", i)
+            resid[i].arrive()
+            stage += 1
+            if stage == stages:
+                stage, phase = 0, phase ^ 1
+            yield ("step",)
+
+    def mma():
+        stage, phase = 0, 0
+        for t in range(my_tiles):
+            for kb in range(total_kb):
+                yield ("wait", full[stage], phase)
+                if slot[stage] != ("op", t, kb):
+                    raise ProtocolError(f"MMA reads {slot[stage]} as operand block ({t}, {kb})")
+                yield ("step",)                 # the MMAs run ...
+                empty[stage].arrive()           # ... and their commit frees the slot
+                stage += 1
+                if stage == stages:
+                    stage, phase = 0, phase ^ 1
+        last_mma_done[0] = True
+
+    def epilogue():
+        ring0 = (my_tiles * total_kb) % stages
+        while not last_mma_done[0]:
+            yield ("step",)
+        for i in range(nbox):
+            yield ("wait", resid[i], 0)
+            if slot[(ring0 + i) % stages] != ("box", i):
+                raise ProtocolError(f"epilogue finds {slot[(ring0 + i) % stages]} where box {i} should be")
+            yield ("step",)
+
+    agents = {"producer": producer(), "mma": mma(), "epi": epilogue()}
+    pending = {k: next(v) for k, v in agents.items()}
+    for _ in range(max_steps):
+        if not agents:
+            return
+        runnable = [k for k, r in pending.items() if r[0] == "step" or r[1].ready(r[2])]
+        if not runnable:
+            raise ProtocolError(f"deadlock: {sorted(pending)}")
+        k = rng.choice(runnable)
+        try:
+            pending[k] = next(agents[k])
+        except StopIteration:
+            del agents[k], pending[k]
+    raise ProtocolError("no progress bound hit")
+
+
+def test_residual_boxes_riding_the_operand_ring():
+    """Every (tiles per CTA pair, k-blocks per tile, boxes) combination the DiT produces and then some: the boxes land
+    in the slots the epilogue computes from `ring0`, behind MMAs that have retired, for any schedule."""
+    rng = random.Random(99)
+    for my_tiles in (1, 2, 3):
+        for total_kb in (1, 2, 5, 6, 7, 32, 96):
+            for nbox in (1, 2, 3, 4):
+                for _ in range(4):
+                    simulate_ring_ride(my_tiles, total_kb, nbox, 6, rng)
