@@ -317,3 +317,86 @@ def test_vae_decode_beyond_one_pass_matches_single_pass():
     assert windowed.shape == single.shape == (2, frames * 1920) and torch.isfinite(single).all()
     assert torch.equal(windowed, single), max_abs(windowed, single)
     vae.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C5 as benchmarked: repaint of a 120 s song through the public pipeline call (encode -> 27 steps -> decode)
+# ---------------------------------------------------------------------------------------------------------
+def test_c5_repaint_chain_full_size(full):
+    """BASELINE configs[4] end to end at full size through `B200Pipeline.repaint` — the call `bench.py --workload c5`
+    times: reference-audio encode (3000 frames), source latents with the silence latent in [750, 2250) and chunk mask
+    1 there, the 27-step CFG 7.0 + APG loop at T = 3000, whole-song decode, peak normalisation.  Each stage against
+    the oracle evaluated in fp32 on the device, stage inputs taken from the CUDA path so that every comparison
+    isolates one stage; codec weights use the low-gain init (tight bf16 spread), bounds as in the tests above:
+    encode / decode max(1.5 x bf16 spread, 1e-2), loop max(1.5 x spread, 3e-2)."""
+    from acestep_b200.pipeline import B200Pipeline
+
+    cfg, w, wd, _dit = full
+    vcfg, vsd, wfd, wbd = _vae_case(0.5)
+    null = make_null_condition_emb(cfg).to(torch.bfloat16)
+    pipe = B200Pipeline(w, vsd, DiTShape.from_config(cfg), VaeShape(), null, DEV, turbo=False)
+    g = torch.Generator().manual_seed(505)
+    T, E, s0, s1, steps = 3000, 512, 750, 2250, 27
+    audio = torch.rand(1, 2, T * vcfg.hop, generator=g) - 0.5
+    eps = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    sil = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    enc = torch.randn(1, E, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    noise = torch.randn(1, T, 64, generator=g).to(torch.bfloat16)
+    out = pipe.repaint(enc, audio, s0, s1, sil, None, posterior_eps=eps, noise=noise, infer_steps=steps,
+                       diffusion_guidance_sale=7.0, shift=3.0)
+    pipe.close()
+    src_lat = out["src_latents"].cpu().float()
+    lat, wav = out["target_latents"].cpu().float(), out["audio"].cpu()
+    assert wav.shape == (1, 2, T * vcfg.hop) and torch.isfinite(wav).all() and torch.isfinite(lat).all()
+    torch.cuda.empty_cache()
+
+    # (1) encode + posterior sample vs the reference's tiled encode of the oracle encoder (mean and scale)
+    a16 = audio.to(torch.bfloat16)
+    with torch.no_grad():
+        def sample(wts, x):
+            mean = ovae.tiled_encode(lambda c, _w0: ovae.encode_moments(wts, vcfg, c)[0], x)
+            scale = ovae.tiled_encode(lambda c, _w0: ovae.encode_moments(wts, vcfg, c)[1], x)
+            e = eps.to(x.device, x.dtype).transpose(1, 2)
+            return (mean + (torch.nn.functional.softplus(scale) + 1e-4) * e).transpose(1, 2)
+        want_src = sample(wfd, a16.float().to(DEV)).cpu()
+        b16_src = sample(wbd, a16.to(DEV)).float().cpu()
+    floor, err = rel_l2(b16_src, want_src), rel_l2(src_lat, want_src)
+    record("c5_chain_encode", rel_l2=err, bf16_torch_spread=floor)
+    assert err <= max(1.5 * floor, 1e-2), (err, floor)
+    torch.cuda.empty_cache()
+
+    # (2) the loop, from the CUDA path's own source latents
+    src = out["src_latents"].clone().cpu()
+    src[:, s0:s1] = sil[:, s0:s1]
+    mask = torch.zeros(1, T, 64, dtype=torch.bfloat16)
+    mask[:, s0:s1] = 1.0
+    ctx = torch.cat([src, mask], -1)
+    wb = {k: v.to(torch.bfloat16) for k, v in wd.items()}
+    ts = torch.linspace(1.0, 0.0, steps + 1, device=DEV, dtype=torch.bfloat16)
+    ts = (3.0 * ts / (1 + 2.0 * ts)).float().cpu()
+    vel32 = lambda xt, t, c, e, cache: dit_forward(wd, cfg, xt, t, c, e, cache, bf16_time=True)
+    vel16 = lambda xt, t, c, e, cache: dit_forward(wb, cfg, xt, t, c, e, cache)
+    d = lambda x, dt: x.to(DEV, dt)
+    with torch.no_grad():
+        want = osamp.sample_base(vel32, d(enc, torch.float32), d(ctx, torch.float32), d(src, torch.float32), None,
+                                 null_emb=d(null, torch.float32), guidance_scale=7.0, shift=3.0, timesteps=ts,
+                                 noise=d(noise, torch.float32), new_cache=CrossCache).cpu()
+        torch.cuda.empty_cache()
+        b16 = osamp.sample_base(vel16, d(enc, torch.bfloat16), d(ctx, torch.bfloat16), d(src, torch.bfloat16), None,
+                                null_emb=d(null, torch.bfloat16), infer_steps=steps, guidance_scale=7.0, shift=3.0,
+                                noise=d(noise, torch.bfloat16), new_cache=CrossCache).cpu().float()
+    del wb
+    torch.cuda.empty_cache()
+    floor, err = rel_l2(b16, want), rel_l2(lat, want)
+    record("c5_chain_loop_27", rel_l2=err, bf16_torch_spread=floor)
+    assert err <= max(1.5 * floor, 3e-2), (err, floor)
+
+    # (3) decode + peak normalisation, from the CUDA path's own latents
+    z = out["target_latents"].transpose(1, 2).contiguous()
+    with torch.no_grad():
+        want_wav = ovae.tiled_decode(lambda x: ovae.decode(wfd, vcfg, x), z.float(), 512, 64).cpu()
+        b16_wav = ovae.tiled_decode(lambda x: ovae.decode(wbd, vcfg, x), z, 512, 64).float().cpu()
+    norm = lambda x: x / x.abs().amax(dim=[1, 2], keepdim=True).clamp(min=1.0)
+    floor, err = rel_l2(norm(b16_wav), norm(want_wav)), rel_l2(wav, norm(want_wav))
+    record("c5_chain_decode", rel_l2=err, bf16_torch_spread=floor)
+    assert err <= max(1.5 * floor, 1e-2), (err, floor)
