@@ -400,3 +400,64 @@ def test_c5_repaint_chain_full_size(full):
     floor, err = rel_l2(norm(b16_wav), norm(want_wav)), rel_l2(wav, norm(want_wav))
     record("c5_chain_decode", rel_l2=err, bf16_torch_spread=floor)
     assert err <= max(1.5 * floor, 1e-2), (err, floor)
+
+
+def test_c2_generate_full_size(full):
+    """The headline call itself — `B200Pipeline.generate` at BASELINE configs[1] (60 s, 27 steps, CFG 7.0 + APG,
+    E = 512), the starting noise drawn inside from a per-song seed exactly as `bench.py` runs it — against the
+    oracle: the loop from the same seeded noise (`prepare_noise` makes the reference's RNG calls), the waveform from
+    the CUDA path's own latents through the reference's tiled decode + peak normalisation (low-gain codec).
+    Two songs back to back through `SongPipeline` as the benchmark does; the second must equal a blocking call."""
+    from acestep_b200.pipeline import B200Pipeline, SongPipeline
+    from acestep_b200.sampler import prepare_noise
+
+    cfg, w, wd, _dit = full
+    vcfg, vsd, wfd, wbd = _vae_case(0.5)
+    null = make_null_condition_emb(cfg).to(torch.bfloat16)
+    pipe = B200Pipeline(w, vsd, DiTShape.from_config(cfg), VaeShape(), null, DEV, turbo=False)
+    g = torch.Generator().manual_seed(202)
+    T, E, steps = 1500, 512, 27
+    enc = torch.randn(1, E, cfg.hidden_size, generator=g).to(torch.bfloat16).pin_memory()
+    src = torch.randn(1, T, 64, generator=g).to(torch.bfloat16).pin_memory()
+    ctx = torch.cat([src, torch.ones(1, T, 64, dtype=torch.bfloat16)], -1).pin_memory()
+    kw = dict(infer_steps=steps, diffusion_guidance_sale=7.0, shift=3.0)
+    q = SongPipeline(depth=1)
+    assert q.submit(pipe.generate_async(enc, ctx, src, [41], **kw)) is None
+    first = q.submit(pipe.generate_async(enc, ctx, src, [42], **kw))
+    second = q.drain()
+    lat, wav = first["target_latents"].cpu().float(), first["audio"].clone()
+    again = pipe.generate(enc, ctx, src, [42], **kw)
+    assert torch.equal(again["audio"], second["audio"]) and torch.equal(again["target_latents"], second["target_latents"])
+    pipe.close()
+    assert wav.shape == (1, 2, T * vcfg.hop) and torch.isfinite(wav).all()
+    torch.cuda.empty_cache()
+
+    noise = prepare_noise((1, T, 64), [41], DEV)
+    wb = {k: v.to(torch.bfloat16) for k, v in wd.items()}
+    ts = torch.linspace(1.0, 0.0, steps + 1, device=DEV, dtype=torch.bfloat16)
+    ts = (3.0 * ts / (1 + 2.0 * ts)).float().cpu()
+    vel32 = lambda xt, t, c, e, cache: dit_forward(wd, cfg, xt, t, c, e, cache, bf16_time=True)
+    vel16 = lambda xt, t, c, e, cache: dit_forward(wb, cfg, xt, t, c, e, cache)
+    d = lambda x, dt: x.to(DEV, dt)
+    with torch.no_grad():
+        want = osamp.sample_base(vel32, d(enc, torch.float32), d(ctx, torch.float32), d(src, torch.float32), None,
+                                 null_emb=d(null, torch.float32), guidance_scale=7.0, shift=3.0, timesteps=ts,
+                                 noise=noise.float(), new_cache=CrossCache).cpu()
+        torch.cuda.empty_cache()
+        b16 = osamp.sample_base(vel16, d(enc, torch.bfloat16), d(ctx, torch.bfloat16), d(src, torch.bfloat16), None,
+                                null_emb=d(null, torch.bfloat16), infer_steps=steps, guidance_scale=7.0, shift=3.0,
+                                noise=noise, new_cache=CrossCache).cpu().float()
+    del wb
+    torch.cuda.empty_cache()
+    floor, err = rel_l2(b16, want), rel_l2(lat, want)
+    record("c2_generate_loop_27", rel_l2=err, bf16_torch_spread=floor)
+    assert err <= max(1.5 * floor, 3e-2), (err, floor)
+
+    z = first["target_latents"].transpose(1, 2).contiguous()
+    with torch.no_grad():
+        want_wav = ovae.tiled_decode(lambda x: ovae.decode(wfd, vcfg, x), z.float(), 512, 64).cpu()
+        b16_wav = ovae.tiled_decode(lambda x: ovae.decode(wbd, vcfg, x), z, 512, 64).float().cpu()
+    norm = lambda x: x / x.abs().amax(dim=[1, 2], keepdim=True).clamp(min=1.0)
+    floor, err = rel_l2(norm(b16_wav), norm(want_wav)), rel_l2(wav.cpu(), norm(want_wav))
+    record("c2_generate_waveform", rel_l2=err, bf16_torch_spread=floor)
+    assert err <= max(1.5 * floor, 1e-2), (err, floor)
