@@ -4,7 +4,7 @@ chain on identical audio, posterior noise, starting noise and weights.
 
 Tolerances: the source latents come out of a bf16 codec pass (bound: the measured spread of an
 all-bf16 torch run of the oracle encoder, floor 2e-2, like tests/test_gpu_kernels.py); the denoised
-latents and the waveform use the bounds of __graft_entry__.smoke() (3e-2 / 1e-1 rel-L2), with the
+latents and the waveform use the bounds of __graft_entry__.smoke() (3e-2 / 2e-2 rel-L2, low-gain codec init), with the
 oracle loop started from the CUDA path's own source latents so the comparison isolates the loop.
 """
 import pytest
@@ -32,7 +32,7 @@ DEV = torch.device("cuda:0")
 def test_repaint_matches_oracle_chain():
     cfg, vcfg = DiTConfig.tiny(), ovae.VaeConfig.tiny()
     w = bf16_round_(make_dit_weights(cfg, seed=0))
-    vsd = make_vae_weights(vcfg, seed=3)
+    vsd = make_vae_weights(vcfg, seed=3, gain=0.5)  # low-gain init: tight codec bound
     wf = folded_vae_state(vsd)
     null = make_null_condition_emb(cfg).to(torch.bfloat16)
     vshape = VaeShape(encoder_hidden_size=vcfg.encoder_hidden_size, downsampling_ratios=vcfg.downsampling_ratios,
@@ -78,7 +78,7 @@ def test_repaint_matches_oracle_chain():
     want_wav = ovae.decode(wf, vcfg, out["target_latents"].cpu().float().transpose(1, 2))
     peak = want_wav.abs().amax(dim=[1, 2], keepdim=True).clamp(min=1.0)
     werr = rel_l2(wav, want_wav / peak)
-    assert werr < 1e-1, werr
+    assert werr < 2e-2, werr
     pipe.close()
 
 
@@ -325,7 +325,7 @@ def test_wrapped_selection_sites_end_to_end_on_real_engines():
         base sampler with CFG + APG -> (outputs, enc, enc_mask, ctx);
       * `tiled_decode(latents)` (handler/vae_decode.py:16-48) and `tiled_encode(audio)` (vae_encode.py:15-43).
     Checked against the oracle chain on bf16-rounded weights: condition encoder 3e-2, loop 3e-2 (started from the
-    CUDA path's own conditioning so the comparison isolates the loop), waveform 1e-1 (bounds of smoke())."""
+    CUDA path's own conditioning so the comparison isolates the loop), waveform 2e-2 on the low-gain codec init (bounds of smoke())."""
     import contextlib
     import types
 
@@ -336,7 +336,7 @@ def test_wrapped_selection_sites_end_to_end_on_real_engines():
     dcfg, ccfg, vcfg = DiTConfig.tiny(), ocond.CondConfig.tiny(), ovae.VaeConfig.tiny()
     w_dit = bf16_round_(make_dit_weights(dcfg, seed=0))
     w_cond = bf16_round_(ocond.make_cond_weights(ccfg, seed=5))
-    vsd = make_vae_weights(vcfg, seed=3)
+    vsd = make_vae_weights(vcfg, seed=3, gain=0.5)  # low-gain init: tight codec bound
     wf = folded_vae_state(vsd)
     null = make_null_condition_emb(dcfg).to(torch.bfloat16)
 
@@ -414,7 +414,7 @@ def test_wrapped_selection_sites_end_to_end_on_real_engines():
     assert wav.shape == (B, 2, T * vcfg.hop) and wav.device.type == "cuda"
     want_wav = ovae.decode(wf, vcfg, lat.cpu().float().transpose(1, 2))
     peak = want_wav.abs().amax(dim=[1, 2], keepdim=True).clamp(min=1.0)
-    assert rel_l2(wav.cpu().float(), want_wav / peak) < 1e-1
+    assert rel_l2(wav.cpu().float(), want_wav / peak) < 2e-2
     z = h.tiled_encode(wav[0].float(), offload_latent_to_cpu=True)  # 2-D input -> 2-D result, stays on the device
     assert z.shape == (64, T) and z.device.type == "cuda"
     for eng in (h.b200_dit, h.b200_cond, h.b200_vae):
