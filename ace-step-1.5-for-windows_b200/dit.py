@@ -6,7 +6,7 @@ once from the loaded PyTorch decoder's state_dict, then called per denoising ste
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
 import torch

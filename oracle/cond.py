@@ -13,7 +13,7 @@ mask, so attention takes a per-sample valid length.  Weights are a flat dict wit
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
