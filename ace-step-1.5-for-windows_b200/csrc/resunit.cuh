@@ -16,14 +16,18 @@
 // address is stepped by tap * dil rows (a K-major SWIZZLE_128B descriptor may start on any 128-byte row: the swizzle
 // follows the absolute shared-memory address, base-offset field zero; tools/desc_rowstep_probe.cu).  Seven shifted
 // [128 x 128] boxes were 224 KB per tile; the one box is 34-47 KB.  The weights (W1: 14 blocks of 16 KB, W2: 2) stream
-// through a 4-stage ring per tile: 303-335 KB per tile in all, against 480 KB before.  (Sharing the W1 stream
+// through a 4-stage ring per tile: 303-335 KB per tile in all, against 480 KB before.  What bounds the kernel is
+// epilogue 2 (tools/ru_timing.cu: ~10.5k busy cycles per tile against 4.1k of tensor work), so the shared memory goes
+// where it keeps THAT warp group fed: two residual tiles (the next one is fetched while epilogue 2 still copies the
+// previous one out) and a single xs box (the tensor pipe idles for its round trip once per tile, for free).  (Sharing the W1 stream
 // between the CTAs of a cluster by TMA multicast was measured twice — 4-CTA clusters: 18.7 vs 12.6 ms per 60 s
 // decode, 2-CTA: within 1 % — multicast saves L2 reads, not the bytes each SM has to take in; it is gone.)
 //
 // One CTA = one 128-frame tile at a time (persistent over tiles), warp-specialised:
-//   warp 0      TMA producer: the xs box of tile it+1 (double-buffered; out-of-range rows are zero-filled = the
-//               conv's padding), the 14 W1 blocks of tile it with the 2 W2 blocks of tile it-1's conv1 slotted in
-//               after block RU_MMA2_AT, and the tile's residual rows x[m0:m0+128, :] (consumed two tiles later)
+//   warp 0      TMA producer: the xs box of tile it (ONE buffer, requested behind the tile's first weight blocks once
+//               the previous tile's conv7 has retired; out-of-range rows are zero-filled = the conv's padding), the
+//               14 W1 blocks of tile it with the 2 W2 blocks of tile it-1's conv1 slotted in after block
+//               RU_MMA2_AT, and the tile's residual rows x[m0:m0+128, :] into one of TWO buffers
 //   warp 1      MMA issuer: conv7 -> D1[it & 1] (TMEM), conv1 of the PREVIOUS tile -> D2[(it-1) & 1]
 //               slotted in at K block 11 so the tensor pipe never waits for the Snake epilogue
 //   warp 2      TMEM allocator (512 columns: D1 x2, D2 x2)
@@ -48,7 +52,7 @@ constexpr int RU_THREADS = 640;  // 4 control warps + 8 (epilogue 1) + 8 (epilog
 constexpr int RU_KB = 14;       // K blocks of 64 per tile: 7 taps x 2
 constexpr int RU_MMA2_AT = 11;  // K block of tile it+1 after which conv1 of tile it is issued
 constexpr int RU_LOADX_AT = 8;  // K block of tile it+1 after which the residual rows of tile it are fetched
-constexpr int RU_LOADA_AT = 3;  // K block of tile it after which the xs box of tile it+1 is fetched
+constexpr int RU_LOADA_AT = 2;  // weight block of tile it after which the xs box of tile it is requested (see below)
 constexpr int RU_MAX_DIL = 9;
 
 struct RuSmem {
@@ -57,14 +61,17 @@ struct RuSmem {
   static constexpr int XS_ROWS = (128 + 6 * RU_MAX_DIL + 7) / 8 * 8;  // 184: rows of the largest xs box, whole atoms
   static constexpr int XS_HALF = XS_ROWS * 128;                        // one 64-channel half of the box
   static constexpr int XS_BYTES = 2 * XS_HALF;
-  static constexpr int OFF_W = 2 * XS_BYTES;                           // after the two xs boxes
+  static constexpr int OFF_W = XS_BYTES;                               // after the xs box
   static constexpr int OFF_HS = OFF_W + RU_STAGES * A_BYTES;
-  static constexpr int OFF_X = OFF_HS + TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_X + TILE_BYTES;
+  static constexpr int OFF_X = OFF_HS + TILE_BYTES;                    // two residual tiles
+  static constexpr int OFF_BAR = OFF_X + 2 * TILE_BYTES;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;  // +1024: manual alignment
 };
 static_assert(RuSmem::XS_HALF % 1024 == 0 && RuSmem::OFF_W % 1024 == 0 && RuSmem::OFF_HS % 1024 == 0, "swizzle atoms");
 static_assert(RuSmem::TOTAL <= 232448, "res_unit shared memory");
+// the MMA warp cannot consume a tile's weight blocks before its xs box has landed: the producer must get to the box
+// request without needing a ring slot back (tests/test_resunit_protocol_model.py)
+static_assert(RU_LOADA_AT < RU_STAGES, "xs box request within the ring depth");
 
 struct RuParams {
   int L;    // frames (rows)
@@ -90,8 +97,8 @@ __device__ long long g_ru_e1[8];     // epilogue 1, warp 4: wait D1F, wait HSE, 
 #endif
 
 enum RuBar {
-  RU_FULL = 0, RU_EMPTY = RU_STAGES, RU_AF = 2 * RU_STAGES, RU_AF1, RU_AE, RU_AE1, RU_D1F, RU_D1F1, RU_D1E, RU_D1E1,
-  RU_HSF, RU_HSE, RU_D2F, RU_D2F1, RU_D2E, RU_D2E1, RU_XF, RU_XE, RU_NBAR
+  RU_FULL = 0, RU_EMPTY = RU_STAGES, RU_AF = 2 * RU_STAGES, RU_AE, RU_D1F, RU_D1F1, RU_D1E, RU_D1E1,
+  RU_HSF, RU_HSE, RU_D2F, RU_D2F1, RU_D2E, RU_D2E1, RU_XF, RU_XF1, RU_XE, RU_XE1, RU_NBAR
 };
 static_assert(RU_NBAR <= 30, "barrier block");
 
@@ -122,18 +129,18 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
       mbar_init(&bar[RU_FULL + i], 1);
       mbar_init(&bar[RU_EMPTY + i], 1);
     }
+    mbar_init(&bar[RU_AF], 1);
+    mbar_init(&bar[RU_AE], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar[RU_AF + i], 1);
-      mbar_init(&bar[RU_AE + i], 1);
       mbar_init(&bar[RU_D1F + i], 1);
       mbar_init(&bar[RU_D1E + i], 8);
       mbar_init(&bar[RU_D2F + i], 1);
       mbar_init(&bar[RU_D2E + i], 8);
+      mbar_init(&bar[RU_XF + i], 1);
+      mbar_init(&bar[RU_XE + i], 8);
     }
     mbar_init(&bar[RU_HSF], 8);
     mbar_init(&bar[RU_HSE], 1);
-    mbar_init(&bar[RU_XF], 1);
-    mbar_init(&bar[RU_XE], 8);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -158,24 +165,24 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     long long ru_w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long ru_t0 = clock64();
 #endif
-    auto load_x = [&](int j) {  // residual rows of this CTA's j-th tile (single buffer)
-      RU_WAIT(2, mbar_wait(&bar[RU_XE], (uint32_t)((j & 1) ^ 1)));
+    auto load_x = [&](int j) {  // residual rows of this CTA's j-th tile (two buffers: epilogue 2 is what bounds the
+      const int buf = j & 1;    // kernel, so tile j's rows are fetched while it still works on tile j-1's)
+      RU_WAIT(2, mbar_wait(&bar[RU_XE + buf], (uint32_t)(((j >> 1) & 1) ^ 1)));
       if (elected) {
         const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * 128;
-        mbar_arrive_expect_tx(&bar[RU_XF], S::TILE_BYTES);
-        tma_load_2d(sX, &tm_x, &bar[RU_XF], 0, m0);
-        tma_load_2d(sX + S::A_BYTES, &tm_x, &bar[RU_XF], 64, m0);
+        uint8_t* dst = sX + buf * S::TILE_BYTES;
+        mbar_arrive_expect_tx(&bar[RU_XF + buf], S::TILE_BYTES);
+        tma_load_2d(dst, &tm_x, &bar[RU_XF + buf], 0, m0);
+        tma_load_2d(dst + S::A_BYTES, &tm_x, &bar[RU_XF + buf], 64, m0);
       }
     };
-    auto load_a = [&](int j) {  // xs box of this CTA's j-th tile: rows [m0 - 3 dil, m0 + 128 + 3 dil), both halves
-      const int buf = j & 1;
-      RU_WAIT(1, mbar_wait(&bar[RU_AE + buf], (uint32_t)(((j >> 1) & 1) ^ 1)));
+    auto load_a = [&](int j) {  // xs box of this CTA's j-th tile: rows [m0 - 3 dil, m0 + 128 + 3 dil), both halves;
+      RU_WAIT(1, mbar_wait(&bar[RU_AE], (uint32_t)((j & 1) ^ 1)));  // ONE box: free once tile j-1's conv7 has retired
       if (elected) {
         const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * 128;
-        uint8_t* dst = smem + buf * S::XS_BYTES;
-        mbar_arrive_expect_tx(&bar[RU_AF + buf], (uint32_t)(2 * xs_rows * 128));
-        tma_load_2d(dst, &tm_xs, &bar[RU_AF + buf], 0, m0 - 3 * p.dil);
-        tma_load_2d(dst + S::XS_HALF, &tm_xs, &bar[RU_AF + buf], 64, m0 - 3 * p.dil);
+        mbar_arrive_expect_tx(&bar[RU_AF], (uint32_t)(2 * xs_rows * 128));
+        tma_load_2d(smem, &tm_xs, &bar[RU_AF], 0, m0 - 3 * p.dil);
+        tma_load_2d(smem + S::XS_HALF, &tm_xs, &bar[RU_AF], 64, m0 - 3 * p.dil);
       }
     };
     int stage = 0;
@@ -191,13 +198,13 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
         phase ^= 1;
       }
     };
-    if (my_tiles > 0) load_a(0);
     for (int it = 0; it < my_tiles; ++it) {
       for (int kb = 0; kb < RU_KB; ++kb) {
         load_w(&tm_w1, (kb >> 1) * RU_C + (kb & 1) * 64);
-        // the next tile's xs box: its buffer was released when tile it-1's conv7 retired, i.e. before the MMA warp
-        // started on this tile, so this wait does not hold up the weight stream
-        if (kb == RU_LOADA_AT && it + 1 < my_tiles) load_a(it + 1);
+        // this tile's xs box, behind its first weight blocks (which the ring could take while the previous tile's
+        // conv7 was still running): the tensor pipe idles for the box's round trip once per tile, which is free —
+        // it is busy 4.1k of the >= 11k cycles epilogue 2 needs per tile
+        if (kb == RU_LOADA_AT) load_a(it);
         // the previous tile's residual rows are needed only after its conv1, which the MMA warp issues
         // at K block RU_MMA2_AT of this tile; by now epilogue 2 of the tile before that has long
         // released the buffer, so this wait never stalls the loads that feed the tensor core
@@ -263,10 +270,10 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       RU_WAIT(2, mbar_wait(&bar[RU_D1E + b], (uint32_t)(((it >> 1) & 1) ^ 1)));
-      RU_WAIT(1, mbar_wait(&bar[RU_AF + b], (uint32_t)((it >> 1) & 1)));
+      RU_WAIT(1, mbar_wait(&bar[RU_AF], (uint32_t)(it & 1)));
       tcgen05_fence_after();
       const uint32_t d1 = tmem_base + (uint32_t)(b * RU_C);
-      const uint32_t box_lo = xs_lo + (uint32_t)b * (S::XS_BYTES >> 4);
+      const uint32_t box_lo = xs_lo;
       for (int kb = 0; kb < RU_KB; ++kb) {
         RU_WAIT(0, mbar_wait(&bar[RU_FULL + stage], phase));
         tcgen05_fence_after();
@@ -279,7 +286,7 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
           umma_commit(&bar[RU_EMPTY + stage]);
           if (kb == RU_KB - 1) {
             umma_commit(&bar[RU_D1F + b]);
-            umma_commit(&bar[RU_AE + b]);
+            umma_commit(&bar[RU_AE]);
           }
         }
         next_stage();
@@ -351,7 +358,7 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     // LSU data pipe at 63 % and lg_throttle stalls on this kernel, 92 M store sectors for 2.9 M requests.
     const int quarter = (warp - 12) & 3, r = quarter * 32 + lane;
     const int c_lo = ((warp - 12) >> 2) * 64;  // this warp's 64 channels
-    const WarpStage slab{sX + (c_lo >> 6) * S::A_BYTES + quarter * 32 * 128};  // same XOR-by-row swizzle as TMA's
+    uint8_t* const slab0 = sX + (c_lo >> 6) * S::A_BYTES + quarter * 32 * 128;  // same XOR-by-row swizzle as TMA's
 #ifdef ACE_RU_TIMING
     const bool e2_stamp = blockIdx.x == 0 && warp == 12;
     long long ru_e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, e_prev = clock64();
@@ -360,9 +367,10 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * 128 + quarter * 32;
+      const WarpStage slab{slab0 + b * S::TILE_BYTES};
       mbar_wait(&bar[RU_D2F + b], (uint32_t)((it >> 1) & 1));
       RU_E2(0);
-      mbar_wait(&bar[RU_XF], (uint32_t)(it & 1));
+      mbar_wait(&bar[RU_XF + b], (uint32_t)((it >> 1) & 1));
       RU_E2(1);
       tcgen05_fence_after();
       __syncwarp();
@@ -411,7 +419,7 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
       slab.store_rows(lane, 64, [&](int rr) -> bf16* {
         return row0 + rr < p.L ? p.oxs + (row0 + rr) * RU_C + c_lo : nullptr;
       });
-      if (lane == 0) mbar_arrive(&bar[RU_XE]);
+      if (lane == 0) mbar_arrive(&bar[RU_XE + b]);
       RU_E2(4);
     }
 #ifdef ACE_RU_TIMING

@@ -1,7 +1,9 @@
 """Executable model of the barrier protocol of the fused codec residual unit (csrc/resunit.cuh): TMA producer warp,
 MMA issuer, epilogue 1 (D1 -> snake -> hs tile) and epilogue 2 (D2 + x -> x', snake(x')), with the shared-memory
-resources of the shipped kernel: two xs boxes, a 4-stage weight ring that carries the 14 W1 blocks of a tile AND the
-2 W2 blocks of the previous tile's conv1 (slotted in after block RU_MMA2_AT), one hs tile, one residual tile, and the
+resources of the shipped kernel: ONE xs box (fetched right after the first weight blocks of its tile, once the
+previous tile's conv7 has retired), a 4-stage weight ring that carries the 14 W1 blocks of a tile AND the 2 W2 blocks
+of the previous tile's conv1 (slotted in after block RU_MMA2_AT), one hs tile, TWO residual tiles (epilogue 2 is what
+bounds the kernel: the next tile's residual rows are fetched while it still works on the previous ones), and the
 double-buffered D1 / D2 accumulators.  Same idea as tests/test_tail_protocol_model.py: coroutines that block on
 mbarrier parity waits like the device code, a seeded random scheduler, and checks that (a) nothing deadlocks for any
 number of tiles, (b) every consumer sees the tile it expects in the buffer it reads, (c) no buffer is overwritten
@@ -12,7 +14,7 @@ import random
 
 import pytest
 
-STAGES, KB, MMA2_AT, LOADX_AT, LOADA_AT = 4, 14, 11, 8, 3
+STAGES, KB, MMA2_AT, LOADX_AT, LOADA_AT = 4, 14, 11, 8, 2
 
 
 class Barrier:
@@ -30,16 +32,18 @@ class ProtocolError(AssertionError):
     pass
 
 
-def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, max_steps=400000):
+def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, loada_at=LOADA_AT, max_steps=400000):
     full = [Barrier() for _ in range(STAGES)]
     empty = [Barrier() for _ in range(STAGES)]
-    af, ae = [Barrier(), Barrier()], [Barrier(), Barrier()]
+    af, ae = Barrier(), Barrier()
     d1f, d1e = [Barrier(), Barrier()], [Barrier(), Barrier()]
     d2f, d2e = [Barrier(), Barrier()], [Barrier(), Barrier()]
-    hsf, hse, xf, xe = Barrier(), Barrier(), Barrier(), Barrier()
+    hsf, hse = Barrier(), Barrier()
+    xf, xe = [Barrier(), Barrier()], [Barrier(), Barrier()]
     ring = [None] * STAGES            # ("w1", tile, kb) / ("w2", tile, half)
-    xs_box = [None, None]
-    hs_tile, x_tile = [None], [None]
+    xs_box = [None]
+    xs_busy = [False]
+    hs_tile, x_tile = [None], [None, None]
     d1, d2 = [None, None], [None, None]
 
     def producer():
@@ -54,22 +58,22 @@ def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, max_steps=400000):
                 st["stage"], st["phase"] = 0, st["phase"] ^ 1
 
         def load_a(j):
-            yield ("wait", ae[j & 1], ((j >> 1) & 1) ^ 1)
-            xs_box[j & 1] = j
-            af[j & 1].arrive()
+            yield ("wait", ae, (j & 1) ^ 1)
+            if xs_busy[0]:
+                raise ProtocolError(f"xs box of tile {xs_box[0]} overwritten by tile {j} while conv7 reads it")
+            xs_box[0], xs_busy[0] = j, True
+            af.arrive()
 
         def load_x(j):
-            yield ("wait", xe, (j & 1) ^ 1)
-            x_tile[0] = j
-            xf.arrive()
+            yield ("wait", xe[j & 1], ((j >> 1) & 1) ^ 1)
+            x_tile[j & 1] = j
+            xf[j & 1].arrive()
 
-        if n_tiles > 0:
-            yield from load_a(0)
         for it in range(n_tiles):
             for kb in range(KB):
                 yield from load_w(("w1", it, kb))
-                if kb == LOADA_AT and it + 1 < n_tiles:
-                    yield from load_a(it + 1)
+                if kb == loada_at:
+                    yield from load_a(it)
                 if kb == LOADX_AT and it > 0:
                     yield from load_x(it - 1)
                 if kb == MMA2_AT and it > 0:
@@ -108,15 +112,16 @@ def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, max_steps=400000):
         for it in range(n_tiles):
             b = it & 1
             yield ("wait", d1e[b], ((it >> 1) & 1) ^ 1)
-            yield ("wait", af[b], (it >> 1) & 1)
-            if xs_box[b] != it:
-                raise ProtocolError(f"conv7 of tile {it} reads the xs box of tile {xs_box[b]}")
+            yield ("wait", af, it & 1)
+            if xs_box[0] != it:
+                raise ProtocolError(f"conv7 of tile {it} reads the xs box of tile {xs_box[0]}")
             for kb in range(KB):
                 yield from take(("w1", it, kb))
                 if kb == KB - 1:
                     d1[b] = it
+                    xs_busy[0] = False
                     d1f[b].arrive()
-                    ae[b].arrive()
+                    ae.arrive()
                 if kb == mma2_at_mma and it > 0:
                     yield from mma2(it - 1)
                 yield ("step",)
@@ -139,13 +144,15 @@ def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, max_steps=400000):
         for it in range(n_tiles):
             b = it & 1
             yield ("wait", d2f[b], (it >> 1) & 1)
-            yield ("wait", xf, it & 1)
-            if d2[b] != it or x_tile[0] != it:
-                raise ProtocolError(f"epilogue 2 of tile {it}: D2 of {d2[b]}, residual rows of {x_tile[0]}")
+            yield ("wait", xf[b], (it >> 1) & 1)
+            if d2[b] != it or x_tile[b] != it:
+                raise ProtocolError(f"epilogue 2 of tile {it}: D2 of {d2[b]}, residual rows of {x_tile[b]}")
             yield ("step",)
             d2e[b].arrive()
             yield ("step",)   # the two output copies read the slab before it is handed back
-            xe.arrive()
+            if x_tile[b] != it:
+                raise ProtocolError(f"residual tile of {it} overwritten by tile {x_tile[b]} during the output copies")
+            xe[b].arrive()
 
     agents = {"producer": producer(), "mma": mma(), "epi1": epilogue1(), "epi2": epilogue2()}
     pending = {}
@@ -173,6 +180,17 @@ def test_residual_unit_protocol_survives_random_schedules():
     for n_tiles in list(range(0, 9)) + [17, 40, 153]:
         for _ in range(12 if n_tiles < 20 else 3):
             simulate(n_tiles, rng)
+
+
+def test_the_xs_box_must_be_requested_within_the_ring_depth():
+    """The one xs box of tile it is requested by the producer after weight block RU_LOADA_AT of that tile; the MMA
+    warp cannot consume any of those blocks before the box has landed, so a position at or beyond the ring depth
+    deadlocks (the kernel has a static_assert for it)."""
+    rng = random.Random(2)
+    with pytest.raises(ProtocolError):
+        simulate(3, rng, loada_at=STAGES)
+    for _ in range(10):
+        simulate(3, rng, loada_at=STAGES - 1)
 
 
 def test_ring_is_consumed_in_program_order():
