@@ -105,6 +105,7 @@ static_assert(RU_NBAR <= 30, "barrier block");
 __global__ void __launch_bounds__(RU_THREADS, 1)
 res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_w1,
                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_x,
+                const __grid_constant__ CUtensorMap tm_ox, const __grid_constant__ CUtensorMap tm_oxs,
                 const RuParams p) {
   using S = RuSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -123,6 +124,8 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     tma_prefetch_desc(&tm_w1);
     tma_prefetch_desc(&tm_w2);
     tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_ox);
+    tma_prefetch_desc(&tm_oxs);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < RU_STAGES; ++i) {
@@ -306,10 +309,17 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
     const int quarter = (warp - 4) & 3, r = quarter * 32 + lane;
     const int c_lo = ((warp - 4) >> 2) * 64;  // this warp's 64 channels
     uint8_t* rowp = sHS + r * 128;
+#ifdef ACE_RU_TIMING
+    const bool e2_stamp = blockIdx.x == 0 && warp == 4;
+    long long ru_e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, e_prev = clock64();
+    const long long e_t0 = e_prev;
+#endif
     for (int it = 0; it < my_tiles; ++it) {
       const int b = it & 1;
       mbar_wait(&bar[RU_D1F + b], (uint32_t)((it >> 1) & 1));
+      RU_E2(0);
       mbar_wait(&bar[RU_HSE], (uint32_t)((it & 1) ^ 1));  // conv1 of the previous tile has read hs
+      RU_E2(1);
       tcgen05_fence_after();
       __syncwarp();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * RU_C);
@@ -348,14 +358,21 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
         mbar_arrive(&bar[RU_D1E + b]);
         mbar_arrive(&bar[RU_HSF]);
       }
+      RU_E2(2);
     }
+#ifdef ACE_RU_TIMING
+    if (e2_stamp && lane == 0) {
+      for (int i = 0; i < 3; ++i) g_ru_e1[i] = ru_e[i];
+      g_ru_e1[3] = clock64() - e_t0;
+    }
+#endif
   } else if (warp >= 12) {
     // ---------------- epilogue 2: D2 + b2 + x -> x', snake_next(x') ----------------
     // Each warp owns a [32 rows x 64 channels] slab of the residual tile in sX (its lane quarter's rows of its
-    // channel half): it turns the slab into x' IN PLACE, copies it out with 8 lanes per row (4 rows x 128 contiguous
-    // bytes per store instruction), then overwrites it with snake_next(x') and copies that out the same way.  Storing
-    // thread-per-row straight from registers made every 16-byte store of a warp hit 32 different lines: ncu had the
-    // LSU data pipe at 63 % and lg_throttle stalls on this kernel, 92 M store sectors for 2.9 M requests.
+    // channel half): it turns the slab into x' IN PLACE, hands it to a TMA store, then overwrites it with
+    // snake_next(x') and hands that to a second one.  Storing thread-per-row straight from registers made every
+    // 16-byte store of a warp hit 32 different lines: ncu had the LSU data pipe at 63 % and lg_throttle stalls on
+    // this kernel, 92 M store sectors for 2.9 M requests.
     const int quarter = (warp - 12) & 3, r = quarter * 32 + lane;
     const int c_lo = ((warp - 12) >> 2) * 64;  // this warp's 64 channels
     uint8_t* const slab0 = sX + (c_lo >> 6) * S::A_BYTES + quarter * 32 * 128;  // same XOR-by-row swizzle as TMA's
@@ -409,16 +426,30 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[RU_D2E + b]);  // the accumulator is in registers / shared memory
       RU_E2(2);
-      slab.store_rows(lane, 64, [&](int rr) -> bf16* {
-        return row0 + rr < p.L ? p.ox + (row0 + rr) * RU_C + c_lo : nullptr;
-      });
+      // the slab ([32 rows x 64 channels], one swizzle-atom-aligned 4 KB piece of the residual tile) leaves by a TMA
+      // store of its own — tensor maps with [64 x 32] boxes; rows past L are clipped — issued by one lane of THIS
+      // warp: no cross-warp barrier, and the warp does not spend 8 + 8 load/store pairs per output on the copy
+      const int row0i = (int)row0;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_ox, slab.base, c_lo, row0i);
+        tma_store_commit();
+        tma_store_wait_read_all();  // x' has been read out of the slab
+      }
+      __syncwarp();
       RU_E2(3);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         *slab.at(lane, q) = make_uint4(xs_packed[4 * q], xs_packed[4 * q + 1], xs_packed[4 * q + 2], xs_packed[4 * q + 3]);
-      slab.store_rows(lane, 64, [&](int rr) -> bf16* {
-        return row0 + rr < p.L ? p.oxs + (row0 + rr) * RU_C + c_lo : nullptr;
-      });
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_oxs, slab.base, c_lo, row0i);
+        tma_store_commit();
+        tma_store_wait_read_all();
+      }
+      __syncwarp();
       if (lane == 0) mbar_arrive(&bar[RU_XE + b]);
       RU_E2(4);
     }
@@ -440,7 +471,7 @@ res_unit_kernel(const __grid_constant__ CUtensorMap tm_xs, const __grid_constant
 inline int launch_res_unit_fused(const bf16* xs, const bf16* x, const bf16* w1, const bf16* w2, const RuParams& p,
                                  cudaStream_t stream) {
   if (p.L <= 0) return ACE_OK;
-  CUtensorMap tm_xs, tm_w1, tm_w2, tm_x;
+  CUtensorMap tm_xs, tm_w1, tm_w2, tm_x, tm_ox, tm_oxs;
   if (p.dil < 1 || p.dil > RU_MAX_DIL) {
     set_error("res_unit: dilation %d outside [1, %d]", p.dil, RU_MAX_DIL);
     return ACE_ERR_INVALID;
@@ -449,6 +480,8 @@ inline int launch_res_unit_fused(const bf16* xs, const bf16* x, const bf16* w1, 
   ACE_PROPAGATE(encode_tmap_2d(&tm_w1, w1, 7 * RU_C, RU_C, 7 * RU_C * sizeof(bf16), 128));
   ACE_PROPAGATE(encode_tmap_2d(&tm_w2, w2, RU_C, RU_C, RU_C * sizeof(bf16), 128));
   ACE_PROPAGATE(encode_tmap_2d(&tm_x, x, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 128));
+  ACE_PROPAGATE(encode_tmap_2d(&tm_ox, p.ox, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 32));   // one warp's slab
+  ACE_PROPAGATE(encode_tmap_2d(&tm_oxs, p.oxs, RU_C, (uint64_t)p.L, RU_C * sizeof(bf16), 32));
   static bool attr_set = false;
   if (!attr_set) {
     ACE_CUDA_CHECK(cudaFuncSetAttribute(res_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RuSmem::TOTAL));
@@ -459,7 +492,7 @@ inline int launch_res_unit_fused(const bf16* xs, const bf16* x, const bf16* w1, 
   prof_tag_gemm(p.L, RU_C, 8 * RU_C);
   prof_begin(PROF_GEMM, 2.0 * p.L * RU_C * 8.0 * RU_C, 4.0 * p.L * RU_C * 2.0, stream);
   ACE_CUDA_CHECK(launch_kernel(res_unit_kernel, dim3(grid), dim3(RU_THREADS), (size_t)RuSmem::TOTAL, stream, tm_xs,
-                               tm_w1, tm_w2, tm_x, p));
+                               tm_w1, tm_w2, tm_x, tm_ox, tm_oxs, p));
   prof_end(stream);
   ACE_CUDA_CHECK(cudaGetLastError());
   return ACE_OK;

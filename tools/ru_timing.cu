@@ -32,6 +32,11 @@ int main(int argc, char** argv) {
     if (rep == 2)
       printf("   epilogue 2 (warp 12), cycles per tile: total %.0f | wait D2 %.0f | wait x tile %.0f | TMEM + math %.0f | x' out %.0f | xs' out %.0f\n",
              e2[5] / (double)w[6], e2[0] / (double)w[6], e2[1] / (double)w[6], e2[2] / (double)w[6], e2[3] / (double)w[6], e2[4] / (double)w[6]);
+    long long e1[8];
+    cudaMemcpyFromSymbol(e1, g_ru_e1, sizeof(e1));
+    if (rep == 2)
+      printf("   epilogue 1 (warp 4), cycles per tile: total %.0f | wait D1 %.0f | wait hs free %.0f | TMEM + snake + hs store %.0f\n",
+             e1[3] / (double)w[6], e1[0] / (double)w[6], e1[1] / (double)w[6], e1[2] / (double)w[6]);
     long long pw[8];
     cudaMemcpyFromSymbol(pw, g_ru_pwait, sizeof(pw));
     const double t = (double)w[6];
