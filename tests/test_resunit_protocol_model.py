@@ -149,7 +149,7 @@ def simulate(n_tiles, rng, mma2_at_mma=MMA2_AT, loada_at=LOADA_AT, max_steps=400
                 raise ProtocolError(f"epilogue 2 of tile {it}: D2 of {d2[b]}, residual rows of {x_tile[b]}")
             yield ("step",)
             d2e[b].arrive()
-            yield ("step",)   # the two output copies read the slab before it is handed back
+            yield ("step",)   # the two TMA stores read the slab (cp.async.bulk.wait_group.read) before it is handed back
             if x_tile[b] != it:
                 raise ProtocolError(f"residual tile of {it} overwritten by tile {x_tile[b]} during the output copies")
             xe[b].arrive()
